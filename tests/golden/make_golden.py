@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by RUNNING THE UNMODIFIED REFERENCE.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference (NOC-OI/ship-track-estimators) is imported from ``/root/reference/src``.  Its
+``utils.py`` imports the third-party ``geographiclib`` at module top, which is not installed
+here; a three-line stub package is put on ``sys.path`` (the stub raises if it is ever called --
+every track below is built with the reference's own ``haversine_formula`` / ``heading`` through
+the injection points ``ship_track.py:67-68``).  Nothing of the reference is copied into this
+repository; only the numerical inputs and outputs of the runs are stored.
+
+Noise: the reference draws unseeded ``np.random.normal`` noise in predict/update/rts_step
+(``unscented.py:198-202, 232-236, 320-323``).  Fixtures are generated with that function patched
+(a) to return zeros ("zero" mode) or (b) to draw unit normals from a seeded generator, record
+them and return ``unit * scale`` ("tape" mode; the recorded units are stored so the GPU path can
+replay them).
+
+Gating: ``check_robustness`` is dead code in the reference (call commented out, ``unscented.py:228``).
+For the gating fixtures a subclass re-enables that one line (and silences its ``print``).
+"""
+from __future__ import annotations
+
+import builtins
+import contextlib
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+
+# --------------------------------------------------------------------------- #
+# import the reference                                                        #
+# --------------------------------------------------------------------------- #
+_stub = tempfile.mkdtemp(prefix="geographiclib_stub_")
+os.makedirs(os.path.join(_stub, "geographiclib"))
+open(os.path.join(_stub, "geographiclib", "__init__.py"), "w").close()
+with open(os.path.join(_stub, "geographiclib", "geodesic.py"), "w") as fh:
+    fh.write(
+        "class _W:\n"
+        "    def Inverse(self, *a, **k):\n"
+        "        raise RuntimeError('geographiclib stub called')\n"
+        "class Geodesic:\n"
+        "    WGS84 = _W()\n"
+    )
+sys.path.insert(0, _stub)
+sys.path.insert(0, os.path.join(REF, "src"))
+sys.path.insert(0, REPO)
+
+from track_estimators.kalman_filters.non_linear_process import geodetic_dynamics  # noqa: E402
+from track_estimators.kalman_filters.unscented import UnscentedKalmanFilter  # noqa: E402
+from track_estimators.ship_track import ShipTrack  # noqa: E402
+from track_estimators.utils import generate_dts, haversine_formula, heading, smooth  # noqa: E402
+
+from ship_track_estimators_b200.synthetic import make_tracks  # noqa: E402
+
+warnings.simplefilter("ignore")
+
+
+class GatedUKF(UnscentedKalmanFilter):
+    """Reference UKF with the robustification line re-enabled (unscented.py:228-229)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.gate_iters = []
+        self.gate_lambda = []
+
+    def update_lambda_factor(self, *a, **k):
+        lam = super().update_lambda_factor(*a, **k)
+        self._iters += 1
+        self._lam = lam
+        return lam
+
+    def update(self, z):
+        z = z.reshape(-1, 1)
+        self._iters, self._lam = 0, 1.0
+        _print = builtins.print
+        builtins.print = lambda *a, **k: None
+        try:
+            R_scaled = self.check_robustness(z, self.P, self.R)
+        finally:
+            builtins.print = _print
+        self.gate_iters.append(self._iters)
+        self.gate_lambda.append(self._lam)
+        R_keep = self.R
+        self.R = R_scaled  # update() reads self.R at :229
+        try:
+            super().update(z)
+        finally:
+            self.R = R_keep
+
+
+@contextlib.contextmanager
+def pinned_noise(mode, seed=0):
+    """Patch ``np.random.normal``; yields the list the unit draws are recorded into."""
+    orig = np.random.normal
+    tape = []
+    rng = np.random.default_rng(seed)
+
+    def zeros(loc=0.0, scale=1.0, size=None):
+        return np.zeros(size)
+
+    def taped(loc=0.0, scale=1.0, size=None):
+        unit = rng.standard_normal(size)
+        tape.append(unit.copy())
+        return unit * scale
+
+    np.random.normal = zeros if mode == "zero" else taped
+    try:
+        yield tape
+    finally:
+        np.random.normal = orig
+
+
+def fake_track(lon, lat, dts, sog, cog, sog_rate, cog_rate):
+    """A reference ShipTrack carrying exactly the given arrays (no CSV involved)."""
+    st = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
+    st.lon, st.lat, st.dts = np.asarray(lon), np.asarray(lat), np.asarray(dts)
+    st.sog, st.cog = np.asarray(sog), np.asarray(cog)
+    st.sog_rate, st.cog_rate = np.asarray(sog_rate), np.asarray(cog_rate)
+    st.z = np.vstack((st.lon, st.lat, st.sog, st.cog))
+    return st
+
+
+def run_reference(st, H, Q, R, P, dt_array, *, smoother=True, noise="zero", seed=0, gating=False, x0=None):
+    """One track through the reference; returns inputs and outputs as a flat dict."""
+    cls = GatedUKF if gating else UnscentedKalmanFilter
+    x0 = st.z[:, 0].reshape(-1, 1).copy() if x0 is None else np.asarray(x0, dtype=float).reshape(-1, 1)
+    rec = dict(
+        x0=x0[:, 0].copy(), P0=np.array(P, dtype=float), H=np.array(H, dtype=float),
+        Q=np.array(Q, dtype=float), R=np.array(R, dtype=float),
+        dt_array=np.array(dt_array, dtype=float), dts=np.array(st.dts, dtype=float),
+        z=st.z.copy(), sog_rate=np.array(st.sog_rate, dtype=float), cog_rate=np.array(st.cog_rate, dtype=float),
+    )
+    ukf = cls(H=np.array(H, dtype=float), Q=np.array(Q, dtype=float), R=np.array(R, dtype=float),
+              P=np.array(P, dtype=float), x0=x0, non_linear_process=geodetic_dynamics)
+    upd_at = []
+    inner_update = ukf.update
+
+    def spy(z):
+        upd_at.append(len(ukf.means))  # states stored so far: s+1 inside step s, 1 for the initial one
+        return inner_update(z)
+
+    ukf.update = spy
+    with pinned_noise(noise, seed) as tape:
+        means, covs = ukf.run(len(dt_array), np.array(dt_array, dtype=float), st)
+        n_fwd = len(tape)
+        if smoother:
+            means_s, covs_s = ukf.run_rts_smoother(st)
+    N = len(dt_array)
+    mask = np.zeros(N, dtype=bool)
+    for s in upd_at[1:]:
+        mask[s - 1] = True
+    rec.update(means=means.reshape(N + 1, -1), covs=covs.reshape(N + 1, 4, 4), mask=mask)
+    if smoother:
+        rec.update(means_s=means_s.reshape(N + 1, -1), covs_s=covs_s.reshape(N + 1, 4, 4))
+    if gating:
+        rec.update(gate_iters=np.asarray(ukf.gate_iters, dtype=np.int32), gate_lambda=np.asarray(ukf.gate_lambda))
+    if noise == "tape":
+        # split the flat record by call site: update(0), then per step predict [, update]; then
+        # the smoother's draws for steps N-1 ... 0
+        fwd = tape[:n_fwd]
+        upd, pred, k = [fwd[0]], [], 1
+        for s in range(N):
+            pred.append(fwd[k]); k += 1
+            if mask[s]:
+                upd.append(fwd[k]); k += 1
+        assert k == n_fwd
+        rec.update(noise_pred=np.asarray(pred), noise_upd=np.asarray(upd))
+        if smoother:
+            bwd = np.asarray(tape[n_fwd:])  # drawn for step N-1 first
+            assert bwd.shape[0] == N
+            rec.update(noise_bwd=bwd[::-1].copy())  # stored indexed by step
+    return rec
+
+
+def pack(tracks):
+    """List of per-track dicts -> flat dict for np.savez (keys ``t{i}_{name}``)."""
+    out = {"n_tracks": np.asarray(len(tracks))}
+    for i, tr in enumerate(tracks):
+        for k, v in tr.items():
+            out[f"t{i}_{k}"] = np.asarray(v)
+    return out
+
+
+def save(name, tracks, **extra):
+    path = os.path.join(HERE, name + ".npz")
+    d = pack(tracks)
+    d.update({k: np.asarray(v) for k, v in extra.items()})
+    np.savez_compressed(path, **d)
+    print(f"{name}: {len(tracks)} tracks, {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+# default parameter sets ----------------------------------------------------- #
+CLI = dict(  # examples/cli_example/input.json:1-9
+    H=np.diag([1.0, 1.0, 0.0, 0.0]), R=np.diag([1e-3, 1e-3, 0.0, 0.0]),
+    Q=np.diag([1e-2, 1e-2, 1e-4, 1e-4]), P=np.eye(4),
+)
+EX_RTS = dict(  # examples/example_ukf_rts_smoother.py:31-40
+    H=np.diag([1.0, 1.0, 0.0, 0.0]), R=np.diag([0.25, 0.25, 0.0, 0.0]) * 0.01,
+    Q=np.diag([1e-4, 1e-4, 1e-6, 1e-6]) * 25, P=np.eye(4),
+)
+EX_BATCH = dict(  # examples/example_ukf_rts_smoother_batch.py:43-52
+    H=np.diag([1.0, 1.0, 0.0, 0.0]), R=np.diag([0.25, 0.25, 0.0, 0.0]),
+    Q=np.diag([1e-4, 1e-4, 1e-6, 1e-6]), P=np.eye(4),
+)
+
+
+def real_track(csv, ship_id, id_col, lat_col, lon_col, max_obs=None, smooth_width=None):
+    st = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
+    st.read_csv(csv_file=csv, ship_id=ship_id, id_col=id_col, lat_col=lat_col, lon_col=lon_col)
+    if max_obs is not None:
+        st.lon, st.lat, st.dts = st.lon[:max_obs], st.lat[:max_obs], st.dts[: max_obs - 1]
+    if smooth_width:
+        st.calculate_cog(); st.calculate_sog()
+        st.sog = smooth(st.sog, smooth_width); st.cog = smooth(st.cog, smooth_width)
+    st.get_measurements(include_sog=True, include_cog=True)
+    st.calculate_cog_rate(); st.calculate_sog_rate()
+    return st
+
+
+def synthetic_tracks(n, nobs, **kw):
+    syn = make_tracks(n, nobs, device="cpu", **kw)
+    out = []
+    for t in range(n):
+        m = int(syn.nobs[t])
+        out.append(fake_track(
+            syn.lon[:m, t].numpy(), syn.lat[:m, t].numpy(), syn.dts[: m - 1, t].numpy(),
+            syn.sog[:m, t].numpy(), syn.cog[:m, t].numpy(),
+            syn.sog_rate[:m, t].numpy(), syn.cog_rate[:m, t].numpy(),
+        ))
+    return out
+
+
+def main():
+    hist = os.path.join(REF, "data/historical_ships/historical_ship_data.csv")
+    modern = os.path.join(REF, "data/modern_ships/WCE5063_subset.csv")
+
+    # ---- known answers for the building blocks ---------------------------- #
+    rng = np.random.default_rng(20261018)
+    xs = np.stack([rng.uniform(-180, 180, 64), rng.uniform(-89, 89, 64), rng.uniform(0, 60, 64), rng.uniform(-90, 450, 64)], 1)
+    xs[:4] = [[-30.5, -0.5, 14.5, 198.5], [179.9, 0.0, 30.0, 90.0], [0.0, 89.5, 20.0, 0.0], [10.0, -45.0, 0.0, 270.0]]
+    dt = rng.choice([0.5, 1.0, 3.0, 12.0, 24.0], 64); dt[0] = 12.0
+    sr = rng.normal(0, 0.05, 64); cr = rng.normal(0, 0.5, 64); sr[0], cr[0] = 0.01, -0.02
+    geo = np.stack([geodetic_dynamics(xs[i], None, dt[i], sog_rate=sr[i], cog_rate=cr[i]) for i in range(64)])
+    Ps, Xs, x_sp = [], [], []
+    for i in range(32):
+        A = rng.normal(size=(4, 4)) * rng.choice([1e-2, 1.0, 10.0])
+        P = A @ A.T + np.diag(rng.uniform(1e-6, 1e-2, 4))
+        if i % 8 == 7:  # indefinite: sqrtm goes complex, the reference keeps the real part
+            w, V = np.linalg.eigh(P); w[0] = -abs(w[1]) * 0.3; P = (V * w) @ V.T; P = 0.5 * (P + P.T)
+        x = xs[i].copy()
+        u = UnscentedKalmanFilter(H=np.eye(4), P=P, x0=x)
+        u.compute_weights()
+        Xs.append(u.compute_sigma_points().copy()); Ps.append(P); x_sp.append(x)
+    u = UnscentedKalmanFilter(H=np.eye(4)); W = u.compute_weights().copy()
+    np.savez_compressed(
+        os.path.join(HERE, "kat_blocks.npz"), geo_x=xs, geo_dt=dt, geo_sog_rate=sr, geo_cog_rate=cr, geo_out=geo,
+        sp_x=np.asarray(x_sp), sp_P=np.asarray(Ps), sp_X=np.asarray(Xs), weights=W,
+    )
+    print("kat_blocks done")
+
+    # ---- C1: the two single-ship configs ---------------------------------- #
+    st = real_track(hist, "01203823", "primary.id", "lat", "lon")
+    c1a = run_reference(st, dt_array=generate_dts(st.dts, 2), **CLI)
+    st = real_track(hist, "01204106", "id", "lat", "lon2")
+    c1b = run_reference(st, dt_array=generate_dts(st.dts, 4), **EX_RTS)
+    save("c1_single_ship", [c1a, c1b])
+
+    # ---- C2: the batch example (historical) + a modern ship ---------------- #
+    import pandas as pd
+    ids = pd.read_csv(hist)["primary.id"].unique().tolist()
+    ids.pop(1)  # examples/example_ukf_rts_smoother_batch.py:17
+    tracks, names, skipped = [], [], 0
+    for sid in ids:
+        try:
+            st = real_track(hist, sid, "primary.id", "lat", "lon2")
+            dta = generate_dts(st.dts, 2)
+            if dta.max() > 48:  # :70-72
+                skipped += 1
+                continue
+            r = run_reference(st, dt_array=dta, **EX_BATCH)
+            if not (np.all(np.isfinite(r["means_s"])) and np.all(np.isfinite(r["covs_s"]))):
+                continue
+        except Exception:
+            continue
+        if len(tracks) >= 12:  # full covariances for a dozen ships keep the fixture small
+            r = {k: v for k, v in r.items()}
+            r["covs_diag"] = np.diagonal(r.pop("covs"), axis1=1, axis2=2).copy()
+            r["covs_s_diag"] = np.diagonal(r.pop("covs_s"), axis1=1, axis2=2).copy()
+        tracks.append(r); names.append(str(sid))
+    print("historical: ran", len(tracks), "skipped dt>48:", skipped)
+    save("c2_historical_batch", tracks, ids=np.asarray(names))
+    st = real_track(modern, "WCE5063", "id", "lat", "lon", max_obs=400)
+    save("c2_modern_ship", [run_reference(st, dt_array=generate_dts(st.dts, 2), **CLI)])
+
+    # ---- C3 / C5 shape: constant dt = 1 h, k = 1 --------------------------- #
+    sts = synthetic_tracks(6, 97, seed=3)
+    save("c3_const_dt", [run_reference(s, dt_array=generate_dts(s.dts, 1), **CLI) for s in sts])
+
+    # ---- C4 shape: ragged, mixed dts, k = 2, box smoothing 2, outliers, gating ---- #
+    sts = synthetic_tracks(6, 90, seed=4, nobs_min=40, dts_choices=(1, 2, 3, 6, 12, 24), outlier_frac=0.03, smooth_width=2)
+    GATE = dict(CLI); GATE["R"] = np.diag([0.05, 0.05, 0.0, 0.0])
+    save("c4_ragged_gated", [run_reference(s, dt_array=generate_dts(s.dts, 2), gating=True, **GATE) for s in sts])
+    save("c4_ragged_ungated", [run_reference(s, dt_array=generate_dts(s.dts, 2), **CLI) for s in sts[:3]])
+
+    # ---- noise tape --------------------------------------------------------- #
+    sts = synthetic_tracks(4, 40, seed=5, dts_choices=(1, 2, 6))
+    save("tape_noise", [run_reference(s, dt_array=generate_dts(s.dts, 2), noise="tape", seed=100 + i, **CLI) for i, s in enumerate(sts)])
+
+    # ---- dense H / R, sub-step counts that miss observation times ------------ #
+    sts = synthetic_tracks(4, 30, seed=6, dts_choices=(1, 2, 3))
+    DENSE = dict(H=np.eye(4), R=np.diag([1e-3, 1e-3, 4.0, 25.0]), Q=np.diag([1e-2, 1e-2, 1e-4, 1e-4]), P=np.eye(4) * 2.0)
+    MIX = dict(DENSE)
+    MIX["H"] = np.array([[1, 0, 0, 0], [0.2, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+    MIX["R"] = np.array([[2e-3, 5e-4, 0, 0], [5e-4, 1e-3, 0, 0], [0, 0, 4.0, 0.5], [0, 0, 0.5, 25.0]])
+    save("dense_h", [run_reference(sts[0], dt_array=generate_dts(sts[0].dts, 2), **DENSE),
+                     run_reference(sts[1], dt_array=generate_dts(sts[1].dts, 3), **MIX),
+                     # k = 7 misses some observation times (exact fp equality, kalman_filter.py:101)
+                     run_reference(sts[2], dt_array=generate_dts(sts[2].dts, 7), smoother=False, **CLI),
+                     # scalar dt: pure prediction between the observation times it happens to hit
+                     run_reference(sts[3], dt_array=np.ones(40) * 0.5, smoother=False, **CLI)])
+
+    # ---- robustification known answers ------------------ #
+    rows = []
+    for d in (0.5, 3.0, 6.0, 20.0, 100.0):
+        g = GatedUKF(H=np.diag([1.0, 1, 0, 0]), R=np.diag([0.25, 0.25, 0, 0]), P=np.diag([0.3, 0.3, 1, 1]),
+                     x0=np.array([10.0, 20, 12, 90]))
+        z = np.array([10.0 + d, 20.0 - d, 12, 90]).reshape(-1, 1)
+        g._iters, g._lam = 0, 1.0
+        _print = builtins.print; builtins.print = lambda *a, **k: None
+        with pinned_noise("zero"):
+            Rs = g.check_robustness(z, g.P, g.R)
+        builtins.print = _print
+        rows.append([d, g._iters, g._lam, Rs[0, 0] / 0.25])
+    np.savez_compressed(os.path.join(HERE, "kat_gating.npz"), rows=np.asarray(rows))
+    print(np.asarray(rows))
+
+
+if __name__ == "__main__":
+    main()
