@@ -1,0 +1,159 @@
+/*
+ * ste_ukf.h - C ABI of the B200-native batched UKF + URTSS library (libste_ukf.so).
+ *
+ * The reference (NOC-OI/ship-track-estimators) is pure Python and has no FFI layer; the
+ * "operator interface" this ABI sits behind is the Python class API of
+ *   src/track_estimators/kalman_filters/unscented.py   (UnscentedKalmanFilter)
+ *   src/track_estimators/kalman_filters/kalman_filter.py (KalmanFilterBase.run / run_rts_smoother)
+ *   src/track_estimators/kalman_filters/non_linear_process.py (geodetic_dynamics)
+ * Each entry point names the reference function(s) it replaces.  A maintainer binds it with
+ * ctypes; the shipped binding is ship_track_estimators_b200/_native.py.
+ *
+ * Conventions
+ *  - n = 4 state [lon deg, lat deg, SOG km/h, COG deg]; time in hours; all arithmetic fp64.
+ *  - Every array is structure-of-arrays with the TRACK index fastest: element (plane, t) lives at
+ *    base[plane * ld + t], ld >= n_tracks ("leading dimension", lets a launch address a
+ *    sub-range of a larger allocation).  Matrices are row-major planes: P[i][j] is plane i*4+j.
+ *  - Pointers are DEVICE pointers unless stated; the caller (torch) owns every buffer.  The
+ *    library allocates nothing persistent and never frees caller memory.
+ *  - Calls are asynchronous on the given CUDA stream (a cudaStream_t passed as void*; NULL =
+ *    legacy default stream) and never synchronise.  Stateless and re-entrant.
+ *  - Return value: 0 = launched; negative = STE_ERR_* (nothing launched).  Per-track numerical
+ *    events go to the status[] output, never to the return code.  ste_last_error() returns a
+ *    thread-local message for the last non-zero return.
+ *  - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef STE_UKF_H
+#define STE_UKF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STE_ABI_VERSION 1
+#define STE_DIM 4
+#define STE_NSIGMA 9
+
+/* return codes */
+#define STE_OK 0
+#define STE_ERR_INVALID_ARG (-1)
+#define STE_ERR_CUDA (-2)
+#define STE_ERR_UNSUPPORTED (-3)
+
+/* SteProblem.flags */
+#define STE_FLAG_GATING 0x1u      /* Mahalanobis robustification before every update            */
+#define STE_FLAG_FORCE_GENERIC 0x2u /* never take the position-only (H = diag(1,1,0,0)) fast path */
+
+/* per-track status bits (SteOutputs.status) */
+#define STE_STATUS_NONFINITE 0x1     /* a state or covariance entry became NaN/Inf                  */
+#define STE_STATUS_INDEFINITE 0x2    /* a covariance had a negative eigenvalue at a square root;    */
+                                     /* the reference keeps Re(sqrtm) = root of the clamped spectrum */
+#define STE_STATUS_GATE_CAP 0x4      /* robustification hit gate_max_iter                           */
+#define STE_STATUS_OBS_OVERRUN 0x8   /* more update times matched than observations exist           */
+                                     /* (the reference raises IndexError; the host binding does too) */
+#define STE_STATUS_RANK_DEFICIENT 0x10 /* a pseudo-inverse dropped a non-structural singular value  */
+
+/*
+ * Problem description shared by all tracks of a launch ("tile").
+ * H, Q, R, P0: reference UnscentedKalmanFilter.__init__ (unscented.py:20-74).  Q, R, P0 must be
+ * symmetric.
+ */
+typedef struct SteProblem {
+    int32_t n_tracks;      /* T                                                             */
+    int32_t max_steps;     /* N_max: filter steps of the longest track (states = N_max + 1) */
+    int32_t max_obs;       /* rows available in the observation arrays                      */
+    int32_t substeps;      /* k >= 1: used when upd_mask == NULL: step s assimilates an     */
+                           /* observation iff (s + 1) % k == 0                              */
+    int32_t rate_repeat;   /* backward pass reads rate[step / rate_repeat] when the         */
+                           /* per-track array is NULL (unscented.py:287-292)                */
+    uint32_t flags;        /* STE_FLAG_*                                                    */
+    int32_t gate_max_iter; /* cap on robustification iterations (reference: unbounded)      */
+    int32_t reserved;
+    int64_t ld;            /* leading dimension of every SoA array (>= n_tracks)            */
+    double gate_chi;       /* chi_alpha, reference value 50 (unscented.py:357)              */
+    double H[16];
+    double Q[16];
+    double R[16];
+    double P0[16];
+} SteProblem;
+
+/* Inputs of the forward and backward passes (reference: the ShipTrack attributes read at
+ * kalman_filter.py:73-108 and unscented.py:287-311, plus the dt array of run()). */
+typedef struct SteInputs {
+    const double *x0;        /* [4][ld] initial state (reference: x0 = z[:, 0])                   */
+    const double *P0;        /* [16][ld] per-track prior covariance, or NULL -> SteProblem.P0    */
+    const double *dt;        /* [max_steps][ld] step lengths (hours)                              */
+    const uint8_t *upd_mask; /* [max_steps][ld] 1 = step ends exactly on an observation time      */
+                             /* (kalman_filter.py:101), or NULL -> SteProblem.substeps cadence   */
+    const int32_t *n_steps;  /* [T] steps per track, or NULL -> max_steps for all                */
+    const double *z[4];      /* [max_obs][ld] observation rows lon, lat, sog, cog.  A row may be */
+                             /* NULL when neither H nor R reference it (it is then read as 0)   */
+    const double *sog_rate;  /* [max_obs][ld]                                                     */
+    const double *cog_rate;  /* [max_obs][ld]                                                     */
+    const int32_t *rate_repeat; /* [T] backward-pass rate repeat per track, or NULL             */
+    /* optional noise tapes of UNIT normals (NULL = zero noise), scaled on the device by        */
+    /* sqrt(diag Q) / sqrt(diag R) as np.random.normal(scale=...) does                           */
+    const double *noise_pred; /* [max_steps][4][ld]  unscented.py:198-202                        */
+    const double *noise_upd;  /* [max_obs][4][ld]    unscented.py:232-236, row = update index    */
+    const double *noise_bwd;  /* [max_steps][4][ld]  unscented.py:320-323, row = backward step   */
+} SteInputs;
+
+typedef struct SteOutputs {
+    double *mean_f;      /* [max_steps+1][4][ld]  filtered means; row 0 = prior (kalman_filter.py:76) */
+    double *cov_f;       /* [max_steps+1][16][ld] filtered covariances                                */
+    double *mean_s;      /* smoothed, same shapes (may alias mean_f / cov_f for in-place smoothing)  */
+    double *cov_s;
+    int32_t *status;     /* [T] OR-ed STE_STATUS_* (the forward pass overwrites, the backward ORs)    */
+    int32_t *n_updates;  /* [T] observations assimilated incl. the initial one, or NULL               */
+    uint8_t *gate_iters; /* [max_obs][ld] robustification iterations per update, or NULL              */
+    double *gate_lambda; /* [max_obs][ld] final lambda factor per update, or NULL                     */
+    double *gate_scale;  /* [max_obs][ld] accumulated scale of R (product of lambdas), or NULL        */
+} SteOutputs;
+
+/* library / device -------------------------------------------------------------------------- */
+int ste_version(void);
+const char *ste_last_error(void);
+
+/* KalmanFilterBase.run (kalman_filter.py:36-117) with UnscentedKalmanFilter.predict / update
+ * (unscented.py:144-265) [+ check_robustness :353-511 when STE_FLAG_GATING] for T tracks. */
+int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream);
+
+/* UnscentedKalmanFilter.rts_step (unscented.py:267-351) for T tracks; reads mean_f/cov_f
+ * written by the forward pass, writes mean_s/cov_s. */
+int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream);
+
+/* One UnscentedKalmanFilter.predict (unscented.py:144-207) for T independent filters, in place.
+ * x [4][ld], P [16][ld], dt/sog_rate/cog_rate [T]; noise [4][ld] unit normals or NULL;
+ * sigma_prior / sigma_post [36][ld] (plane = row*9 + point) or NULL; status [T] or NULL. */
+int ste_ukf_predict_f64(const SteProblem *prob, double *x, double *P, const double *dt,
+                        const double *sog_rate, const double *cog_rate, const double *noise,
+                        double *sigma_prior, double *sigma_post, int32_t *status, void *stream);
+
+/* One UnscentedKalmanFilter.update (unscented.py:209-265) for T filters, in place.
+ * z [4][ld]; noise [4][ld] or NULL; gate_iters / gate_lambda / gate_scale [T] or NULL
+ * (check_robustness, unscented.py:353-387: R_scaled = R * gate_scale). */
+int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const double *z,
+                       const double *noise, uint8_t *gate_iters, double *gate_lambda,
+                       double *gate_scale, int32_t *status, void *stream);
+
+/* UnscentedKalmanFilter.compute_sigma_points (unscented.py:76-107), any n <= 8:
+ * X[:, 0] = x, X[:, 1+i] = x + M[:, i], X[:, 1+n+i] = x - M[:, i], M = Re sqrtm(scale * P).
+ * x [n][ld], P [n*n][ld], X [n*(2n+1)][ld] (plane = row*(2n+1) + point). */
+int ste_sigma_points_f64(int32_t n, int32_t n_tracks, int64_t ld, double scale, const double *x,
+                         const double *P, double *X, int32_t *status, void *stream);
+
+/* geodetic_dynamics (non_linear_process.py:6-85) for T states: x_in/x_out [4][ld]. */
+int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const double *dt,
+                     const double *sog_rate, const double *cog_rate, double *x_out, void *stream);
+
+/* Measurement helper for the roofline report: runs `iters` dependent-free DFMA rounds on every
+ * thread of `blocks` x `threads` and writes one double per thread to sink (device, blocks*threads).
+ * FLOPs issued = 2 * 8 * iters * blocks * threads. */
+int ste_probe_fp64_fma(int32_t blocks, int32_t threads, int32_t iters, double *sink, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STE_UKF_H */

@@ -1,0 +1,379 @@
+"""Batched UKF + URTSS over many independent tracks: the B200-native entry point.
+
+The reference has no batched API ("batch" there is a Python loop over ships,
+``examples/example_ukf_rts_smoother_batch.py:19``); this module is what that loop becomes.  A
+:class:`TrackBatch` is the structure-of-arrays tile the kernels read (track index fastest),
+:class:`BatchedUKF` launches the forward filter and the backward smoother through the C ABI and
+:class:`TrackResults` carries the per-step states back.  The single-track
+``UnscentedKalmanFilter`` class of the reference API is a batch of one on top of this.
+
+Host-side decisions that must match the reference exactly are taken here, once per track, with
+the reference's own arithmetic (numpy fp64):
+  * which steps assimilate an observation: ``self.time += dt`` against ``np.cumsum(dts)`` by exact
+    float equality (reference ``kalman_filter.py:73, 98, 101``) -> ``upd_mask``;
+  * the smoother's rate expansion ``np.repeat(rate, int(nstates / len(dts)))`` (reference
+    ``unscented.py:287-292``) -> ``rate_repeat``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+def _as44(name: str, M) -> np.ndarray:
+    M = np.asarray(M, dtype=np.float64)
+    if M.shape != (4, 4):
+        raise NotImplementedError(
+            f"{name} has shape {M.shape}: the CUDA UKF path is built for the n = 4 state "
+            "[lon, lat, SOG, COG] (the reference's update/rts_step hard-code state index 3 as heading)"
+        )
+    return np.ascontiguousarray(M)
+
+
+@dataclass
+class FilterModel:
+    """H, Q, R, P0 of ``UnscentedKalmanFilter.__init__`` (reference ``unscented.py:20-74``) plus the
+    robustification switch (reference ``unscented.py:353-387``, disabled there)."""
+
+    H: np.ndarray
+    Q: np.ndarray
+    R: np.ndarray
+    P0: np.ndarray
+    gating: bool = False
+    gate_chi: float = 50.0
+    gate_max_iter: int = 100
+    force_generic: bool = False
+
+    def __post_init__(self):
+        self.H = _as44("H", self.H)
+        self.Q = _as44("Q", self.Q)
+        self.R = _as44("R", self.R)
+        self.P0 = _as44("P", self.P0)
+        for name in ("Q", "R", "P0"):
+            M = getattr(self, name)
+            if not np.array_equal(M, M.T):
+                raise NotImplementedError(f"{name} must be symmetric for the CUDA path")
+
+    def rows_needed(self) -> List[bool]:
+        """Observation rows the update can actually read (a row multiplying only exact zeros of
+        pinv(H P H^T + R) may be absent)."""
+        pos = (not self.force_generic) and np.array_equal(self.H, np.diag([1.0, 1.0, 0.0, 0.0])) and not (
+            np.any(self.R[2:, :]) or np.any(self.R[:, 2:])
+        )
+        if pos:
+            return [True, True, False, False]
+        return [bool(self.gating or np.any(self.H[r]) or np.any(self.R[r])) for r in range(4)]
+
+
+def exact_update_mask(dt_array: np.ndarray, dts: np.ndarray, time0: float = 0.0) -> np.ndarray:
+    """Steps whose accumulated time equals an observation time exactly.
+
+    ``self.time += dt`` (reference ``kalman_filter.py:98``) and ``np.cumsum`` (``:73``) are both
+    sequential fp64 sums; ``in`` (``:101``) is float equality against any element.
+    """
+    dt_array = np.asarray(dt_array, dtype=np.float64)
+    if dt_array.size == 0:
+        return np.zeros(0, dtype=bool)
+    if time0 == 0:
+        times = np.cumsum(dt_array)
+    else:
+        times = np.cumsum(np.concatenate(([np.float64(time0)], dt_array)))[1:]
+    return np.isin(times, np.cumsum(np.asarray(dts, dtype=np.float64)))
+
+
+@dataclass
+class TrackBatch:
+    """Device-resident inputs of one tile of ``n_tracks`` tracks (all tensors ``[plane][track]``)."""
+
+    x0: torch.Tensor  # [4][T]
+    dt: torch.Tensor  # [max_steps][T]
+    sog_rate: torch.Tensor  # [max_obs][T]
+    cog_rate: torch.Tensor  # [max_obs][T]
+    z: List[Optional[torch.Tensor]]  # 4 x [max_obs][T] (rows lon, lat, sog, cog)
+    upd_mask: Optional[torch.Tensor] = None  # [max_steps][T] uint8; None -> every `substeps`-th step
+    n_steps: Optional[torch.Tensor] = None  # [T] int32; None -> max_steps for all
+    rate_repeat: Optional[torch.Tensor] = None  # [T] int32; None -> rate_repeat_all
+    substeps: int = 1
+    rate_repeat_all: int = 1
+    P0: Optional[torch.Tensor] = None  # [16][T] per-track prior covariance
+    noise_pred: Optional[torch.Tensor] = None  # [max_steps][4][T] unit normals
+    noise_upd: Optional[torch.Tensor] = None  # [max_obs][4][T]
+    noise_bwd: Optional[torch.Tensor] = None  # [max_steps][4][T]
+    n_steps_host: Optional[np.ndarray] = None  # host copy for result slicing
+
+    @property
+    def n_tracks(self) -> int:
+        return int(self.x0.shape[1])
+
+    @property
+    def max_steps(self) -> int:
+        return int(self.dt.shape[0])
+
+    @property
+    def max_obs(self) -> int:
+        return int(self.sog_rate.shape[0])
+
+    @property
+    def device(self) -> torch.device:
+        return self.x0.device
+
+    def track_steps(self) -> int:
+        """Total filter steps in the tile (the unit of the throughput metric)."""
+        if self.n_steps_host is not None:
+            return int(self.n_steps_host.sum())
+        if self.n_steps is not None:
+            return int(self.n_steps.sum().item())
+        return self.n_tracks * self.max_steps
+
+    # ------------------------------------------------------------------ #
+    @classmethod
+    def from_synthetic(cls, syn, substeps: int = 1, need_rows: Sequence[bool] = (True, True, False, False)):
+        """Tile from :func:`synthetic.make_tracks` output living on the target device.  The step grid
+        is ``generate_dts(dts, substeps)`` per track and the update cadence is every ``substeps``-th
+        step, which is what the exact-equality rule yields for ``dts / k`` re-summed ``k`` times when
+        ``k`` is a power of two (and for k = 1)."""
+        if substeps < 1 or (substeps & (substeps - 1)) != 0:
+            raise ValueError("from_synthetic supports power-of-two substeps (exact re-summation)")
+        k = int(substeps)
+        dts = syn.dts
+        if not bool((torch.round(dts * 1024.0) == dts * 1024.0).all().item()):
+            raise ValueError("from_synthetic needs dts on a 2^-10 h grid so that sub-step sums are exact; use from_tracks")
+        dt = (dts / k).repeat_interleave(k, dim=0).contiguous() if k > 1 else dts.contiguous()
+        nobs = syn.nobs
+        uniform = bool((nobs == nobs[0]).all().item())
+        n_steps = None if uniform else ((nobs - 1) * k).to(torch.int32).contiguous()
+        rows = [syn.lon, syn.lat, syn.sog, syn.cog]
+        z = [rows[r].contiguous() if need_rows[r] else None for r in range(4)]
+        rate_rep, rate_rep_all = None, k
+        nsteps_host = ((nobs - 1) * k).cpu().numpy()
+        rep_host = ((nsteps_host + 1) // np.maximum(nobs.cpu().numpy() - 1, 1)).astype(np.int32)
+        if np.all(rep_host == rep_host[0]):
+            rate_rep_all = int(rep_host[0])
+        else:
+            rate_rep = torch.from_numpy(rep_host).to(syn.lon.device)
+        return cls(
+            x0=syn.x0().contiguous(), dt=dt, sog_rate=syn.sog_rate.contiguous(), cog_rate=syn.cog_rate.contiguous(),
+            z=z, upd_mask=None, n_steps=n_steps, rate_repeat=rate_rep, substeps=k, rate_repeat_all=rate_rep_all,
+            n_steps_host=nsteps_host,
+        )
+
+    @classmethod
+    def from_tracks(
+        cls,
+        tracks: Sequence,
+        dt_arrays: Sequence[np.ndarray],
+        device="cuda",
+        x0: Optional[Sequence[np.ndarray]] = None,
+        time0: float = 0.0,
+        noise: Optional[Sequence[Optional[Dict[str, np.ndarray]]]] = None,
+        smoother: bool = True,
+    ):
+        """Pack ``ShipTrack``-like objects (attributes ``dts, z, sog_rate, cog_rate``) with their step
+        grids ``dt_arrays`` (what ``run(nsteps, dt, ship_track)`` receives).
+
+        Raises ``IndexError`` where the reference would: more matched observation times than
+        observations (``kalman_filter.py:101-108``) or a smoother rate index past the repeated rate
+        arrays (``unscented.py:287-311``).
+        """
+        T = len(tracks)
+        if T == 0:
+            raise ValueError("empty batch")
+        dt_arrays = [np.asarray(d, dtype=np.float64).reshape(-1) for d in dt_arrays]
+        nsteps = np.array([len(d) for d in dt_arrays], dtype=np.int32)
+        nobs = np.array([np.asarray(tr.z).shape[1] for tr in tracks], dtype=np.int32)
+        N, M = int(nsteps.max()), int(nobs.max())
+        dt = np.zeros((max(N, 1), T))
+        mask = np.zeros((max(N, 1), T), dtype=np.uint8)
+        z = np.zeros((4, M, T))
+        sr = np.zeros((M, T))
+        cr = np.zeros((M, T))
+        x0a = np.zeros((4, T))
+        rep = np.ones(T, dtype=np.int32)
+        for i, tr in enumerate(tracks):
+            zi = np.asarray(tr.z, dtype=np.float64)
+            if zi.shape[0] != 4:
+                raise NotImplementedError("the CUDA path needs the 4-row measurement z = [lon; lat; sog; cog]")
+            n, m = int(nsteps[i]), int(nobs[i])
+            mk = exact_update_mask(dt_arrays[i], tr.dts, time0)
+            if 1 + int(mk.sum()) > m:
+                raise IndexError(f"track {i}: {1 + int(mk.sum())} update times matched but only {m} observations")
+            dt[:n, i] = dt_arrays[i]
+            mask[:n, i] = mk
+            z[:, :m, i] = zi
+            sri, cri = np.asarray(tr.sog_rate, dtype=np.float64), np.asarray(tr.cog_rate, dtype=np.float64)
+            if len(sri) < m or len(cri) < m:
+                raise IndexError(f"track {i}: sog_rate/cog_rate shorter than the observations")
+            sr[:m, i], cr[:m, i] = sri[:m], cri[:m]
+            x0a[:, i] = zi[:, 0] if x0 is None else np.asarray(x0[i], dtype=np.float64).reshape(-1)
+            if smoother:
+                r = int((n + 1) / max(len(np.asarray(tr.dts)), 1)) if len(np.asarray(tr.dts)) else 0
+                if r < 1 or (n > 0 and (n - 1) // r >= m):
+                    raise IndexError(f"track {i}: smoother rate index out of range (repeat {r})")
+                rep[i] = r
+        dev = torch.device(device)
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+        kw = {}
+        if noise is not None:
+            npred = np.zeros((max(N, 1), 4, T))
+            nupd = np.zeros((M, 4, T))
+            nbwd = np.zeros((max(N, 1), 4, T))
+            for i, nz in enumerate(noise):
+                if nz is None:
+                    continue
+                if "pred" in nz and nz["pred"] is not None:
+                    npred[: nsteps[i], :, i] = nz["pred"]
+                if "upd" in nz and nz["upd"] is not None:
+                    nupd[: len(nz["upd"]), :, i] = nz["upd"]
+                if "bwd" in nz and nz["bwd"] is not None:
+                    nbwd[: nsteps[i], :, i] = nz["bwd"]
+            kw = dict(noise_pred=up(npred), noise_upd=up(nupd), noise_bwd=up(nbwd))
+        return cls(
+            x0=up(x0a), dt=up(dt), sog_rate=up(sr), cog_rate=up(cr), z=[up(z[r]) for r in range(4)],
+            upd_mask=up(mask), n_steps=up(nsteps), rate_repeat=up(rep), substeps=1, rate_repeat_all=1,
+            n_steps_host=nsteps.copy(), **kw,
+        )
+
+
+@dataclass
+class TrackResults:
+    """Per-step states of a tile, in the kernels' layout: ``mean [N+1][4][T]``, ``cov [N+1][16][T]``."""
+
+    mean_f: torch.Tensor
+    cov_f: torch.Tensor
+    mean_s: Optional[torch.Tensor]
+    cov_s: Optional[torch.Tensor]
+    status: torch.Tensor
+    n_updates: torch.Tensor
+    gate_iters: Optional[torch.Tensor] = None
+    gate_lambda: Optional[torch.Tensor] = None
+    gate_scale: Optional[torch.Tensor] = None
+    n_steps_host: Optional[np.ndarray] = None
+
+    def track(self, i: int) -> Dict[str, np.ndarray]:
+        """Host copies for one track in the reference's shapes: means (N+1, 4), covs (N+1, 4, 4)."""
+        n = int(self.n_steps_host[i]) if self.n_steps_host is not None else self.mean_f.shape[0] - 1
+        out = {
+            "means": self.mean_f[: n + 1, :, i].cpu().numpy(),
+            "covs": self.cov_f[: n + 1, :, i].cpu().numpy().reshape(n + 1, 4, 4),
+            "status": int(self.status[i].item()),
+            "n_updates": int(self.n_updates[i].item()),
+        }
+        if self.mean_s is not None:
+            out["means_s"] = self.mean_s[: n + 1, :, i].cpu().numpy()
+            out["covs_s"] = self.cov_s[: n + 1, :, i].cpu().numpy().reshape(n + 1, 4, 4)
+        if self.gate_iters is not None:
+            m = out["n_updates"]
+            out["gate_iters"] = self.gate_iters[:m, i].cpu().numpy().astype(np.int32)
+            out["gate_lambda"] = self.gate_lambda[:m, i].cpu().numpy()
+            out["gate_scale"] = self.gate_scale[:m, i].cpu().numpy()
+        return out
+
+
+class BatchedUKF:
+    """UKF forward filter + URTSS backward smoother over a :class:`TrackBatch` on one GPU.
+
+    Results parity contract: every track equals a fresh reference ``UnscentedKalmanFilter`` run
+    (``run`` then ``run_rts_smoother``) on the same inputs, with the reference's noise draws either
+    zero or replayed from the batch's noise tapes.
+    """
+
+    def __init__(self, H, Q=None, R=None, P=None, *, gating=False, gate_chi=50.0, gate_max_iter=100, force_generic=False):
+        if H is None:
+            raise ValueError("Set proper system dynamics.")  # reference unscented.py:52-53
+        eye = np.eye(4)
+        self.model = FilterModel(
+            H=H, Q=eye if Q is None else Q, R=eye if R is None else R, P0=eye if P is None else P,
+            gating=gating, gate_chi=gate_chi, gate_max_iter=gate_max_iter, force_generic=force_generic,
+        )
+        self._lib = nat.load()
+
+    # ------------------------------------------------------------------ #
+    def _problem(self, b: TrackBatch) -> nat.SteProblem:
+        m = self.model
+        p = nat.SteProblem()
+        p.n_tracks, p.max_steps, p.max_obs = b.n_tracks, b.max_steps, b.max_obs
+        p.substeps, p.rate_repeat = int(b.substeps), int(b.rate_repeat_all)
+        p.flags = (nat.STE_FLAG_GATING if m.gating else 0) | (nat.STE_FLAG_FORCE_GENERIC if m.force_generic else 0)
+        p.gate_max_iter, p.gate_chi = int(m.gate_max_iter), float(m.gate_chi)
+        p.ld = b.n_tracks
+        for name, M in (("H", m.H), ("Q", m.Q), ("R", m.R), ("P0", m.P0)):
+            getattr(p, name)[:] = M.reshape(-1).tolist()
+        return p
+
+    @staticmethod
+    def _inputs(b: TrackBatch) -> nat.SteInputs:
+        i = nat.SteInputs()
+        i.x0, i.P0, i.dt = nat.ptr(b.x0), nat.ptr(b.P0), nat.ptr(b.dt)
+        i.upd_mask, i.n_steps = nat.ptr(b.upd_mask), nat.ptr(b.n_steps)
+        for r in range(4):
+            i.z[r] = nat.ptr(b.z[r])
+        i.sog_rate, i.cog_rate, i.rate_repeat = nat.ptr(b.sog_rate), nat.ptr(b.cog_rate), nat.ptr(b.rate_repeat)
+        i.noise_pred, i.noise_upd, i.noise_bwd = nat.ptr(b.noise_pred), nat.ptr(b.noise_upd), nat.ptr(b.noise_bwd)
+        return i
+
+    def allocate(self, b: TrackBatch, smoother: bool = True, in_place: bool = False) -> TrackResults:
+        """Output buffers for a tile (caller-owned, reusable across tiles of the same shape)."""
+        dev, T, S = b.device, b.n_tracks, b.max_steps + 1
+        f64 = dict(dtype=torch.float64, device=dev)
+        mean_f = torch.empty(S, 4, T, **f64)
+        cov_f = torch.empty(S, 16, T, **f64)
+        mean_s = cov_s = None
+        if smoother:
+            mean_s, cov_s = (mean_f, cov_f) if in_place else (torch.empty(S, 4, T, **f64), torch.empty(S, 16, T, **f64))
+        res = TrackResults(
+            mean_f=mean_f, cov_f=cov_f, mean_s=mean_s, cov_s=cov_s,
+            status=torch.zeros(T, dtype=torch.int32, device=dev), n_updates=torch.zeros(T, dtype=torch.int32, device=dev),
+            n_steps_host=b.n_steps_host,
+        )
+        if self.model.gating:
+            res.gate_iters = torch.zeros(b.max_obs, T, dtype=torch.uint8, device=dev)
+            res.gate_lambda = torch.ones(b.max_obs, T, **f64)
+            res.gate_scale = torch.ones(b.max_obs, T, **f64)
+        return res
+
+    def _outputs(self, r: TrackResults) -> nat.SteOutputs:
+        o = nat.SteOutputs()
+        o.mean_f, o.cov_f = nat.ptr(r.mean_f), nat.ptr(r.cov_f)
+        o.mean_s, o.cov_s = nat.ptr(r.mean_s), nat.ptr(r.cov_s)
+        o.status, o.n_updates = nat.ptr(r.status), nat.ptr(r.n_updates)
+        o.gate_iters, o.gate_lambda = nat.ptr(r.gate_iters), nat.ptr(r.gate_lambda)
+        o.gate_scale = nat.ptr(r.gate_scale)
+        return o
+
+    def _check_rows(self, b: TrackBatch):
+        for r, need in enumerate(self.model.rows_needed()):
+            if need and b.z[r] is None:
+                raise ValueError(f"observation row {r} is referenced by H/R but absent from the batch")
+
+    def forward(self, b: TrackBatch, res: TrackResults) -> None:
+        """Launch the forward filter (asynchronous on the current stream)."""
+        self._check_rows(b)
+        if self.model.gating and b.noise_upd is not None:
+            raise NotImplementedError("gating with measurement noise tapes (data-dependent draw count)")
+        p, i, o = self._problem(b), self._inputs(b), self._outputs(res)
+        with torch.cuda.device(b.device):
+            nat.check(self._lib.ste_ukf_forward_f64(C.byref(p), C.byref(i), C.byref(o), nat.current_stream()))
+
+    def backward(self, b: TrackBatch, res: TrackResults) -> None:
+        """Launch the URTSS backward pass over the filtered states in ``res``."""
+        if res.mean_s is None:
+            raise ValueError("results were allocated without smoother buffers")
+        p, i, o = self._problem(b), self._inputs(b), self._outputs(res)
+        with torch.cuda.device(b.device):
+            nat.check(self._lib.ste_urtss_backward_f64(C.byref(p), C.byref(i), C.byref(o), nat.current_stream()))
+
+    def run(self, b: TrackBatch, smoother: bool = True, res: Optional[TrackResults] = None, in_place: bool = False) -> TrackResults:
+        res = res if res is not None else self.allocate(b, smoother=smoother, in_place=in_place)
+        self.forward(b, res)
+        if smoother:
+            self.backward(b, res)
+        return res

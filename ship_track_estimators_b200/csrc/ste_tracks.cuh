@@ -1,0 +1,195 @@
+// ste_tracks.cuh - the per-track time loops (forward filter, backward smoother).
+//
+// One call = one track, sequential in time.  The CUDA kernels in ste_ukf.cu call these with
+// t = global thread index; the developer-side host sandbox (tools/host_emul) calls the very same
+// code in a CPU loop to check numerical changes before GPU time is spent.
+#pragma once
+#include "ste_filter.cuh"
+
+namespace ste {
+
+#if defined(__CUDA_ARCH__)
+#define STE_STORE_STREAM(p, v) __stcs((p), (v))
+#define STE_LOAD_STREAM(p) __ldcs(p)
+#else
+#define STE_STORE_STREAM(p, v) (*(p) = (v))
+#define STE_LOAD_STREAM(p) (*(p))
+#endif
+
+template <typename T>
+STE_DEV T min_(T a, T b) { return a < b ? a : b; }
+
+struct KernelArgs {
+    SteProblem prob;
+    SteInputs in;
+    SteOutputs out;
+};
+
+STE_DEV void store_state(double *mean, double *cov, int64_t ld, int64_t s, int t,
+                                            const double (&x)[4], const double (&P)[10]) {
+    double *m = mean + (s * 4) * ld + t;
+    double *c = cov + (s * 16) * ld + t;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) STE_STORE_STREAM(m + r * ld, x[r]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) STE_STORE_STREAM(c + (i * 4 + j) * ld, P[SYM(i, j)]);
+}
+
+STE_DEV void load_state(const double *mean, const double *cov, int64_t ld, int64_t s, int t,
+                                           double (&x)[4], double (&P)[10]) {
+    const double *m = mean + (s * 4) * ld + t;
+    const double *c = cov + (s * 16) * ld + t;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = STE_LOAD_STREAM(m + r * ld);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) P[SYM(i, j)] = STE_LOAD_STREAM(c + (i * 4 + j) * ld);
+}
+
+STE_DEV bool any_nonfinite(const double (&x)[4], const double (&P)[10]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc += x[r] * 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc += P[k] * 0.0;
+    return !(acc == 0.0);
+}
+
+// ------------------------------------------------------------------------------------------ //
+// Forward filter: KalmanFilterBase.run (kalman_filter.py:36-117).
+// ------------------------------------------------------------------------------------------ //
+template <bool POS_ONLY, bool GATING>
+STE_DEV void forward_track(const KernelArgs &a, const int t) {
+    const int64_t ld = a.prob.ld;
+    const int nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
+    const Model model{a.prob.H, a.prob.Q, a.prob.R};
+    const int k_sub = a.prob.substeps > 0 ? a.prob.substeps : 1;
+
+    double x[4], P[10];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = a.in.x0[r * ld + t];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j)
+            P[SYM(i, j)] = a.in.P0 ? a.in.P0[(i * 4 + j) * ld + t] : a.prob.P0[i * 4 + j];
+    int status = 0;
+    store_state(a.out.mean_f, a.out.cov_f, ld, 0, t, x, P);  // the prior (kalman_filter.py:76-77)
+
+    auto assimilate = [&](int ui) {
+        double z[4], un[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) z[r] = a.in.z[r] ? a.in.z[r][(int64_t)ui * ld + t] : 0.0;
+        const double *noise = nullptr;
+        if (a.in.noise_upd) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) un[r] = a.in.noise_upd[((int64_t)ui * 4 + r) * ld + t];
+            noise = un;
+        }
+        int it;
+        double lam, rs;
+        if (POS_ONLY)
+            ukf_update_position<GATING>(x, P, model, z, noise, a.prob.gate_chi, a.prob.gate_max_iter, status, it, lam, rs);
+        else
+            ukf_update_generic<GATING>(x, P, model, z, noise, a.prob.gate_chi, a.prob.gate_max_iter, status, it, lam, rs);
+        if (GATING) {
+            if (a.out.gate_iters) a.out.gate_iters[(int64_t)ui * ld + t] = (uint8_t)min_(it, 255);
+            if (a.out.gate_lambda) a.out.gate_lambda[(int64_t)ui * ld + t] = lam;
+            if (a.out.gate_scale) a.out.gate_scale[(int64_t)ui * ld + t] = rs;
+        }
+    };
+
+    int ui = 0;
+    assimilate(0);  // kalman_filter.py:81
+
+    // inputs of step 0
+    double dt = 0.0, sr = 0.0, cr = 0.0;
+    bool upd = false;
+    if (nt > 0) {
+        dt = a.in.dt[t];
+        sr = a.in.sog_rate[t];
+        cr = a.in.cog_rate[t];
+        upd = a.in.upd_mask ? (a.in.upd_mask[t] != 0) : (1 % k_sub == 0);
+    }
+    for (int s = 0; s < nt; ++s) {
+        double e[4] = {0.0, 0.0, 0.0, 0.0};
+        if (a.in.noise_pred) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
+        }
+        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, nullptr, nullptr, ld);
+        const bool do_upd = upd;
+        if (do_upd) {
+            if (ui + 1 < a.prob.max_obs) {
+                ++ui;
+            } else {
+                status |= STE_STATUS_OBS_OVERRUN;
+            }
+        }
+        // prefetch the next step's inputs before the (long) update / store
+        if (s + 1 < nt) {
+            const int64_t o = (int64_t)(s + 1) * ld + t;
+            dt = a.in.dt[o];
+            upd = a.in.upd_mask ? (a.in.upd_mask[o] != 0) : ((s + 2) % k_sub == 0);
+            sr = a.in.sog_rate[(int64_t)ui * ld + t];
+            cr = a.in.cog_rate[(int64_t)ui * ld + t];
+        }
+        if (do_upd) assimilate(ui);
+        store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, x, P);
+    }
+    if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
+    a.out.status[t] = status;
+    if (a.out.n_updates) a.out.n_updates[t] = ui + 1;
+}
+
+// ------------------------------------------------------------------------------------------ //
+// Backward smoother: UnscentedKalmanFilter.rts_step (unscented.py:267-351).
+// ------------------------------------------------------------------------------------------ //
+STE_DEV void backward_track(const KernelArgs &a, const int t) {
+    const int64_t ld = a.prob.ld;
+    const int nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
+    int rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
+    rep = rep > 0 ? rep : 1;
+    int status = 0;
+
+    double xs[4], Ps[10];
+    load_state(a.out.mean_f, a.out.cov_f, ld, nt, t, xs, Ps);
+    if (a.out.mean_s != a.out.mean_f || a.out.cov_s != a.out.cov_f)
+        store_state(a.out.mean_s, a.out.cov_s, ld, nt, t, xs, Ps);  // last state is untouched (:297)
+
+    double xf[4], Pf[10], dt = 0.0, sr = 0.0, cr = 0.0;
+    auto fetch = [&](int step) {
+        load_state(a.out.mean_f, a.out.cov_f, ld, step, t, xf, Pf);
+        dt = a.in.dt[(int64_t)step * ld + t];
+        const int ri = min_(step / rep, a.prob.max_obs - 1);
+        sr = a.in.sog_rate[(int64_t)ri * ld + t];
+        cr = a.in.cog_rate[(int64_t)ri * ld + t];
+    };
+    if (nt > 0) fetch(nt - 1);
+    for (int step = nt - 1; step >= 0; --step) {
+        double xc[4], Pc[10];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xc[r] = xf[r];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) Pc[k] = Pf[k];
+        const double dtc = dt, src = sr, crc = cr;
+        double e[4] = {0.0, 0.0, 0.0, 0.0};
+        if (a.in.noise_bwd) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                e[r] = a.in.noise_bwd[((int64_t)step * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
+        }
+        if (step > 0) fetch(step - 1);  // prefetch while this step computes
+        urtss_step(xc, Pc, xs, Ps, a.prob.Q, dtc, src, crc, e, status);
+        store_state(a.out.mean_s, a.out.cov_s, ld, step, t, xs, Ps);
+    }
+    if (any_nonfinite(xs, Ps)) status |= STE_STATUS_NONFINITE;
+    a.out.status[t] |= status;
+}
+
+
+}  // namespace ste

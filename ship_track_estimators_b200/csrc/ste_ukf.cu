@@ -1,0 +1,385 @@
+// ste_ukf.cu - kernels and C ABI of libste_ukf.so (sm_100a only).
+//
+// Execution model: one thread per track, sequential in time (the UKF recursion is a
+// loop-carried dependency through sqrtm + trigonometry; tracks are the parallel axis).
+// All arrays are [plane][track] so that a warp's 32 loads/stores of one plane are one
+// contiguous 256-byte segment.  The kernels are bound by the FP64 pipe (about 26 flop per
+// algorithmic byte), so the time loop keeps every matrix in registers and
+// prefetches the next step's inputs while the current step computes.
+#include <cstdio>
+#include <cstring>
+
+#include "ste_tracks.cuh"
+
+namespace ste {
+
+constexpr int kThreads = 128;
+
+template <bool POS_ONLY, bool GATING>
+__global__ void __launch_bounds__(kThreads) ukf_forward_kernel(const __grid_constant__ KernelArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t);
+}
+
+__global__ void __launch_bounds__(kThreads) urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.prob.n_tracks) backward_track(a, t);
+}
+
+// ------------------------------------------------------------------------------------------ //
+// Single-step entry points behind UnscentedKalmanFilter.predict / .update.
+// ------------------------------------------------------------------------------------------ //
+struct StepArgs {
+    SteProblem prob;
+    double *x;
+    double *P;
+    const double *dt, *sog_rate, *cog_rate, *noise, *z;
+    double *sigma_prior, *sigma_post;
+    uint8_t *gate_iters;
+    double *gate_lambda;
+    double *gate_scale;
+    int32_t *status;
+};
+
+__device__ __forceinline__ void load_xP(const StepArgs &a, int t, double (&x)[4], double (&P)[10]) {
+    const int64_t ld = a.prob.ld;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = a.x[r * ld + t];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) P[SYM(i, j)] = a.P[(i * 4 + j) * ld + t];
+}
+__device__ __forceinline__ void store_xP(const StepArgs &a, int t, const double (&x)[4], const double (&P)[10]) {
+    const int64_t ld = a.prob.ld;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a.x[r * ld + t] = x[r];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a.P[(i * 4 + j) * ld + t] = P[SYM(i, j)];
+}
+
+__global__ void __launch_bounds__(kThreads) ukf_predict_kernel(const __grid_constant__ StepArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.prob.n_tracks) return;
+    const int64_t ld = a.prob.ld;
+    double x[4], P[10], e[4] = {0.0, 0.0, 0.0, 0.0};
+    load_xP(a, t, x, P);
+    if (a.noise) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e[r] = a.noise[r * ld + t] * sqrt(a.prob.Q[r * 5]);
+    }
+    int status = 0;
+    ukf_predict(x, P, a.prob.Q, a.dt[t], a.sog_rate[t], a.cog_rate[t], e, status,
+                a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, ld);
+    if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
+    store_xP(a, t, x, P);
+    if (a.status) a.status[t] = status;
+}
+
+template <bool POS_ONLY, bool GATING>
+__global__ void __launch_bounds__(kThreads) ukf_update_kernel(const __grid_constant__ StepArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.prob.n_tracks) return;
+    const int64_t ld = a.prob.ld;
+    const Model model{a.prob.H, a.prob.Q, a.prob.R};
+    double x[4], P[10], z[4], un[4];
+    load_xP(a, t, x, P);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) z[r] = a.z[r * ld + t];
+    const double *noise = nullptr;
+    if (a.noise) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) un[r] = a.noise[r * ld + t];
+        noise = un;
+    }
+    int status = 0, it;
+    double lam, rs;
+    if (POS_ONLY)
+        ukf_update_position<GATING>(x, P, model, z, noise, a.prob.gate_chi, a.prob.gate_max_iter, status, it, lam, rs);
+    else
+        ukf_update_generic<GATING>(x, P, model, z, noise, a.prob.gate_chi, a.prob.gate_max_iter, status, it, lam, rs);
+    if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
+    store_xP(a, t, x, P);
+    if (a.gate_iters) a.gate_iters[t] = (uint8_t)min_(it, 255);
+    if (a.gate_lambda) a.gate_lambda[t] = lam;
+    if (a.gate_scale) a.gate_scale[t] = rs;
+    if (a.status) a.status[t] = status;
+}
+
+// ------------------------------------------------------------------------------------------ //
+// compute_sigma_points for any n <= 8 (unscented.py:76-107).  Not on the hot path: generic-n
+// cyclic Jacobi on thread-local arrays.
+// ------------------------------------------------------------------------------------------ //
+__global__ void __launch_bounds__(kThreads) sigma_points_kernel(int n, int T, int64_t ld, double scale, const double *x,
+                                                                 const double *P, double *X, int32_t *status) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double A[64], V[64];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            // the root is taken of the symmetric part; P is symmetric up to rounding in the filter
+            A[i * 8 + j] = 0.5 * scale * (P[(i * n + j) * ld + t] + P[(j * n + i) * ld + t]);
+            V[i * 8 + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, dia = 0.0;
+        for (int i = 0; i < n; ++i) {
+            dia += A[i * 8 + i] * A[i * 8 + i];
+            for (int j = i + 1; j < n; ++j) off += A[i * 8 + j] * A[i * 8 + j];
+        }
+        if (!(off > 1e-36 * dia)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * 8 + q];
+                if (apq == 0.0) continue;
+                const double d = A[q * 8 + q] - A[p * 8 + p], b = apq + apq;
+                const double tt = (d >= 0.0 ? b : -b) / (fabs(d) + sqrt(fma(d, d, b * b)));
+                const double c = rsqrt_f64(fma(tt, tt, 1.0)), s = tt * c;
+                for (int r = 0; r < n; ++r) {  // columns p, q of A and V
+                    const double arp = A[r * 8 + p], arq = A[r * 8 + q];
+                    A[r * 8 + p] = fma(c, arp, -s * arq);
+                    A[r * 8 + q] = fma(s, arp, c * arq);
+                    const double vrp = V[r * 8 + p], vrq = V[r * 8 + q];
+                    V[r * 8 + p] = fma(c, vrp, -s * vrq);
+                    V[r * 8 + q] = fma(s, vrp, c * vrq);
+                }
+                for (int r = 0; r < n; ++r) {  // rows p, q of A
+                    const double apr = A[p * 8 + r], aqr = A[q * 8 + r];
+                    A[p * 8 + r] = fma(c, apr, -s * aqr);
+                    A[q * 8 + r] = fma(s, apr, c * aqr);
+                }
+                A[p * 8 + q] = 0.0;
+                A[q * 8 + p] = 0.0;
+            }
+    }
+    int st = 0;
+    double wmax = 0.0;
+    for (int k = 0; k < n; ++k) wmax = fmax(wmax, fabs(A[k * 8 + k]));
+    double f[8];
+    for (int k = 0; k < n; ++k) {
+        if (A[k * 8 + k] < -1e-13 * wmax) st |= STE_STATUS_INDEFINITE;
+        f[k] = sqrt(fmax(A[k * 8 + k], 0.0));
+    }
+    const int L = 2 * n + 1;
+    for (int r = 0; r < n; ++r) {
+        const double xr = x[r * ld + t];
+        X[(r * L) * ld + t] = xr;
+        for (int i = 0; i < n; ++i) {
+            double m = 0.0;
+            for (int k = 0; k < n; ++k) m = fma(V[r * 8 + k] * f[k], V[i * 8 + k], m);
+            X[(r * L + 1 + i) * ld + t] = xr + m;
+            X[(r * L + 1 + n + i) * ld + t] = xr - m;
+        }
+    }
+    if (status) status[t] = st;
+}
+
+__global__ void __launch_bounds__(kThreads) geodetic_kernel(int T, int64_t ld, const double *xin, const double *dt,
+                                                            const double *sog_rate, const double *cog_rate,
+                                                            double *xout) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double x[4], y[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = xin[r * ld + t];
+    const double d = dt[t];
+    geodetic_step(x, d, d / kEarthRadiusKm, sog_rate[t], cog_rate[t], y);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xout[r * ld + t] = y[r];
+}
+
+__global__ void fp64_fma_probe_kernel(int iters, double *sink) {
+    double acc[8];
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-12 * (blockIdx.x + 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.1 * k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fma(acc[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------ //
+// host side of the ABI
+// ------------------------------------------------------------------------------------------ //
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+static int check_launch(const char *what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return STE_ERR_CUDA;
+    }
+    return STE_OK;
+}
+
+static bool is_symmetric(const double *M) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < i; ++j)
+            if (M[i * 4 + j] != M[j * 4 + i]) return false;
+    return true;
+}
+
+// H == diag(1,1,0,0) exactly and R zero outside its leading 2x2 block
+static bool position_only(const SteProblem &p) {
+    if (p.flags & STE_FLAG_FORCE_GENERIC) return false;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const double h = (i == j && i < 2) ? 1.0 : 0.0;
+            if (p.H[i * 4 + j] != h) return false;
+            if ((i >= 2 || j >= 2) && p.R[i * 4 + j] != 0.0) return false;
+        }
+    return true;
+}
+
+static int validate_problem(const SteProblem *p) {
+    if (!p) return fail(STE_ERR_INVALID_ARG, "null SteProblem");
+    if (p->n_tracks < 0 || p->max_steps < 0 || p->max_obs < 1) return fail(STE_ERR_INVALID_ARG, "negative sizes");
+    if (p->ld < p->n_tracks) return fail(STE_ERR_INVALID_ARG, "ld < n_tracks");
+    if (!is_symmetric(p->Q) || !is_symmetric(p->R) || !is_symmetric(p->P0))
+        return fail(STE_ERR_UNSUPPORTED, "Q, R and P0 must be symmetric");
+    return STE_OK;
+}
+
+}  // namespace ste
+
+using namespace ste;
+
+extern "C" {
+
+int ste_version(void) { return STE_ABI_VERSION; }
+
+const char *ste_last_error(void) { return g_err; }
+
+int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream) {
+    if (int rc = validate_problem(prob)) return rc;
+    if (!in || !out) return fail(STE_ERR_INVALID_ARG, "null SteInputs/SteOutputs");
+    if (!in->x0 || !in->dt || !in->sog_rate || !in->cog_rate) return fail(STE_ERR_INVALID_ARG, "missing input array");
+    if (!out->mean_f || !out->cov_f || !out->status) return fail(STE_ERR_INVALID_ARG, "missing output array");
+    const bool gating = (prob->flags & STE_FLAG_GATING) != 0;
+    if (gating && in->noise_upd)
+        return fail(STE_ERR_UNSUPPORTED, "gating draws a data-dependent number of normals; only zero measurement noise is supported with it");
+    if (gating && prob->gate_max_iter < 1) return fail(STE_ERR_INVALID_ARG, "gate_max_iter < 1");
+    const bool pos = position_only(*prob);
+    for (int r = 0; r < 4; ++r) {
+        bool used = gating;  // generic gating: y = z - x touches every row
+        for (int j = 0; j < 4; ++j) used |= prob->H[r * 4 + j] != 0.0 || prob->R[r * 4 + j] != 0.0;
+        if (pos) used = r < 2;  // rows 2, 3 only ever multiply exact zeros of pinv(S)
+        if (used && !in->z[r]) return fail(STE_ERR_INVALID_ARG, "observation row referenced by H/R is NULL");
+    }
+    if (prob->n_tracks == 0) return STE_OK;
+    KernelArgs a;
+    a.prob = *prob;
+    a.in = *in;
+    a.out = *out;
+    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pos) {
+        if (gating) ukf_forward_kernel<true, true><<<grid, block, 0, s>>>(a);
+        else ukf_forward_kernel<true, false><<<grid, block, 0, s>>>(a);
+    } else {
+        if (gating) ukf_forward_kernel<false, true><<<grid, block, 0, s>>>(a);
+        else ukf_forward_kernel<false, false><<<grid, block, 0, s>>>(a);
+    }
+    return check_launch("ukf_forward_kernel");
+}
+
+int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream) {
+    if (int rc = validate_problem(prob)) return rc;
+    if (!in || !out) return fail(STE_ERR_INVALID_ARG, "null SteInputs/SteOutputs");
+    if (!in->dt || !in->sog_rate || !in->cog_rate) return fail(STE_ERR_INVALID_ARG, "missing input array");
+    if (!out->mean_f || !out->cov_f || !out->mean_s || !out->cov_s || !out->status)
+        return fail(STE_ERR_INVALID_ARG, "missing output array");
+    if ((out->mean_s == out->mean_f) != (out->cov_s == out->cov_f))
+        return fail(STE_ERR_INVALID_ARG, "in-place smoothing must alias both mean and cov");
+    if (prob->n_tracks == 0) return STE_OK;
+    KernelArgs a;
+    a.prob = *prob;
+    a.in = *in;
+    a.out = *out;
+    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    urtss_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("urtss_backward_kernel");
+}
+
+int ste_ukf_predict_f64(const SteProblem *prob, double *x, double *P, const double *dt, const double *sog_rate,
+                        const double *cog_rate, const double *noise, double *sigma_prior, double *sigma_post,
+                        int32_t *status, void *stream) {
+    if (int rc = validate_problem(prob)) return rc;
+    if (!x || !P || !dt || !sog_rate || !cog_rate) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if ((sigma_prior == nullptr) != (sigma_post == nullptr))
+        return fail(STE_ERR_INVALID_ARG, "sigma_prior and sigma_post must be given together");
+    if (prob->n_tracks == 0) return STE_OK;
+    StepArgs a{};
+    a.prob = *prob;
+    a.x = x; a.P = P; a.dt = dt; a.sog_rate = sog_rate; a.cog_rate = cog_rate; a.noise = noise;
+    a.sigma_prior = sigma_prior; a.sigma_post = sigma_post; a.status = status;
+    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    ukf_predict_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("ukf_predict_kernel");
+}
+
+int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const double *z, const double *noise,
+                       uint8_t *gate_iters, double *gate_lambda, double *gate_scale, int32_t *status, void *stream) {
+    if (int rc = validate_problem(prob)) return rc;
+    if (!x || !P || !z) return fail(STE_ERR_INVALID_ARG, "missing array");
+    const bool gating = (prob->flags & STE_FLAG_GATING) != 0;
+    if (gating && noise) return fail(STE_ERR_UNSUPPORTED, "gating supports zero measurement noise only");
+    if (gating && prob->gate_max_iter < 1) return fail(STE_ERR_INVALID_ARG, "gate_max_iter < 1");
+    if (prob->n_tracks == 0) return STE_OK;
+    StepArgs a{};
+    a.prob = *prob;
+    a.x = x; a.P = P; a.z = z; a.noise = noise;
+    a.gate_iters = gate_iters; a.gate_lambda = gate_lambda; a.gate_scale = gate_scale; a.status = status;
+    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (position_only(*prob)) {
+        if (gating) ukf_update_kernel<true, true><<<grid, block, 0, s>>>(a);
+        else ukf_update_kernel<true, false><<<grid, block, 0, s>>>(a);
+    } else {
+        if (gating) ukf_update_kernel<false, true><<<grid, block, 0, s>>>(a);
+        else ukf_update_kernel<false, false><<<grid, block, 0, s>>>(a);
+    }
+    return check_launch("ukf_update_kernel");
+}
+
+int ste_sigma_points_f64(int32_t n, int32_t n_tracks, int64_t ld, double scale, const double *x, const double *P,
+                         double *X, int32_t *status, void *stream) {
+    if (n < 1 || n > 8) return fail(STE_ERR_UNSUPPORTED, "sigma points: 1 <= n <= 8");
+    if (n_tracks < 0 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / ld");
+    if (!x || !P || !X) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if (n_tracks == 0) return STE_OK;
+    const dim3 grid((n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    sigma_points_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n, n_tracks, ld, scale, x, P, X, status);
+    return check_launch("sigma_points_kernel");
+}
+
+int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const double *dt, const double *sog_rate,
+                     const double *cog_rate, double *x_out, void *stream) {
+    if (n_tracks < 0 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / ld");
+    if (!x_in || !dt || !sog_rate || !cog_rate || !x_out) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if (n_tracks == 0) return STE_OK;
+    const dim3 grid((n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    geodetic_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_tracks, ld, x_in, dt, sog_rate, cog_rate, x_out);
+    return check_launch("geodetic_kernel");
+}
+
+int ste_probe_fp64_fma(int32_t blocks, int32_t threads, int32_t iters, double *sink, void *stream) {
+    if (blocks < 1 || threads < 1 || threads > 1024 || iters < 1 || !sink)
+        return fail(STE_ERR_INVALID_ARG, "bad probe arguments");
+    fp64_fma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+    return check_launch("fp64_fma_probe_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+"""Unscented Kalman Filter with the reference's class API, executed on the GPU.
+
+Drop-in for reference ``src/track_estimators/kalman_filters/unscented.py`` (Cole & Schamberg,
+Applied Ocean Research 124 (2022) 103205).  Every arithmetic entry point - ``predict``, ``update``,
+``run``, ``rts_step`` / ``run_rts_smoother``, ``compute_sigma_points``, ``check_robustness`` - is a
+call into ``libste_ukf.so`` on a batch of one track; the many-track entry point is
+:class:`ship_track_estimators_b200.batch.BatchedUKF`.  There is no host implementation: without
+the CUDA library or a GPU these methods raise.
+
+Noise.  The reference perturbs the predicted mean, the measurement and the back-predicted mean
+with fresh ``np.random.normal`` draws (``unscented.py:198-202, 232-236, 320-323``).  This class
+draws the same number of *unit* normals from the same global numpy generator in the same order and
+lets the kernels scale them by ``sqrt(diag Q)`` / ``sqrt(diag R)``, so a seeded or monkey-patched
+``np.random.normal`` pins both implementations identically.  ``noise="zero"`` (constructor or
+``UnscentedKalmanFilter.default_noise``) disables the draws.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from typing import Callable, Optional
+
+import numpy as np
+
+from .kalman_filter import KalmanFilterBase
+from .non_linear_process import geodetic_dynamics
+
+
+def _unit_normals(rows: int, n: int) -> np.ndarray:
+    """``rows`` successive ``np.random.normal(size=n)`` draws (same stream order as the reference)."""
+    if rows == 0:
+        return np.zeros((0, n))
+    return np.asarray(np.random.normal(size=(rows, n)), dtype=np.float64).reshape(rows, n)
+
+
+class UnscentedKalmanFilter(KalmanFilterBase):
+    default_noise = "numpy"  # "numpy": reference semantics; "zero": deterministic
+
+    def __init__(
+        self,
+        H=None,
+        Q=None,
+        R=None,
+        P=None,
+        x0=None,
+        non_linear_process: Optional[Callable] = None,
+        measurement_model: Optional[Callable] = None,
+        *,
+        gating: bool = False,
+        noise: Optional[str] = None,
+    ):
+        """Same parameters as the reference (``unscented.py:20-74``); ``gating`` re-enables the
+        Mahalanobis robustification the reference leaves commented out (``:228``)."""
+        super().__init__()
+        if H is None:
+            raise ValueError("Set proper system dynamics.")
+        self.H = H
+        self.n = H.shape[1]
+        self.Q = np.eye(self.n) if Q is None else np.asarray(Q)
+        self.R = np.eye(self.n) if R is None else np.asarray(R)
+        self.P_orig = np.eye(self.n) if P is None else np.asarray(P)
+        self.P = np.eye(self.n) if P is None else np.asarray(P)
+        self.x = np.zeros((self.n, 1)) if x0 is None else np.asarray(x0).reshape(-1, 1)
+
+        self.n_sigma_points = 2 * self.n + 1
+        self.sigma_points = np.zeros((self.n, self.n_sigma_points))
+        self.sigma_points_orig = None
+        self.weights = np.zeros((self.n_sigma_points, self.n_sigma_points))
+
+        self.non_linear_process = non_linear_process
+        self.measurement_model = measurement_model
+        self.gating = bool(gating)
+        self.noise = noise
+        self.status = 0  # OR of STE_STATUS_* bits seen by this filter
+        self.gate_iters: list = []
+        self.gate_lambda: list = []
+
+    # ------------------------------------------------------------------ #
+    # helpers                                                            #
+    # ------------------------------------------------------------------ #
+    def _noise_on(self) -> bool:
+        mode = self.noise if self.noise is not None else type(self).default_noise
+        if mode not in ("numpy", "zero"):
+            raise ValueError(f"unknown noise mode {mode!r}")
+        return mode == "numpy"
+
+    def _require_n4(self, what: str):
+        if self.n != 4:
+            raise NotImplementedError(
+                f"{what}: the CUDA path implements the n = 4 state [lon, lat, SOG, COG] "
+                f"(this filter has n = {self.n}); only compute_weights / compute_sigma_points are dimension-generic"
+            )
+
+    def _resolve_process(self, non_linear_process):
+        if non_linear_process is None:
+            assert self.non_linear_process is not None, "Non-linear process is not set."
+            non_linear_process = self.non_linear_process
+        assert callable(non_linear_process), "Non-linear process model must be callable."
+        if non_linear_process is not geodetic_dynamics:
+            raise NotImplementedError(
+                "the CUDA path fuses the geodetic process model; pass "
+                "ship_track_estimators_b200.kalman_filters.non_linear_process.geodetic_dynamics"
+            )
+        return non_linear_process
+
+    def _model(self, P0=None):
+        from ..batch import BatchedUKF
+
+        if self.measurement_model is not None:
+            assert callable(self.measurement_model), "Measurement model must be callable."
+            raise NotImplementedError("measurement_model hooks are not supported on the CUDA path")
+        return BatchedUKF(self.H, self.Q, self.R, self.P if P0 is None else P0, gating=self.gating)
+
+    def _step_problem(self, engine):
+        from ..batch import TrackBatch  # noqa: F401  (keeps import order explicit)
+        from .. import _native as nat
+
+        p = nat.SteProblem()
+        m = engine.model
+        p.n_tracks, p.max_steps, p.max_obs, p.substeps, p.rate_repeat = 1, 1, 1, 1, 1
+        p.flags = nat.STE_FLAG_GATING if m.gating else 0
+        p.gate_max_iter, p.gate_chi, p.ld = int(m.gate_max_iter), float(m.gate_chi), 1
+        for name, M in (("H", m.H), ("Q", m.Q), ("R", m.R), ("P0", m.P0)):
+            getattr(p, name)[:] = M.reshape(-1).tolist()
+        return p
+
+    # ------------------------------------------------------------------ #
+    # sigma points and weights (dimension-generic)                       #
+    # ------------------------------------------------------------------ #
+    def compute_weights(self, weight0: Optional[float] = None) -> np.ndarray:
+        """Diagonal weight matrix, ``W0 = 1 - n/3`` by default (reference ``:109-142``)."""
+        if weight0 is None:
+            weight0 = 1 - self.n / 3.0
+        assert weight0 < 1.0 and weight0 > -1.0, "Weight0 value ({}) is outside [-1, 1] range.".format(weight0)
+        weightn = (1 - weight0) / (2 * self.n)
+        np.fill_diagonal(self.weights, weightn)
+        self.weights[0, 0] = weight0
+        logging.debug("Weights\n\n%s", self.weights)
+        return self.weights
+
+    def compute_sigma_points(self, x: Optional[np.ndarray] = None, P: Optional[np.ndarray] = None) -> np.ndarray:
+        """``X0 = x, Xi = x +/- sqrtm(n / (1 - W0) P)[:, i]`` (reference ``:76-107``), on the GPU."""
+        import torch
+
+        from .. import _native as nat
+
+        if x is None:
+            assert self.x is not None, "Set proper initial state estimate."
+            x = self.x
+        if P is None:
+            assert self.P is not None, "Set proper initial state covariance matrix."
+            P = self.P
+        n = self.n
+        if n > 8:
+            raise NotImplementedError("sigma points on the CUDA path support n <= 8")
+        scale = n / (1 - self.weights[0, 0])
+        lib = nat.load()
+        dev = torch.device("cuda")
+        xd = torch.from_numpy(np.asarray(x, dtype=np.float64).reshape(n, 1).copy()).to(dev)
+        Pd = torch.from_numpy(np.asarray(P, dtype=np.float64).reshape(n * n, 1).copy()).to(dev)
+        Xd = torch.empty(n * self.n_sigma_points, 1, dtype=torch.float64, device=dev)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        nat.check(lib.ste_sigma_points_f64(n, 1, 1, float(scale), nat.ptr(xd), nat.ptr(Pd), nat.ptr(Xd), nat.ptr(st), nat.current_stream()))
+        self.status |= int(st.item())
+        self.sigma_points = Xd.cpu().numpy().reshape(n, self.n_sigma_points)
+        return self.sigma_points
+
+    # ------------------------------------------------------------------ #
+    # single steps                                                       #
+    # ------------------------------------------------------------------ #
+    def predict(self, non_linear_process: Optional[Callable] = None, **non_linear_process_kwargs) -> None:
+        """One unscented prediction (reference ``:144-207``); kwargs ``dt, c, sog_rate, cog_rate``."""
+        import torch
+
+        from .. import _native as nat
+
+        self._resolve_process(non_linear_process)
+        self._require_n4("predict")
+        kw = dict(non_linear_process_kwargs)
+        if kw.get("c", None) is not None and np.size(kw["c"]) != 0:
+            raise NotImplementedError("only c=None is supported (the reference never passes a control vector)")
+        dt = float(kw["dt"])
+        sog_rate, cog_rate = float(kw.get("sog_rate", 0.0)), float(kw.get("cog_rate", 0.0))
+        self.x = self.x.reshape(-1, 1)
+        self.compute_weights()
+        engine = self._model()
+        p = self._step_problem(engine)
+        dev = torch.device("cuda")
+        f64 = dict(dtype=torch.float64, device=dev)
+        xd = torch.from_numpy(np.asarray(self.x, dtype=np.float64).reshape(4, 1).copy()).to(dev)
+        Pd = torch.from_numpy(np.asarray(self.P, dtype=np.float64).reshape(16, 1).copy()).to(dev)
+        scal = torch.tensor([[dt], [sog_rate], [cog_rate]], **f64)
+        noise = torch.from_numpy(_unit_normals(1, 4).reshape(4, 1).copy()).to(dev) if self._noise_on() else None
+        sp0, sp1 = torch.empty(36, 1, **f64), torch.empty(36, 1, **f64)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        nat.check(engine._lib.ste_ukf_predict_f64(
+            C.byref(p), nat.ptr(xd), nat.ptr(Pd), nat.ptr(scal[0]), nat.ptr(scal[1]), nat.ptr(scal[2]),
+            nat.ptr(noise), nat.ptr(sp0), nat.ptr(sp1), nat.ptr(st), nat.current_stream()))
+        self.x = xd.cpu().numpy().reshape(4, 1)
+        self.P = Pd.cpu().numpy().reshape(4, 4)
+        self.sigma_points_orig = sp0.cpu().numpy().reshape(4, 9)
+        self.sigma_points = sp1.cpu().numpy().reshape(4, 9)
+        self.status |= int(st.item())
+
+    def _update_device(self, x, P, R, z, use_noise):
+        """Shared by ``update`` and ``check_robustness``: returns (x, P, iters, lambda, scale)."""
+        import torch
+
+        from ..batch import BatchedUKF
+        from .. import _native as nat
+
+        if self.measurement_model is not None:
+            assert callable(self.measurement_model), "Measurement model must be callable."
+            raise NotImplementedError("measurement_model hooks are not supported on the CUDA path")
+        engine = BatchedUKF(self.H, self.Q, R, P, gating=self.gating)
+        p = self._step_problem(engine)
+        dev = torch.device("cuda")
+        f64 = dict(dtype=torch.float64, device=dev)
+        xd = torch.from_numpy(np.asarray(x, dtype=np.float64).reshape(4, 1).copy()).to(dev)
+        Pd = torch.from_numpy(np.asarray(P, dtype=np.float64).reshape(16, 1).copy()).to(dev)
+        zd = torch.from_numpy(np.asarray(z, dtype=np.float64).reshape(4, 1).copy()).to(dev)
+        noise = torch.from_numpy(_unit_normals(1, 4).reshape(4, 1).copy()).to(dev) if use_noise else None
+        it = torch.zeros(1, dtype=torch.uint8, device=dev)
+        lam = torch.ones(1, **f64)
+        scale = torch.ones(1, **f64)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        nat.check(engine._lib.ste_ukf_update_f64(
+            C.byref(p), nat.ptr(xd), nat.ptr(Pd), nat.ptr(zd), nat.ptr(noise), nat.ptr(it), nat.ptr(lam),
+            nat.ptr(scale), nat.ptr(st), nat.current_stream()))
+        self.status |= int(st.item())
+        return xd.cpu().numpy().reshape(4, 1), Pd.cpu().numpy().reshape(4, 4), int(it.item()), float(lam.item()), float(scale.item())
+
+    def update(self, z: np.ndarray) -> None:
+        """Linear measurement update with pseudo-inverse gain and Joseph-form covariance
+        (reference ``:209-265``)."""
+        self._require_n4("update")
+        z = np.asarray(z, dtype=np.float64).reshape(-1, 1)
+        use_noise = self._noise_on() and not self.gating  # gating: zero measurement noise
+        self.x, self.P, it, lam, _ = self._update_device(self.x, self.P, self.R, z, use_noise)
+        if self.gating:
+            self.gate_iters.append(it)
+            self.gate_lambda.append(lam)
+
+    # ------------------------------------------------------------------ #
+    # the two hot loops                                                  #
+    # ------------------------------------------------------------------ #
+    def _run_device(self, nsteps, dt, ship_track):
+        from ..batch import TrackBatch, exact_update_mask
+
+        self._resolve_process(None)
+        self._require_n4("run")
+        N = int(nsteps)
+        mask = exact_update_mask(dt, ship_track.dts, self.time)
+        tape = None
+        if self._noise_on():
+            n_upd = 1 + int(mask.sum())
+            meas = not self.gating
+            draws = _unit_normals(N + (n_upd if meas else 0), 4)
+            pred, upd, k = np.zeros((N, 4)), np.zeros((n_upd, 4)), 0
+            if meas:
+                upd[0] = draws[0]
+                k = 1
+            u = 1
+            for s in range(N):  # reference call order: predict, then update when the step matches
+                pred[s] = draws[k]
+                k += 1
+                if mask[s] and meas:
+                    upd[u] = draws[k]
+                    k += 1
+                    u += 1
+            tape = [dict(pred=pred, upd=upd)]
+        engine = self._model()
+        batch = TrackBatch.from_tracks([ship_track], [dt], x0=[np.asarray(self.x).reshape(-1)], time0=self.time,
+                                       noise=tape, smoother=False)
+        res = engine.run(batch, smoother=False)
+        out = res.track(0)
+        self.status |= out["status"]
+        for s in range(N + 1):
+            self.means.append(out["means"][s].reshape(4, 1).copy())
+            self.covariances.append(out["covs"][s].copy())
+        self.x = self.means[-1]
+        self.P = self.covariances[-1]
+        if N > 0:
+            self.time = np.cumsum(np.concatenate(([np.float64(self.time)], dt)))[-1]
+        ui = out["n_updates"] - 1
+        self.c = np.asarray([ship_track.sog[ui], ship_track.cog[ui]]) if getattr(ship_track, "sog", None) is not None else None
+        if self.gating:
+            self.gate_iters.extend(out["gate_iters"].tolist())
+            self.gate_lambda.extend(out["gate_lambda"].tolist())
+
+    def rts_step(self, fwd_means, fwd_vars, ship_track, *args, **kwargs):
+        """Unscented RTS smoother over explicit filtered states (reference ``:267-351``).
+
+        ``fwd_means (N+1, 4, 1)``, ``fwd_vars (N+1, 4, 4)``; returns arrays of the same shapes.
+        Unlike the reference this does not overwrite ``ship_track.sog_rate / cog_rate`` with their
+        ``np.repeat`` expansion (``:287-292``); the expansion is applied as an index map on the device.
+        """
+        import torch
+
+        from ..batch import BatchedUKF, TrackBatch, TrackResults
+
+        self._resolve_process(None)
+        self._require_n4("rts_step")
+        fwd_means = np.asarray(fwd_means, dtype=np.float64)
+        fwd_vars = np.asarray(fwd_vars, dtype=np.float64)
+        nstates = fwd_means.shape[0]
+        N = nstates - 1
+        if self.dt is None or len(self.dt) < N:
+            raise IndexError("rts_step needs the dt array of the forward run (self.dt)")
+        sog_rate = np.asarray(ship_track.sog_rate, dtype=np.float64)
+        cog_rate = np.asarray(ship_track.cog_rate, dtype=np.float64)
+        rep = int(nstates / len(ship_track.dts))
+        if N > 0 and (rep < 1 or (N - 1) // rep >= min(len(sog_rate), len(cog_rate))):
+            raise IndexError("index out of bounds for the repeated sog_rate / cog_rate arrays")
+        dev = torch.device("cuda")
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+        noise_bwd = None
+        if self._noise_on() and N > 0:
+            draws = _unit_normals(N, 4)  # drawn for step N-1 first
+            noise_bwd = up(draws[::-1].reshape(N, 4, 1))
+        m = len(sog_rate)
+        batch = TrackBatch(
+            x0=up(fwd_means[0].reshape(4, 1)), dt=up(np.asarray(self.dt, dtype=np.float64)[:N].reshape(N, 1) if N else np.zeros((1, 1))),
+            sog_rate=up(sog_rate.reshape(m, 1)), cog_rate=up(cog_rate.reshape(m, 1)), z=[None] * 4,
+            n_steps=torch.tensor([N], dtype=torch.int32, device=dev), rate_repeat_all=max(rep, 1),
+            noise_bwd=noise_bwd, n_steps_host=np.array([N], dtype=np.int32),
+        )
+        engine = BatchedUKF(self.H, self.Q, self.R, self.P_orig)
+        S = batch.max_steps + 1
+        mean_f = torch.zeros(S, 4, 1, dtype=torch.float64, device=dev)
+        cov_f = torch.zeros(S, 16, 1, dtype=torch.float64, device=dev)
+        mean_f[:nstates] = up(fwd_means.reshape(nstates, 4, 1))
+        cov_f[:nstates] = up(fwd_vars.reshape(nstates, 16, 1))
+        res = TrackResults(
+            mean_f=mean_f, cov_f=cov_f, mean_s=torch.empty_like(mean_f), cov_s=torch.empty_like(cov_f),
+            status=torch.zeros(1, dtype=torch.int32, device=dev), n_updates=torch.zeros(1, dtype=torch.int32, device=dev),
+            n_steps_host=batch.n_steps_host,
+        )
+        engine.backward(batch, res)
+        self.status |= int(res.status.item())
+        x = res.mean_s[:nstates].cpu().numpy().reshape(nstates, 4, 1)
+        P = res.cov_s[:nstates].cpu().numpy().reshape(nstates, 4, 4)
+        return x, P
+
+    # ------------------------------------------------------------------ #
+    # robustification (reference :353-511; dead code there)              #
+    # ------------------------------------------------------------------ #
+    def check_robustness(self, z: np.ndarray, P: np.ndarray, R: np.ndarray) -> np.ndarray:
+        """Mahalanobis-distance outlier judging: returns the inflated measurement covariance
+        ``R * prod(lambda)`` (reference ``:353-387``), with zero measurement noise."""
+        self._require_n4("check_robustness")
+        keep = self.gating
+        self.gating = True
+        try:
+            _, _, it, lam, scale = self._update_device(self.x, P, R, np.asarray(z, dtype=np.float64).reshape(-1, 1), False)
+        finally:
+            self.gating = keep
+        self.last_gate = dict(iterations=it, lambda_factor=lam, scale=scale)
+        return np.asarray(R) * scale
+
+    def scale_measurement_uncertainty(self, R: np.ndarray, lambda_factor: float) -> np.ndarray:
+        """``R * lambda`` (reference ``:484-511``)."""
+        return R * lambda_factor

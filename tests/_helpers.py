@@ -18,6 +18,12 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 TOL = 1e-9
+# Where the reference's own output moves by more than TOL under a rounding-only change of its
+# LAPACK calls (fixture key ``unc``, see tests/golden/make_golden.py: rounding_variant), parity is
+# asserted at UNC_FACTOR x that self-uncertainty instead: the smoother inverts covariances with
+# condition numbers up to ~1e10 on long-gap tracks, which bounds what "equal to the reference"
+# can mean there.
+UNC_FACTOR = 10.0
 
 
 def load_golden(name):
@@ -63,22 +69,30 @@ def diag_err(got_diag, ref_diag, ref_scale=None):
     return float(np.max(np.abs(got_diag - ref_diag) / np.maximum(den, 1e-300)))
 
 
-def assert_track_close(got, ref, tol=TOL, smoother=True, label=""):
-    """``got``/``ref``: dicts with means, covs[, means_s, covs_s] (or *_diag for slim fixtures)."""
-    e = mean_err(got["means"], ref["means"])
-    assert e <= tol, f"{label} filtered mean err {e:.3e}"
+def track_errors(got, ref, smoother=True):
+    """-> [filtered mean, filtered cov, smoothed mean, smoothed cov] errors (nan = not compared)."""
+    e = [mean_err(got["means"], ref["means"]), np.nan, np.nan, np.nan]
     if "covs" in ref:
-        e = cov_err(got["covs"], ref["covs"])
-        assert e <= tol, f"{label} filtered cov err {e:.3e}"
+        e[1] = cov_err(got["covs"], ref["covs"])
     else:
-        e = diag_err(np.diagonal(got["covs"], axis1=1, axis2=2), ref["covs_diag"])
-        assert e <= tol, f"{label} filtered var err {e:.3e}"
+        e[1] = diag_err(np.diagonal(got["covs"], axis1=1, axis2=2), ref["covs_diag"])
     if smoother and "means_s" in ref:
-        e = mean_err(got["means_s"], ref["means_s"])
-        assert e <= tol, f"{label} smoothed mean err {e:.3e}"
+        e[2] = mean_err(got["means_s"], ref["means_s"])
         if "covs_s" in ref:
-            e = cov_err(got["covs_s"], ref["covs_s"])
-            assert e <= tol, f"{label} smoothed cov err {e:.3e}"
+            e[3] = cov_err(got["covs_s"], ref["covs_s"])
         else:
-            e = diag_err(np.diagonal(got["covs_s"], axis1=1, axis2=2), ref["covs_s_diag"])
-            assert e <= tol, f"{label} smoothed var err {e:.3e}"
+            e[3] = diag_err(np.diagonal(got["covs_s"], axis1=1, axis2=2), ref["covs_s_diag"])
+    return e
+
+
+def assert_track_close(got, ref, tol=TOL, smoother=True, label="", unc=None):
+    """``got``/``ref``: dicts with means, covs[, means_s, covs_s] (or *_diag for slim fixtures).
+    ``unc``: the reference's self-uncertainty for the four quantities (defaults to ``ref["unc"]``)."""
+    if unc is None:
+        unc = ref.get("unc", np.zeros(4))
+    names = ("filtered mean", "filtered cov", "smoothed mean", "smoothed cov")
+    for name, e, u in zip(names, track_errors(got, ref, smoother), unc):
+        if np.isnan(e):
+            continue
+        bound = max(tol, UNC_FACTOR * float(u))
+        assert e <= bound, f"{label} {name} err {e:.3e} > {bound:.3e} (reference self-uncertainty {u:.3e})"

@@ -119,6 +119,51 @@ def pinned_noise(mode, seed=0):
         np.random.normal = orig
 
 
+@contextlib.contextmanager
+def rounding_variant():
+    """Swap the reference's two LAPACK-backed calls for mathematically identical, equally
+    backward-stable ones (symmetric-eigen square root and pseudo-inverse).  Re-running the reference
+    under this patch measures how far its OWN output moves under a change of rounding only: the
+    "self-uncertainty" stored with every track.  Where a covariance the smoother inverts is
+    ill-conditioned (cond up to 1e9-1e10 on long-gap tracks) this exceeds 1e-9, and no independent
+    implementation can be expected to agree with the reference more closely than the reference
+    agrees with itself."""
+    import scipy.linalg
+
+    orig_sqrtm, orig_pinv = scipy.linalg.sqrtm, np.linalg.pinv
+
+    def sqrtm_eigh(A):
+        A = np.asarray(A, dtype=float)
+        w, V = np.linalg.eigh(0.5 * (A + A.T))
+        return (V * np.sqrt(np.maximum(w, 0.0))) @ V.T
+
+    def pinv_eigh(A):
+        A = np.asarray(A, dtype=float)
+        w, V = np.linalg.eigh(0.5 * (A + A.T))
+        keep = np.abs(w) > 1e-15 * np.max(np.abs(w))
+        f = np.zeros_like(w)
+        f[keep] = 1.0 / w[keep]
+        return (V * f) @ V.T
+
+    scipy.linalg.sqrtm, np.linalg.pinv = sqrtm_eigh, pinv_eigh
+    try:
+        yield
+    finally:
+        scipy.linalg.sqrtm, np.linalg.pinv = orig_sqrtm, orig_pinv
+
+
+def _mean_err(got, ref):
+    d = got - ref
+    d[..., 3] = (got[..., 3] - ref[..., 3] + 180.0) % 360.0 - 180.0
+    return float(np.max(np.abs(d) / np.maximum(1.0, np.abs(ref))))
+
+
+def _cov_err(got, ref):
+    num = np.max(np.abs(got - ref), axis=(-2, -1))
+    den = np.max(np.abs(ref), axis=(-2, -1))
+    return float(np.max(num / np.maximum(den, 1e-300)))
+
+
 def fake_track(lon, lat, dts, sog, cog, sog_rate, cog_rate):
     """A reference ShipTrack carrying exactly the given arrays (no CSV involved)."""
     st = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
@@ -129,7 +174,28 @@ def fake_track(lon, lat, dts, sog, cog, sog_rate, cog_rate):
     return st
 
 
-def run_reference(st, H, Q, R, P, dt_array, *, smoother=True, noise="zero", seed=0, gating=False, x0=None):
+def run_reference(st, H, Q, R, P, dt_array, **kw):
+    """One track through the reference, plus its self-uncertainty under ``rounding_variant``:
+    ``unc`` = [filtered mean, filtered cov, smoothed mean, smoothed cov] in the metrics of
+    tests/_helpers.py (0 where not applicable)."""
+    import copy
+
+    # rts_step overwrites st.sog_rate / st.cog_rate with their np.repeat expansion
+    # (unscented.py:287-292), so every run gets its own copy of the track
+    rec = _run_reference(copy.deepcopy(st), H, Q, R, P, dt_array, **kw)
+    with rounding_variant():
+        var = _run_reference(copy.deepcopy(st), H, Q, R, P, dt_array, **kw)
+    unc = [_mean_err(var["means"], rec["means"]), _cov_err(var["covs"], rec["covs"]), 0.0, 0.0]
+    if "means_s" in rec:
+        unc[2:] = [_mean_err(var["means_s"], rec["means_s"]), _cov_err(var["covs_s"], rec["covs_s"])]
+    rec["unc"] = np.asarray(unc)
+    if "gate_iters" in rec:
+        assert np.array_equal(var["gate_iters"], rec["gate_iters"]), "gating decisions are rounding-sensitive on this track"
+    assert np.array_equal(var["mask"], rec["mask"])
+    return rec
+
+
+def _run_reference(st, H, Q, R, P, dt_array, *, smoother=True, noise="zero", seed=0, gating=False, x0=None):
     """One track through the reference; returns inputs and outputs as a flat dict."""
     cls = GatedUKF if gating else UnscentedKalmanFilter
     x0 = st.z[:, 0].reshape(-1, 1).copy() if x0 is None else np.asarray(x0, dtype=float).reshape(-1, 1)

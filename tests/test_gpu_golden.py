@@ -1,0 +1,98 @@
+"""GPU parity against the reference-generated golden fixtures (tests/golden/*.npz), through the
+C ABI.  Tolerance 1e-9 (BASELINE.json north_star); decisions (update mask, gating iterations) exact."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from _helpers import TOL, assert_track_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _as_track(tr):
+    return SimpleNamespace(dts=tr["dts"], z=tr["z"], sog_rate=tr["sog_rate"], cog_rate=tr["cog_rate"])
+
+
+def _groups(tracks):
+    """Tracks sharing (H, Q, R, P0, smoother, gating) run as one batch."""
+    out = {}
+    for i, tr in enumerate(tracks):
+        key = (tr["H"].tobytes(), tr["Q"].tobytes(), tr["R"].tobytes(), tr["P0"].tobytes(), "means_s" in tr, "gate_iters" in tr)
+        out.setdefault(key, []).append(i)
+    return list(out.values())
+
+
+def _run_group(tracks, idx, cuda, force_generic=False):
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+
+    t0 = tracks[idx[0]]
+    smoother, gating = "means_s" in t0, "gate_iters" in t0
+    noise = None
+    if "noise_pred" in t0:
+        noise = [dict(pred=tracks[i]["noise_pred"], upd=tracks[i]["noise_upd"], bwd=tracks[i].get("noise_bwd")) for i in idx]
+    batch = TrackBatch.from_tracks(
+        [_as_track(tracks[i]) for i in idx], [tracks[i]["dt_array"] for i in idx], device=cuda,
+        x0=[tracks[i]["x0"] for i in idx], noise=noise, smoother=smoother,
+    )
+    ukf = BatchedUKF(t0["H"], t0["Q"], t0["R"], t0["P0"], gating=gating, force_generic=force_generic)
+    res = ukf.run(batch, smoother=smoother)
+    return [res.track(j) for j in range(len(idx))]
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize(
+    "name",
+    ["c1_single_ship", "c2_historical_batch", "c2_modern_ship", "c3_const_dt", "c4_ragged_ungated", "c4_ragged_gated", "tape_noise", "dense_h"],
+)
+def test_golden_fixture(name, force_generic, cuda, native_lib):
+    tracks, _ = load_golden(name)
+    for idx in _groups(tracks):
+        got = _run_group(tracks, idx, cuda, force_generic)
+        for g, i in zip(got, idx):
+            ref = tracks[i]
+            label = f"{name}[{i}] generic={force_generic}"
+            assert g["n_updates"] == 1 + int(ref["mask"].sum()), label
+            assert not (g["status"] & 0x1), f"{label}: non-finite state"
+            if "gate_iters" in ref:
+                assert np.array_equal(g["gate_iters"], ref["gate_iters"]), f"{label}: gating decisions differ"
+                np.testing.assert_allclose(g["gate_lambda"], ref["gate_lambda"], rtol=1e-9, err_msg=label)
+            assert_track_close(g, ref, tol=TOL, smoother="means_s" in ref, label=label)
+
+
+def test_geodetic_known_answers(cuda, native_lib):
+    from ship_track_estimators_b200.kalman_filters.non_linear_process import geodetic_dynamics
+
+    d = np.load(__import__("os").path.join(__import__("_helpers").GOLDEN, "kat_blocks.npz"))
+    got = geodetic_dynamics(d["geo_x"].T.copy(), None, d["geo_dt"], d["geo_sog_rate"], d["geo_cog_rate"]).T
+    np.testing.assert_allclose(got, d["geo_out"], rtol=1e-13, atol=1e-12)
+    # SURVEY section 9.3 known answer
+    one = geodetic_dynamics(np.array([-30.5, -0.5, 14.5, 198.5]), None, 12.0, sog_rate=0.01, cog_rate=-0.02)
+    np.testing.assert_allclose(one, [-30.99621056441692, -1.9822576603313298, 14.62, 198.26], rtol=1e-13)
+
+
+def test_sigma_points_known_answers(cuda, native_lib):
+    from ship_track_estimators_b200.kalman_filters.unscented import UnscentedKalmanFilter
+
+    d = np.load(__import__("os").path.join(__import__("_helpers").GOLDEN, "kat_blocks.npz"))
+    for x, P, X in zip(d["sp_x"], d["sp_P"], d["sp_X"]):
+        u = UnscentedKalmanFilter(H=np.eye(4), P=P, x0=x)
+        W = u.compute_weights()
+        np.testing.assert_array_equal(W, d["weights"])
+        got = u.compute_sigma_points()
+        scale = np.max(np.abs(X - x[:, None]))
+        assert np.max(np.abs(got - X)) <= 1e-10 * max(scale, 1.0)
+
+
+def test_gating_known_answers(cuda, native_lib):
+    """SURVEY section 9.3 / tests/golden/kat_gating.npz: iterations, final lambda, R scale."""
+    from ship_track_estimators_b200.kalman_filters.unscented import UnscentedKalmanFilter
+
+    rows = np.load(__import__("os").path.join(__import__("_helpers").GOLDEN, "kat_gating.npz"))["rows"]
+    for d, iters, lam, scale in rows:
+        g = UnscentedKalmanFilter(H=np.diag([1.0, 1, 0, 0]), R=np.diag([0.25, 0.25, 0, 0]), P=np.diag([0.3, 0.3, 1, 1]),
+                                  x0=np.array([10.0, 20, 12, 90]))
+        Rs = g.check_robustness(np.array([10.0 + d, 20.0 - d, 12, 90]), g.P, g.R)
+        assert g.last_gate["iterations"] == int(iters)
+        assert abs(g.last_gate["lambda_factor"] - lam) <= 1e-9 * lam
+        assert abs(Rs[0, 0] / 0.25 - scale) <= 1e-9 * scale

@@ -1,0 +1,33 @@
+// Developer-side numerical sandbox: compiles the per-track device code (csrc/ste_*.cuh) for the
+// HOST with g++ so that algorithmic changes can be checked against the golden fixtures without
+// a GPU.  NOT part of the product: the package never loads this library, tests and bench never
+// use it, and its results are not bit-identical to the GPU (different libm).
+#include <cstdint>
+#include "../../ship_track_estimators_b200/csrc/ste_tracks.cuh"
+
+using namespace ste;
+
+extern "C" int emul_forward(const SteProblem *prob, const SteInputs *in, SteOutputs *out) {
+    KernelArgs a;
+    a.prob = *prob; a.in = *in; a.out = *out;
+    bool pos = !(prob->flags & STE_FLAG_FORCE_GENERIC);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const double h = (i == j && i < 2) ? 1.0 : 0.0;
+            if (prob->H[i * 4 + j] != h) pos = false;
+            if ((i >= 2 || j >= 2) && prob->R[i * 4 + j] != 0.0) pos = false;
+        }
+    const bool gating = prob->flags & STE_FLAG_GATING;
+    for (int t = 0; t < prob->n_tracks; ++t) {
+        if (pos) { if (gating) forward_track<true, true>(a, t); else forward_track<true, false>(a, t); }
+        else     { if (gating) forward_track<false, true>(a, t); else forward_track<false, false>(a, t); }
+    }
+    return 0;
+}
+
+extern "C" int emul_backward(const SteProblem *prob, const SteInputs *in, SteOutputs *out) {
+    KernelArgs a;
+    a.prob = *prob; a.in = *in; a.out = *out;
+    for (int t = 0; t < prob->n_tracks; ++t) backward_track(a, t);
+    return 0;
+}

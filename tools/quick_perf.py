@@ -1,0 +1,49 @@
+"""Quick device timing of the forward / backward kernels and the FP64 FMA probe (dev tool)."""
+import argparse, json, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from ship_track_estimators_b200 import _native as nat
+from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+from ship_track_estimators_b200.synthetic import make_tracks
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--tracks", type=int, default=148 * 128 * 4)
+ap.add_argument("--steps", type=int, default=256)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--generic", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+lib = nat.load()
+
+def timed(fn, reps):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), ts
+
+# FP64 probe
+blocks, threads, iters = 148 * 16, 256, 20000
+sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
+ms, _ = timed(lambda: nat.check(lib.ste_probe_fp64_fma(blocks, threads, iters, nat.ptr(sink), nat.current_stream())), 3)
+flops = 2.0 * 8 * iters * blocks * threads
+print(json.dumps({"probe": "fp64_fma", "ms": ms, "tflops": flops / ms / 1e9}))
+
+t0 = time.time()
+syn = make_tracks(a.tracks, a.steps + 1, seed=1, device="cuda:0")
+torch.cuda.synchronize(); print("gen s", time.time() - t0)
+batch = TrackBatch.from_synthetic(syn, substeps=1)
+H = np.diag([1.0, 1, 0, 0]); R = np.diag([1e-3, 1e-3, 0, 0]); Q = np.diag([1e-2, 1e-2, 1e-4, 1e-4]); P = np.eye(4)
+ukf = BatchedUKF(H, Q, R, P, force_generic=a.generic)
+res = ukf.allocate(batch, smoother=True)
+f_ms, f_all = timed(lambda: ukf.forward(batch, res), a.reps)
+b_ms, b_all = timed(lambda: ukf.backward(batch, res), a.reps)
+ts = a.tracks * a.steps
+print(json.dumps({"tracks": a.tracks, "steps": a.steps, "fwd_ms": f_ms, "bwd_ms": b_ms,
+                  "fwd_steps_per_s": ts / f_ms * 1e3, "bwd_steps_per_s": ts / b_ms * 1e3,
+                  "both_steps_per_s": ts / (f_ms + b_ms) * 1e3,
+                  "fwd_GBs": ts * 200 / f_ms / 1e6, "both_GBs": ts * 544 / (f_ms + b_ms) / 1e6,
+                  "status_nonzero": int((res.status != 0).sum().item()), "all": [f_all, b_all]}))
+print("sample smoothed", res.mean_s[0, :, 0].tolist(), res.mean_s[-1, :, 0].tolist())
