@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: fp64 UKF + URTSS track-steps/second on synthetic 1024-step tracks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on): 16 M tracks x 1024 steps,
+constant dt = 1 h, k = 1, UKF + URTSS, zero noise, track-sharded over the GPUs.  16 M tracks do not
+fit one GPU's HBM at once (inputs alone are 690 GB), so the job is processed in tiles of
+``--tracks`` tracks; a "step" of this benchmark is one pass of the hot path (forward filter +
+backward smoother) over one tile whose inputs are already resident in HBM.  The job is
+embarrassingly parallel over tiles, so whole-job throughput = tile throughput; per-GPU work is
+fixed as N grows (weak scaling) and there is no collective inside the timed region.
+
+One JSON line is printed by rank 0; see README / DESIGN.md for the keys.  ``--impl reference``
+times the CPU implementation of the same path (the numpy oracle port, which calls the reference's
+own scipy/numpy routines) on all host cores of the box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_STEPS = 1024
+BYTES_FWD, BYTES_BWD = 200.0, 344.0  # algorithmic bytes per track-step at k = 1
+MODEL = dict(H=[1.0, 1.0, 0.0, 0.0], R=[1e-3, 1e-3, 0.0, 0.0], Q=[1e-2, 1e-2, 1e-4, 1e-4], P=[1.0, 1.0, 1.0, 1.0])
+METRIC = "track-steps/sec (UKF+URTSS fp64)"
+UNIT = "track-steps/s"
+
+
+# ------------------------------------------------------------------------------------------- #
+# CPU arm: the oracle port on host cores                                                      #
+# ------------------------------------------------------------------------------------------- #
+def _cpu_worker(job):
+    """One worker = one core: ``n_tracks`` synthetic tracks of ``n_steps`` steps, UKF then URTSS."""
+    seed, n_tracks, n_steps = job
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    import numpy as np
+
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    syn = make_tracks(n_tracks, n_steps + 1, seed=seed, device="cpu")
+    H, R, Q, P = (np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
+    t0 = time.perf_counter()
+    done = 0
+    for t in range(n_tracks):
+        z = np.stack([syn.lon[:, t].numpy(), syn.lat[:, t].numpy(), syn.sog[:, t].numpy(), syn.cog[:, t].numpy()])
+        dts = syn.dts[:, t].numpy()
+        O.run_track(z[:, 0], P, H, Q, R, dts, dts, z, syn.sog_rate[:, t].numpy(), syn.cog_rate[:, t].numpy(), smoother=True)
+        done += n_steps
+    return done, time.perf_counter() - t0
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuPool:
+    """One spawned process per host core, each running the oracle port single-threaded."""
+
+    def __init__(self, cores: int):
+        import multiprocessing as mp
+
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores)
+        self.pool.map(_cpu_worker, [(0, 1, 2)] * cores)  # import numpy/scipy/torch once per worker
+
+    def run(self, tracks_per_core: int, n_steps: int, seed: int):
+        """-> (aggregate track-steps/s, track-steps done, slowest worker's busy seconds)."""
+        out = self.pool.map(_cpu_worker, [(seed + c, tracks_per_core, n_steps) for c in range(self.cores)], chunksize=1)
+        steps, busy = sum(o[0] for o in out), max(o[1] for o in out)
+        return steps / busy, steps, busy
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    pool = CpuPool(cores)
+    tracks_per_core, sample_steps = 1, N_STEPS
+    done = []
+    for i in range(args.warmup + args.steps):
+        _, steps, busy = pool.run(tracks_per_core, sample_steps, seed=100 + 1000 * i)
+        if i >= args.warmup:
+            done.append((steps, busy))
+    pool.close()
+    value = sum(s for s, _ in done) / sum(b for _, b in done)
+    sample = (f"each bench step = {cores} processes x {tracks_per_core} track x {sample_steps} steps (UKF then URTSS, zero noise); "
+              "numpy oracle port calling the reference's own scipy.linalg.sqrtm / numpy.linalg.pinv")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(b for _, b in done), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, per_gpu_tracks=None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- #
+# helpers                                                                                     #
+# ------------------------------------------------------------------------------------------- #
+def workload_config(args, per_gpu_tracks):
+    return {
+        "workload": "configs[4]: synthetic 16M tracks x 1024 steps UKF+URTSS fp64, track-sharded; processed in resident tiles",
+        "steps_per_track": N_STEPS, "substeps": 1, "dt_hours": 1.0, "noise": "zero",
+        "tile_tracks_per_gpu": per_gpu_tracks, "job_tracks": 16 * 1024 * 1024,
+        "H": MODEL["H"], "R": MODEL["R"], "Q": MODEL["Q"], "P0": MODEL["P"],
+        "cache": "inputs+outputs per step are GBs (>> 126 MB L2); two input tiles alternate",
+        "parallelism": f"tracks sharded over {args.gpus} GPU(s), no data-path collective",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._thr = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thr.join(timeout=10)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------- #
+# GPU arm                                                                                      #
+# ------------------------------------------------------------------------------------------- #
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ship_track_estimators_b200 import _native as nat
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.sharding import local_summary, reduce_summary
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = nat.load()  # raises if the CUDA library is missing: no fallback
+    H, R, Q, P = (np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
+    ukf = BatchedUKF(H, Q, R, P)
+    T = args.tracks
+
+    # two resident input tiles (different seeds per rank and per tile) and one set of output buffers
+    tiles = []
+    for j in range(2):
+        syn = make_tracks(T, N_STEPS + 1, seed=1000 + 17 * rank + j, device=str(dev))
+        tiles.append(TrackBatch.from_synthetic(syn, substeps=1))
+        del syn
+    res = ukf.allocate(tiles[0], smoother=True, in_place=args.in_place)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    fwd_ms, bwd_ms = [], []
+
+    def step(i, record):
+        b = tiles[i % 2]
+        if record:
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            ukf.forward(b, res)
+            e1.record()
+            ukf.backward(b, res)
+            e2.record()
+            return e0, e1, e2
+        ukf.forward(b, res)
+        ukf.backward(b, res)
+        return None
+
+    for i in range(args.warmup):
+        step(i, False)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t_start, t_end = ev(), ev()
+        t_start.record()
+        marks = [step(args.warmup + i, True) for i in range(args.steps)]
+        t_end.record()
+        barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    for e0, e1, e2 in marks:
+        fwd_ms.append(e0.elapsed_time(e1))
+        bwd_ms.append(e1.elapsed_time(e2))
+    if world > 1:
+        tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        total_ms = float(tmax.item())
+
+    tile_steps = T * N_STEPS
+    value = world * tile_steps * args.steps / (total_ms * 1e-3)
+    summary = reduce_summary(local_summary(res, tile_steps * args.steps), device=dev)  # outside the timed region
+
+    # ---- end-to-end through the public API with host buffers (rank-local tile) ---- #
+    Te = args.e2e_tracks
+    syn = make_tracks(Te, N_STEPS + 1, seed=5000 + rank, device=str(dev))
+    host_batch = TrackBatch.from_synthetic(syn, substeps=1).pin_memory()
+    del syn
+    dev_res = ukf.allocate(host_batch.to(dev), smoother=True)
+    host_out = dev_res.host_like(pinned=True)
+    e2e_steps = max(2, min(args.steps, 3))
+    moved = ukf.run_host(host_batch, host_out, dev_res, device=dev)  # warm-up
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(e2e_steps):
+        moved = ukf.run_host(host_batch, host_out, dev_res, device=dev)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    if world > 1:
+        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tmax.item())
+    e2e_value = world * Te * N_STEPS * e2e_steps / (e2e_ms * 1e-3)
+    assert float(host_out.mean_s[0, 0, 0]) == float(dev_res.mean_s[0, 0, 0].item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        f_ms, b_ms = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
+        dominant = "urtss_backward_kernel" if b_ms >= f_ms else "ukf_forward_kernel"
+        dom_bytes, dom_ms = (BYTES_BWD, b_ms) if b_ms >= f_ms else (BYTES_FWD, f_ms)
+        achieved = dom_bytes * tile_steps / (dom_ms * 1e-3) / 1e9
+        step_gbs = (BYTES_FWD + BYTES_BWD) * tile_steps / ((f_ms + b_ms) * 1e-3) / 1e9
+        # FP64 pipe: probe the DFMA peak on this GPU, compare with the counted instructions
+        blocks, threads, iters = 148 * 16, 256, 20000
+        sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
+        nat.check(lib.ste_probe_fp64_fma(blocks, threads, 200, nat.ptr(sink), nat.current_stream()))
+        p0, p1 = ev(), ev()
+        p0.record()
+        nat.check(lib.ste_probe_fp64_fma(blocks, threads, iters, nat.ptr(sink), nat.current_stream()))
+        p1.record()
+        torch.cuda.synchronize()
+        fp64_peak = 2.0 * 8 * iters * blocks * threads / (p0.elapsed_time(p1) * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, T),
+            "roofline": {
+                "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_track_step": dom_bytes,
+                "kernel_ms": dom_ms, "forward_ms": f_ms, "backward_ms": b_ms,
+                "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_track_step": BYTES_FWD + BYTES_BWD},
+                "fp64_pipe": {"peak_tflops_measured": fp64_peak, "note": "DFMA probe (ste_probe_fp64_fma); see DESIGN.md for the per-step instruction counts"},
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"], "d2h_bytes_per_step": moved["d2h_bytes"],
+                    "tile_tracks": Te, "steps": e2e_steps, "outputs": "filtered+smoothed means and full 4x4 covariances to pinned host"},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks.summary(),
+            "summary": summary,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            pool = CpuPool(cores)
+            v, steps, busy = pool.run(args.cpu_tracks_per_core, N_STEPS, seed=4321)
+            pool.close()
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": (f"{cores} processes x {args.cpu_tracks_per_core} tracks x {N_STEPS} steps of the same synthetic workload (UKF then URTSS, "
+                           f"zero noise), numpy oracle port calling the reference's scipy/numpy routines: {steps} track-steps, slowest worker {busy:.1f} s"),
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tracks", type=int, default=148 * 128 * 8, help="tracks per resident tile per GPU")
+    ap.add_argument("--e2e-tracks", type=int, default=148 * 128, help="tracks of the host-buffer end-to-end tile")
+    ap.add_argument("--in-place", action="store_true", help="smooth in place (halves the state memory)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-tracks-per-core", type=int, default=16)
+    args = ap.parse_args()
+    if args.impl == "b200":
+        args.warmup = max(args.warmup, 3)  # timing rule: at least three warm-up steps
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

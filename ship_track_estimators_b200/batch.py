@@ -131,6 +131,29 @@ class TrackBatch:
             return int(self.n_steps.sum().item())
         return self.n_tracks * self.max_steps
 
+    _TENSORS = ("x0", "dt", "sog_rate", "cog_rate", "upd_mask", "n_steps", "rate_repeat", "P0",
+                "noise_pred", "noise_upd", "noise_bwd")
+
+    def _map(self, fn) -> "TrackBatch":
+        kw = {name: (None if getattr(self, name) is None else fn(getattr(self, name))) for name in self._TENSORS}
+        return TrackBatch(z=[None if r is None else fn(r) for r in self.z], substeps=self.substeps,
+                          rate_repeat_all=self.rate_repeat_all, n_steps_host=self.n_steps_host, **kw)
+
+    def to(self, device, non_blocking: bool = False) -> "TrackBatch":
+        """Copy of the tile on ``device`` (host->device copies are asynchronous from pinned memory)."""
+        return self._map(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self) -> "TrackBatch":
+        """Host tile in page-locked memory (the staging form for :meth:`BatchedUKF.run_host`)."""
+        return self._map(lambda t: t.cpu().pin_memory())
+
+    def input_bytes(self) -> int:
+        total = sum(r.numel() * r.element_size() for r in self.z if r is not None)
+        for name in self._TENSORS:
+            t = getattr(self, name)
+            total += 0 if t is None else t.numel() * t.element_size()
+        return int(total)
+
     # ------------------------------------------------------------------ #
     @classmethod
     def from_synthetic(cls, syn, substeps: int = 1, need_rows: Sequence[bool] = (True, True, False, False)):
@@ -258,6 +281,32 @@ class TrackResults:
     gate_scale: Optional[torch.Tensor] = None
     n_steps_host: Optional[np.ndarray] = None
 
+    _TENSORS = ("mean_f", "cov_f", "mean_s", "cov_s", "status", "n_updates", "gate_iters", "gate_lambda", "gate_scale")
+
+    def host_like(self, pinned: bool = True) -> "TrackResults":
+        """Empty host buffers of the same shapes (page-locked by default) for device->host copies."""
+        def mk(t):
+            if t is None:
+                return None
+            h = torch.empty(t.shape, dtype=t.dtype, device="cpu")
+            return h.pin_memory() if pinned else h
+        kw = {n: mk(getattr(self, n)) for n in self._TENSORS}
+        if self.mean_s is self.mean_f:
+            kw["mean_s"], kw["cov_s"] = kw["mean_f"], kw["cov_f"]
+        return TrackResults(n_steps_host=self.n_steps_host, **kw)
+
+    def copy_to(self, other: "TrackResults", non_blocking: bool = True) -> int:
+        """Copy every buffer into ``other`` (e.g. device -> pinned host); returns the bytes moved."""
+        moved, seen = 0, set()
+        for n in self._TENSORS:
+            src, dst = getattr(self, n), getattr(other, n)
+            if src is None or dst is None or dst.data_ptr() in seen:
+                continue
+            dst.copy_(src, non_blocking=non_blocking)
+            seen.add(dst.data_ptr())
+            moved += src.numel() * src.element_size()
+        return moved
+
     def track(self, i: int) -> Dict[str, np.ndarray]:
         """Host copies for one track in the reference's shapes: means (N+1, 4), covs (N+1, 4, 4)."""
         n = int(self.n_steps_host[i]) if self.n_steps_host is not None else self.mean_f.shape[0] - 1
@@ -370,6 +419,16 @@ class BatchedUKF:
         p, i, o = self._problem(b), self._inputs(b), self._outputs(res)
         with torch.cuda.device(b.device):
             nat.check(self._lib.ste_urtss_backward_f64(C.byref(p), C.byref(i), C.byref(o), nat.current_stream()))
+
+    def run_host(self, host_batch: TrackBatch, host_out: TrackResults, dev_res: TrackResults, smoother: bool = True,
+                 device="cuda") -> Dict[str, int]:
+        """End-to-end call on HOST buffers: pinned inputs -> device, forward (+ backward), results ->
+        pinned ``host_out``.  Asynchronous on the current stream; synchronise before reading
+        ``host_out``.  Returns the bytes copied in each direction."""
+        dev_batch = host_batch.to(device, non_blocking=True)
+        self.run(dev_batch, smoother=smoother, res=dev_res)
+        d2h = dev_res.copy_to(host_out, non_blocking=True)
+        return {"h2d_bytes": host_batch.input_bytes(), "d2h_bytes": d2h}
 
     def run(self, b: TrackBatch, smoother: bool = True, res: Optional[TrackResults] = None, in_place: bool = False) -> TrackResults:
         res = res if res is not None else self.allocate(b, smoother=smoother, in_place=in_place)

@@ -1,0 +1,249 @@
+"""GPU parity of the CUDA path (through the C ABI) against the numpy oracle on seeded synthetic
+tracks, the reference-style class API, and size-independent properties at BASELINE sizes."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from _helpers import GOLDEN, TOL, assert_track_close, cov_err, load_golden, mean_err
+
+pytestmark = pytest.mark.gpu
+
+H_POS = np.diag([1.0, 1.0, 0.0, 0.0])
+R_POS = np.diag([1e-3, 1e-3, 0.0, 0.0])
+Q_DEF = np.diag([1e-2, 1e-2, 1e-4, 1e-4])
+P_DEF = np.eye(4)
+
+
+def _oracle_track(syn, t, k, H, Q, R, P, gating=False, smoother=True):
+    from oracle import ukf_numpy as O
+
+    m = int(syn.nobs[t])
+    z = np.stack([syn.lon[:m, t].numpy(), syn.lat[:m, t].numpy(), syn.sog[:m, t].numpy(), syn.cog[:m, t].numpy()])
+    dts = syn.dts[: m - 1, t].numpy()
+    return O.run_track(z[:, 0], P, H, Q, R, O.generate_dts(dts, k), dts, z, syn.sog_rate[:m, t].numpy(),
+                       syn.cog_rate[:m, t].numpy(), smoother=smoother, gating=gating)
+
+
+@pytest.mark.parametrize("k,kwargs", [
+    (1, dict()),                                                     # C3/C5 shape: dt = 1, update every step
+    (2, dict(dts_choices=(1, 2, 3, 6))),                             # sub-steps
+    (2, dict(dts_choices=(1, 2, 3), nobs_min=20, smooth_width=2)),   # ragged + CLI box smoothing
+])
+def test_synthetic_against_oracle(k, kwargs, cuda, native_lib):
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T, nobs = 48, 61
+    syn = make_tracks(T, nobs, seed=21 + k, device="cpu", **kwargs)
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+    res = ukf.run(TrackBatch.from_synthetic(syn, substeps=k).to(cuda))
+    assert int((res.status & 1).sum().item()) == 0
+    for t in range(0, T, 4):
+        ref = _oracle_track(syn, t, k, H_POS, Q_DEF, R_POS, P_DEF)
+        got = res.track(t)
+        assert got["n_updates"] == int(syn.nobs[t])
+        # the oracle has no stored self-uncertainty: short-gap synthetic tracks are well conditioned
+        assert_track_close(got, ref, tol=TOL, label=f"k={k} track {t}", unc=np.zeros(4))
+
+
+def test_gated_synthetic_against_oracle(cuda, native_lib):
+    """C4 shape: outliers + Mahalanobis gating; decisions must match exactly."""
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T, nobs, k = 32, 50, 2
+    syn = make_tracks(T, nobs, seed=77, device="cpu", dts_choices=(1, 2, 3), nobs_min=25, outlier_frac=0.05, smooth_width=2)
+    R = np.diag([0.05, 0.05, 0.0, 0.0])
+    for force_generic in (False, True):
+        ukf = BatchedUKF(H_POS, Q_DEF, R, P_DEF, gating=True, force_generic=force_generic)
+        need = ukf.model.rows_needed()
+        res = ukf.run(TrackBatch.from_synthetic(syn, substeps=k, need_rows=need).to(cuda))
+        gated = 0
+        for t in range(0, T, 4):
+            ref = _oracle_track(syn, t, k, H_POS, Q_DEF, R, P_DEF, gating=True)
+            got = res.track(t)
+            assert np.array_equal(got["gate_iters"], ref["gate_iters"]), f"track {t} generic={force_generic}"
+            np.testing.assert_allclose(got["gate_lambda"], ref["gate_lambda"], rtol=1e-8)
+            gated += int((ref["gate_iters"] > 0).sum())
+            assert_track_close(got, ref, tol=1e-8, label=f"gated track {t}", unc=np.zeros(4))
+        assert gated > 0
+
+
+def test_class_api_matches_golden(cuda, native_lib):
+    """UnscentedKalmanFilter.run + run_rts_smoother (batch of one) on BASELINE config 1."""
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics
+
+    tracks, _ = load_golden("c1_single_ship")
+    for tr in tracks:
+        st = SimpleNamespace(dts=tr["dts"], z=tr["z"], sog_rate=tr["sog_rate"].copy(), cog_rate=tr["cog_rate"].copy(),
+                             sog=tr["z"][2], cog=tr["z"][3])
+        ukf = UnscentedKalmanFilter(H=tr["H"], Q=tr["Q"], R=tr["R"], P=tr["P0"], x0=tr["x0"].reshape(-1, 1),
+                                    non_linear_process=geodetic_dynamics, noise="zero")
+        means, covs = ukf.run(len(tr["dt_array"]), tr["dt_array"], st)
+        assert means.shape == tr["means"].shape and covs.shape == tr["covs"].shape
+        assert len(ukf.means) == len(tr["dt_array"]) + 1 and ukf.means[0].shape == (4, 1)
+        assert float(ukf.time) == float(np.cumsum(tr["dt_array"])[-1])
+        xs, Ps = ukf.run_rts_smoother(st)
+        assert_track_close(dict(means=means, covs=covs, means_s=xs, covs_s=Ps), tr, label="class API")
+        assert np.array_equal(st.sog_rate, tr["sog_rate"])  # not overwritten (documented difference)
+
+
+def test_class_api_seeded_noise_follows_numpy_stream(cuda, native_lib):
+    """With the same np.random.seed the class draws exactly what the reference draws: replaying the
+    golden noise tape through np.random.normal reproduces the reference's noisy run."""
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics
+
+    tracks, _ = load_golden("tape_noise")
+    tr = tracks[0]
+    N, mask = len(tr["dt_array"]), tr["mask"]
+    order = [tr["noise_upd"][0]]
+    u = 1
+    for s in range(N):
+        order.append(tr["noise_pred"][s])
+        if mask[s]:
+            order.append(tr["noise_upd"][u]); u += 1
+    order += list(tr["noise_bwd"][::-1])
+    queue = [np.asarray(v) for v in order]
+    orig = np.random.normal
+
+    def replay(loc=0.0, scale=1.0, size=None):
+        rows = size[0] if isinstance(size, tuple) else 1
+        out = np.stack([queue.pop(0) for _ in range(rows)])
+        return out if isinstance(size, tuple) else out[0]
+
+    np.random.normal = replay
+    try:
+        st = SimpleNamespace(dts=tr["dts"], z=tr["z"], sog_rate=tr["sog_rate"], cog_rate=tr["cog_rate"], sog=tr["z"][2], cog=tr["z"][3])
+        ukf = UnscentedKalmanFilter(H=tr["H"], Q=tr["Q"], R=tr["R"], P=tr["P0"], x0=tr["x0"], non_linear_process=geodetic_dynamics)
+        means, covs = ukf.run(N, tr["dt_array"], st)
+        xs, Ps = ukf.run_rts_smoother(st)
+    finally:
+        np.random.normal = orig
+    assert not queue
+    assert_track_close(dict(means=means, covs=covs, means_s=xs, covs_s=Ps), tr, label="seeded noise")
+
+
+def test_single_step_predict_update_against_oracle(cuda, native_lib):
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics
+
+    rng = np.random.default_rng(3)
+    for H, R in ((H_POS, R_POS), (np.eye(4), np.diag([1e-3, 2e-3, 4.0, 25.0]))):
+        A = rng.normal(size=(4, 4)) * 0.3
+        P = A @ A.T + np.diag([1e-3, 1e-3, 0.1, 0.5])
+        x = np.array([12.5, -33.0, 18.0, 275.0])
+        ukf = UnscentedKalmanFilter(H=H, Q=Q_DEF, R=R, P=P, x0=x, non_linear_process=geodetic_dynamics, noise="zero")
+        ukf.predict(dt=3.0, c=None, sog_rate=0.02, cog_rate=-0.4)
+        xr, Pr, X0, X1 = O.predict(x, P, Q_DEF, 3.0, 0.02, -0.4, O.ZeroNoise())
+        assert mean_err(ukf.x[:, 0][None], xr[None]) <= 1e-12 and cov_err(ukf.P[None], Pr[None]) <= 1e-11
+        assert np.max(np.abs(ukf.sigma_points_orig - X0)) <= 1e-11 and np.max(np.abs(ukf.sigma_points - X1)) <= 1e-10
+        z = np.array([12.9, -33.4, 17.0, 5.0])  # heading innovation wraps through 0/360
+        ukf.update(z.copy())
+        xu, Pu = O.update(xr, Pr, H, R, z.copy(), O.ZeroNoise())
+        assert mean_err(ukf.x[:, 0][None], xu[None]) <= 1e-11 and cov_err(ukf.P[None], Pu[None]) <= 1e-10
+        assert 0.0 <= ukf.x[3, 0] < 360.0
+
+
+def test_sigma_points_reference_unit_tests(cuda, native_lib):
+    """reference tests/test_unscented_kf.py:24-87 (n = 2) against the CUDA sigma-point kernel."""
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter
+
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        P = np.diag(rng.uniform(0, 1, 2))
+        x = rng.uniform(0, 1, 2).reshape(-1, 1)
+        ukf = UnscentedKalmanFilter(H=np.diag([1, 1]), P=P, x0=x)
+        ukf.compute_sigma_points()
+        assert np.all(np.isclose(ukf.x[:, 0], np.mean(ukf.sigma_points, axis=1)))
+        assert np.all(np.isclose(ukf.P, np.cov(ukf.sigma_points)))
+        ukf.compute_weights()
+        ukf.compute_sigma_points()
+        assert np.all(np.isclose(ukf.x[:, 0], np.sum(np.dot(ukf.sigma_points, ukf.weights), axis=1)))
+        res = ukf.sigma_points - ukf.x
+        assert np.all(np.isclose(ukf.P, np.dot(np.dot(res, ukf.weights), res.T)))
+
+
+def test_full_size_properties(cuda, native_lib):
+    """BASELINE track length (1024 steps): properties that need no oracle.
+    determinism; batch-composition invariance (a track's result does not depend on its neighbours);
+    in-place smoothing == out-of-place; generic path == position-only path; last smoothed state ==
+    last filtered state; symmetric covariances with positive variances; no status flags."""
+    import torch
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T, N = 4096, 1024
+    syn = make_tracks(T, N + 1, seed=99, device=str(cuda))
+    batch = TrackBatch.from_synthetic(syn, substeps=1)
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+    a = ukf.run(batch)
+    b = ukf.run(batch)
+    torch.cuda.synchronize()
+    for name in ("mean_f", "cov_f", "mean_s", "cov_s"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), f"{name} not deterministic"
+    assert int(a.status.abs().sum().item()) == 0
+    assert torch.equal(a.n_updates, torch.full_like(a.n_updates, N + 1))
+    assert torch.isfinite(a.mean_s).all() and torch.isfinite(a.cov_s).all()
+    assert torch.equal(a.mean_s[N], a.mean_f[N]) and torch.equal(a.cov_s[N], a.cov_f[N])
+    for C in (a.cov_f, a.cov_s):
+        M = C.view(N + 1, 4, 4, T)
+        assert torch.equal(M, M.transpose(1, 2))
+        assert (torch.diagonal(M, dim1=1, dim2=2) > 0).all()
+    # smoothing cannot increase the variance of the position estimate on these well-observed tracks
+    assert (a.cov_s[:, 0] <= a.cov_f[:, 0] * (1 + 1e-9)).all()
+    # in place
+    c = ukf.run(batch, in_place=True)
+    assert c.mean_s is c.mean_f
+    assert torch.equal(c.mean_s, a.mean_s) and torch.equal(c.cov_s, a.cov_s)
+    # a sub-batch (different grid, different neighbours in each warp) gives bit-identical tracks
+    sel = torch.arange(5, T, 37, device=cuda)
+    sub = batch._map(lambda t: t.index_select(-1, sel).contiguous() if t.shape[-1] == T else t)
+    d = ukf.run(sub)
+    assert torch.equal(d.mean_s, a.mean_s.index_select(-1, sel)) and torch.equal(d.cov_s, a.cov_s.index_select(-1, sel))
+    # generic update path (4x4 Jacobi pseudo-inverse) vs the position-only specialisation
+    g = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF, force_generic=True).run(sub)
+    scale = d.cov_s.abs().amax(dim=1, keepdim=True)
+    assert float(((g.cov_s - d.cov_s).abs() / scale).max()) <= 1e-9
+    dm = (g.mean_s - d.mean_s)
+    dm[:, 3] = torch.remainder(dm[:, 3] + 180.0, 360.0) - 180.0
+    assert float((dm.abs() / d.mean_s.abs().clamp(min=1.0)).max()) <= 1e-9
+
+
+def test_empty_and_degenerate_batches(cuda, native_lib):
+    """Edge cases: a track with a single observation (no steps), one step, ragged tiles where the
+    longest and shortest tracks differ, and an n_tracks == 0 launch through the raw ABI."""
+    import ctypes as C
+
+    from ship_track_estimators_b200 import _native as nat
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+
+    rng = np.random.default_rng(4)
+
+    def mk(nobs):
+        return SimpleNamespace(dts=np.ones(max(nobs - 1, 0)), z=np.stack([rng.uniform(-5, 5, nobs), rng.uniform(-5, 5, nobs),
+                               rng.uniform(5, 20, nobs), rng.uniform(0, 360, nobs)]), sog_rate=np.zeros(nobs), cog_rate=np.zeros(nobs))
+
+    tracks = [mk(2), mk(9), mk(3)]
+    dts = [np.ones(1), np.ones(8), np.ones(2)]
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+    res = ukf.run(TrackBatch.from_tracks(tracks, dts, device=cuda))
+    from oracle import ukf_numpy as O
+
+    for i, (tr, dt) in enumerate(zip(tracks, dts)):
+        ref = O.run_track(tr.z[:, 0], P_DEF, H_POS, Q_DEF, R_POS, dt, tr.dts, tr.z, tr.sog_rate, tr.cog_rate)
+        assert_track_close(res.track(i), ref, label=f"degenerate {i}", unc=np.zeros(4))
+    p, i_, o = nat.SteProblem(), nat.SteInputs(), nat.SteOutputs()
+    p.n_tracks, p.max_steps, p.max_obs, p.ld = 0, 0, 1, 0
+    import torch
+
+    dummy = torch.zeros(16, dtype=torch.float64, device=cuda)
+    i_.x0 = i_.dt = i_.sog_rate = i_.cog_rate = dummy.data_ptr()
+    i_.z[0] = i_.z[1] = dummy.data_ptr()
+    o.mean_f = o.cov_f = o.mean_s = o.cov_s = dummy.data_ptr()
+    o.status = torch.zeros(1, dtype=torch.int32, device=cuda).data_ptr()
+    p.H[0] = p.H[5] = 1.0
+    assert native_lib.ste_ukf_forward_f64(C.byref(p), C.byref(i_), C.byref(o), None) == 0
+    assert native_lib.ste_urtss_backward_f64(C.byref(p), C.byref(i_), C.byref(o), None) == 0

@@ -1,0 +1,108 @@
+"""CPU: pin the oracle (oracle/ukf_numpy.py) against the reference-generated golden vectors.
+
+The fixtures were produced by running the unmodified reference (tests/golden/make_golden.py);
+the numpy oracle calls the same scipy/numpy routines in the same order, so agreement is expected
+to the last few ulps (asserted at 1e-12, observed 0).  The reference's own unit-test identities
+(reference tests/test_unscented_kf.py:24-87) are restated for the oracle as well.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from _helpers import GOLDEN, cov_err, load_golden, mean_err
+from oracle import ukf_numpy as O
+
+STRICT = 1e-12
+FIXTURES = ["c1_single_ship", "c2_modern_ship", "c3_const_dt", "c4_ragged_ungated", "c4_ragged_gated", "tape_noise", "dense_h"]
+
+
+def _oracle_run(tr):
+    noise = None
+    if "noise_pred" in tr:
+        noise = O.TapeNoise(pred=tr["noise_pred"], upd=tr["noise_upd"], bwd=tr.get("noise_bwd"))
+    return O.run_track(tr["x0"], tr["P0"], tr["H"], tr["Q"], tr["R"], tr["dt_array"], tr["dts"], tr["z"],
+                       tr["sog_rate"], tr["cog_rate"], smoother="means_s" in tr, noise=noise, gating="gate_iters" in tr)
+
+
+def _check(tr, out, label):
+    assert np.array_equal(out["mask"], tr["mask"]), label
+    assert mean_err(out["means"], tr["means"]) <= STRICT, label
+    if "covs" in tr:
+        assert cov_err(out["covs"], tr["covs"]) <= STRICT, label
+    if "means_s" in tr:
+        assert mean_err(out["means_s"], tr["means_s"]) <= STRICT, label
+        if "covs_s" in tr:
+            assert cov_err(out["covs_s"], tr["covs_s"]) <= STRICT, label
+    if "gate_iters" in tr:
+        assert np.array_equal(out["gate_iters"], tr["gate_iters"]), label
+        np.testing.assert_allclose(out["gate_lambda"], tr["gate_lambda"], rtol=STRICT)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_matches_reference_fixture(name):
+    tracks, _ = load_golden(name)
+    for i, tr in enumerate(tracks):
+        _check(tr, _oracle_run(tr), f"{name}[{i}]")
+
+
+def test_oracle_matches_reference_historical_batch_sample():
+    """BASELINE config 2 (71 runnable historical ships): every 6th track keeps the CPU suite short."""
+    tracks, _ = load_golden("c2_historical_batch")
+    for i in range(0, len(tracks), 6):
+        _check(tracks[i], _oracle_run(tracks[i]), f"c2_historical_batch[{i}]")
+
+
+def test_building_block_known_answers():
+    d = np.load(os.path.join(GOLDEN, "kat_blocks.npz"))
+    for x, dt, sr, cr, ref in zip(d["geo_x"], d["geo_dt"], d["geo_sog_rate"], d["geo_cog_rate"], d["geo_out"]):
+        np.testing.assert_allclose(O.geodetic_dynamics(x, dt, sr, cr), ref, rtol=1e-14, atol=1e-13)
+    w0, wi = O.ut_weights(4)
+    W = d["weights"]
+    assert W[0, 0] == w0 and np.all(np.diag(W)[1:] == wi)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for x, P, X in zip(d["sp_x"], d["sp_P"], d["sp_X"]):
+            np.testing.assert_allclose(O.sigma_points(x, P, w0), X, rtol=1e-13, atol=1e-13)
+    # SURVEY section 9.3
+    np.testing.assert_allclose(
+        O.geodetic_dynamics(np.array([-30.5, -0.5, 14.5, 198.5]), 12.0, 0.01, -0.02),
+        [-30.99621056441692, -1.9822576603313298, 14.62, 198.26], rtol=1e-15)
+    assert w0 == -0.33333333333333326 and wi == 0.16666666666666666
+
+
+def test_gating_known_answers():
+    rows = np.load(os.path.join(GOLDEN, "kat_gating.npz"))["rows"]
+    H, R, P = np.diag([1.0, 1, 0, 0]), np.diag([0.25, 0.25, 0, 0]), np.diag([0.3, 0.3, 1, 1])
+    x = np.array([10.0, 20, 12, 90])
+    for d, iters, lam, scale in rows:
+        Rs, it, lm = O.check_robustness(x, x + np.array([d, -d, 0, 0]), P, H, R)
+        assert it == int(iters)
+        assert abs(lm - lam) <= 1e-12 * lam and abs(Rs[0, 0] / 0.25 - scale) <= 1e-12 * scale
+
+
+def test_reference_unit_test_identities():
+    """reference tests/test_unscented_kf.py: n = 2, sigma points recover (x, P) unweighted with
+    W0 = 0 (:24-39) and weighted with the default weights (:64-87); weights sum to 1 (:42-61)."""
+    rng = np.random.default_rng(7)
+    P = np.diag(rng.uniform(0, 1, 2))
+    x = rng.uniform(0, 1, 2)
+    X = O.sigma_points(x, P, 0.0)
+    assert np.allclose(x, X.mean(axis=1)) and np.allclose(P, np.cov(X))
+    w0, wi = O.ut_weights(2)
+    assert np.isclose(w0 + 4 * wi, 1.0) and -1 < w0 < 1
+    X = O.sigma_points(x, P, w0)
+    w = np.array([w0] + [wi] * 4)
+    assert np.allclose(x, (X * w).sum(axis=1))
+    dev = X - x[:, None]
+    assert np.allclose(P, (dev * w) @ dev.T)
+
+
+def test_update_mask_exact_equality():
+    """kalman_filter.py:101: k = 2, 4 re-sum exactly on integer-hour gaps, k = 3 / 7 mostly miss."""
+    dts = np.array([1.0, 2.0, 3.0, 6.0, 12.0, 24.0, 1.0, 3.0])
+    for k, expect_all in ((1, True), (2, True), (4, True), (3, False), (7, False)):
+        m = O.update_mask(O.generate_dts(dts, k), dts)
+        hits = m.reshape(-1, k)[:, -1]
+        assert (hits.all() and m.sum() == len(dts)) == expect_all
