@@ -148,6 +148,11 @@ int ste_sigma_points_f64(int32_t n, int32_t n_tracks, int64_t ld, double scale, 
 int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const double *dt,
                      const double *sog_rate, const double *cog_rate, double *x_out, void *stream);
 
+/* Test hook: evaluates the library's own fp64 elementary functions (csrc/ste_fastmath.cuh) on n
+ * arguments.  kind 0 sincos(a) -> (out0, out1); 1 atan2(a, b); 2 sqrt(a); 3 rsqrt(a); 4 1/a; 5 a/b. */
+int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b, double *out0,
+                       double *out1, void *stream);
+
 /* Measurement helper for the roofline report: runs `iters` dependent-free DFMA rounds on every
  * thread of `blocks` x `threads` and writes one double per thread to sink (device, blocks*threads).
  * FLOPs issued = 2 * 8 * iters * blocks * threads. */

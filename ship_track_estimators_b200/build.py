@@ -12,9 +12,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libste_ukf.so")
+LIB_PATH = os.environ.get("STE_UKF_LIB") or os.path.join(CSRC, "libste_ukf.so")  # env override: developer A/B builds
 SOURCES = ["ste_ukf.cu"]
-HEADERS = ["ste_math.cuh", "ste_filter.cuh", "ste_tracks.cuh", os.path.join("..", "..", "include", "ste_ukf.h")]
+HEADERS = ["ste_fastmath.cuh", "ste_math.cuh", "ste_filter.cuh", "ste_tracks.cuh", os.path.join("..", "..", "include", "ste_ukf.h")]
 
 NVCC_FLAGS = [
     "-O3",
@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``libste_ukf.so`` if missing or older than its sources; returns its path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("STE_EXTRA_NVCC_FLAGS", "").split()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     tmp = LIB_PATH + ".tmp"

@@ -16,6 +16,33 @@ struct Model {
     const double *R;   // [16]
 };
 
+// Per-thread scratch slots outside the register file (shared memory on the device, a plain
+// array in the host sandbox).  Slot k of this thread lives at base[k * stride].  It holds the
+// square-root factor so that the sigma-point loop can stay ROLLED (one instance of the
+// trigonometric code in the instruction cache) and index its columns at run time.
+struct Scratch {
+    double *base;
+    int stride;
+    STE_DEV double &at(int slot) const { return base[(long)slot * stride]; }
+};
+constexpr int kScratchRoot = 0;   // 16 slots: M[r][c] at kScratchRoot + c * 4 + r (column-major)
+constexpr int kScratchSlots = 16;
+
+STE_DEV void stash_root(const Scratch &sc, const double (&M)[10]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sc.at(kScratchRoot + c * 4 + r) = M[SYM(r, c)];
+}
+
+// offset of sigma point j from the mean: 0, +M[:,0..3], -M[:,0..3]  (unscented.py:100-105)
+STE_DEV void sigma_offset(const Scratch &sc, int j, double (&o)[4]) {
+    const int c = (j - 1) & 3;
+    const double sgn = (j == 0) ? 0.0 : (j <= 4 ? 1.0 : -1.0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) o[r] = sgn * sc.at(kScratchRoot + c * 4 + r);
+}
+
 // ------------------------------------------------------------------------------------------ //
 // predict (:144-207).  Unscented transform of (x, P) through the geodetic model.
 //
@@ -26,49 +53,47 @@ struct Model {
 // This needs no storage for the 9 propagated points.
 // ------------------------------------------------------------------------------------------ //
 STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, double dt,
-                                            double sog_rate, double cog_rate, const double (&e)[4],
-                                            int &status, double *sig_prior, double *sig_post, int64_t ld) {
-    double M[10];
-    if (sqrt_psd4(P, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
-    const double dtR = dt / kEarthRadiusKm;
-    double c[4];
-    geodetic_step(x, dt, dtR, sog_rate, cog_rate, c);
-    if (sig_prior) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            sig_prior[(r * 9) * ld] = x[r];
-            sig_post[(r * 9) * ld] = c[r];
-        }
+                         double sog_rate, double cog_rate, const double (&e)[4],
+                         int &status, const Scratch &sc, double *sig_prior, double *sig_post, int64_t ld) {
+    {
+        double M[10];
+        if (sqrt_psd4(P, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
+        stash_root(sc, M);
     }
+    const double dtR = dt / kEarthRadiusKm;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
     double s1[4] = {0.0, 0.0, 0.0, 0.0};
     double s2[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) s2[k] = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < 9; ++j) {
+        double xi[4], yi[4];
+        sigma_offset(sc, j, xi);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int sgn = 0; sgn < 2; ++sgn) {
-            double xi[4], yi[4], d[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) xi[r] = sgn ? x[r] - M[SYM(r, i)] : x[r] + M[SYM(r, i)];
-            geodetic_step(xi, dt, dtR, sog_rate, cog_rate, yi);
-            if (sig_prior) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    sig_prior[(r * 9 + 1 + i + 4 * sgn) * ld] = xi[r];
-                    sig_post[(r * 9 + 1 + i + 4 * sgn) * ld] = yi[r];
-                }
-            }
+        for (int r = 0; r < 4; ++r) xi[r] += x[r];
+        geodetic_step(xi, dt, dtR, sog_rate, cog_rate, yi);
+        if (sig_prior) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                d[r] = yi[r] - c[r];
-                s1[r] += d[r];
+                sig_prior[(r * 9 + j) * ld] = xi[r];
+                sig_post[(r * 9 + j) * ld] = yi[r];
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int q = r; q < 4; ++q) s2[SYM(r, q)] = fma(d[r], d[q], s2[SYM(r, q)]);
         }
+        if (j == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c[r] = yi[r];
+        }
+        double d[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            d[r] = yi[r] - c[r];
+            s1[r] += d[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = r; q < 4; ++q) s2[SYM(r, q)] = fma(d[r], d[q], s2[SYM(r, q)]);
     }
     double mu[4];
 #pragma unroll
@@ -313,54 +338,53 @@ STE_DEV void ukf_update_position(double (&x)[4], double (&P)[10], const Model &m
 // (xs, Ps) smoothed state at step + 1 on entry, at `step` on return.
 //   x_b  = xf + sum W_i d_i (+ e),      d_i = f(X_i) - xf
 //   P_b  = sum W_i d_i d_i^T + Q         (about the FILTERED mean: reference quirk, :324-325)
-//   D    = sum W_i (X_i - xf)(f(X_i) - x_b)^T = Wi * sum_i M[:,i] (f(X_i+) - f(X_i-))^T
-//          (X_0 - xf = 0 and the +/- pair cancels x_b exactly)
+//   D    = sum W_i (X_i - xf)(f(X_i) - x_b)^T = sum W_i (X_i - xf) d_i^T
+//          (sum W_i (X_i - xf) = 0, so the reference point of the second factor is immaterial)
 //   K = D pinv(P_b);  xs = xf + K wrap(xs - x_b);  Ps = Pf + K (Ps - P_b) K^T
 // ------------------------------------------------------------------------------------------ //
 STE_DEV void urtss_step(const double (&xf)[4], const double (&Pf)[10], double (&xs)[4],
-                                           double (&Ps)[10], const double *Q, double dt, double sog_rate,
-                                           double cog_rate, const double (&e)[4], int &status) {
-    double M[10];
-    if (sqrt_psd4(Pf, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
-    const double dtR = dt / kEarthRadiusKm;
-    double y0[4];
-    geodetic_step(xf, dt, dtR, sog_rate, cog_rate, y0);
-    double s1[4], Pb[10], D[16];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const double d = y0[r] - xf[r];
-        y0[r] = d;
-        s1[r] = kW0 * d;
+                        double (&Ps)[10], const double *Q, double dt, double sog_rate,
+                        double cog_rate, const double (&e)[4], int &status, const Scratch &sc) {
+    {
+        double M[10];
+        if (sqrt_psd4(Pf, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
+        stash_root(sc, M);
     }
+    const double dtR = dt / kEarthRadiusKm;
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, Pb[10], D[16];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = fma(kW0 * y0[r], y0[q], Q[r * 4 + q]);
+        for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = Q[r * 4 + q];
 #pragma unroll
     for (int k = 0; k < 16; ++k) D[k] = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < 9; ++j) {
+        double o[4], xi[4], d[4];
+        sigma_offset(sc, j, o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double xi[4], yp[4], ym[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xi[r] = xf[r] + M[SYM(r, i)];
-        geodetic_step(xi, dt, dtR, sog_rate, cog_rate, yp);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xi[r] = xf[r] - M[SYM(r, i)];
-        geodetic_step(xi, dt, dtR, sog_rate, cog_rate, ym);
+        for (int r = 0; r < 4; ++r) xi[r] = xf[r] + o[r];
+        geodetic_step(xi, dt, dtR, sog_rate, cog_rate, d);
+        const double w = (j == 0) ? kW0 : kWi;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const double diff = yp[r] - ym[r];
-            yp[r] -= xf[r];
-            ym[r] -= xf[r];
-            s1[r] = fma(kWi, yp[r] + ym[r], s1[r]);
+            d[r] -= xf[r];
+            s1[r] = fma(w, d[r], s1[r]);
+        }
+        // D += W_i (X_i - xf) d_i^T: sum_i W_i (X_i - xf) = 0, so subtracting x_b instead of xf
+        // from the propagated points (as the reference does, :328-330) changes nothing
 #pragma unroll
-            for (int q = 0; q < 4; ++q) D[q * 4 + r] = fma(kWi * M[SYM(q, i)], diff, D[q * 4 + r]);
+        for (int q = 0; q < 4; ++q) {
+            const double wo = w * o[q];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) D[q * 4 + r] = fma(wo, d[r], D[q * 4 + r]);
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r) {
+            const double wd = w * d[r];
 #pragma unroll
-            for (int q = r; q < 4; ++q)
-                Pb[SYM(r, q)] = fma(kWi * yp[r], yp[q], fma(kWi * ym[r], ym[q], Pb[SYM(r, q)]));
+            for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = fma(wd, d[q], Pb[SYM(r, q)]);
+        }
     }
     double Pbinv[10];
     if (pinv_sym4(Pb, Pbinv) > 0) status |= STE_STATUS_RANK_DEFICIENT;

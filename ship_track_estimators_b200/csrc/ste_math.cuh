@@ -11,27 +11,11 @@
 //   geodetic_dynamics    kalman_filters/non_linear_process.py:54-78 -> geodetic_step
 //   x % 360, wrap        kalman_filters/unscented.py:250,257,340,346 -> py_mod360, wrap180
 #pragma once
-#include <math.h>
-#if defined(__CUDACC__)
-#include <cuda_runtime.h>
-#define STE_DEV __host__ __device__ __forceinline__
-#define STE_HD __host__ __device__
-#else
-// plain C++ build: only the developer-side numerical sandbox (tools/host_emul) compiles this way;
-// the shipped library is always built by nvcc for sm_100a.
-#define STE_DEV inline
-#define STE_HD
-#endif
+// A plain C++ build of these headers exists only for the developer-side numerical sandbox
+// (tools/host_emul); the shipped library is always built by nvcc for sm_100a.
+#include "ste_fastmath.cuh"
 
 namespace ste {
-
-STE_DEV double rsqrt_f64(double v) {
-#if defined(__CUDA_ARCH__)
-    return rsqrt(v);
-#else
-    return 1.0 / sqrt(v);
-#endif
-}
 
 constexpr double kEarthRadiusKm = 6378.137;           // constants.py:1
 constexpr double kDegToRad = 0.017453292519943295;    // numpy radians(): x * (pi / 180)
@@ -71,10 +55,10 @@ STE_DEV void jacobi_rotate(double (&a)[10], double (&V)[16]) {
     // t = tan(rotation angle), the smaller root of t^2 + 2 theta t - 1 = 0, theta = (aqq-app)/(2apq)
     const double d = aqq - app;
     const double b = apq + apq;
-    const double h = sqrt(fma(d, d, b * b));
-    double t = (d >= 0.0 ? b : -b) / (fabs(d) + h);   // sign(d) * b / (|d| + sqrt(d^2 + b^2))
-    t = (apq == 0.0) ? 0.0 : t;                        // also covers d == b == 0 (0/0)
-    const double c = rsqrt_f64(fma(t, t, 1.0));
+    const double h = fast_sqrt(fma(d, d, b * b));
+    double t = fast_div(d >= 0.0 ? b : -b, fabs(d) + h);   // sign(d) * b / (|d| + sqrt(d^2 + b^2))
+    t = (apq == 0.0) ? 0.0 : t;                             // also covers d == b == 0 (0/0 -> NaN)
+    const double c = fast_rsqrt(fma(t, t, 1.0));
     const double s = t * c;
     a[SYM(P_, P_)] = fma(-t, apq, app);
     a[SYM(Q_, Q_)] = fma(t, apq, aqq);
@@ -149,7 +133,7 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         clamped |= (w[k] < -1e-13 * wmax);
-        f[k] = sqrt(fmax(w[k], 0.0));
+        f[k] = fast_sqrt(fmax(w[k], 0.0));
     }
     sym_from_eig(V, f, M);
     return clamped;
@@ -169,7 +153,7 @@ STE_DEV int pinv_sym4(const double (&A)[10], double (&Ainv)[10]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const bool keep = fabs(w[k]) > cut;
-        f[k] = keep ? 1.0 / w[k] : 0.0;
+        f[k] = keep ? fast_rcp(w[k]) : 0.0;
         dropped += keep ? 0 : 1;
     }
     sym_from_eig(V, f, Ainv);
@@ -182,15 +166,15 @@ STE_DEV int pinv_sym4(const double (&A)[10], double (&Ainv)[10]) {
 STE_DEV int pinv_sym2(double a, double b, double c, double (&inv)[3]) {
     const double d = c - a;
     const double bb = b + b;
-    const double h = sqrt(fma(d, d, bb * bb));
-    double t = (d >= 0.0 ? bb : -bb) / (fabs(d) + h);
+    const double h = fast_sqrt(fma(d, d, bb * bb));
+    double t = fast_div(d >= 0.0 ? bb : -bb, fabs(d) + h);
     t = (b == 0.0) ? 0.0 : t;
-    const double cs = rsqrt_f64(fma(t, t, 1.0));
+    const double cs = fast_rsqrt(fma(t, t, 1.0));
     const double sn = t * cs;
     const double w0 = fma(-t, b, a), w1 = fma(t, b, c);
     const double cut = kPinvRcond * fmax(fabs(w0), fabs(w1));
     const bool k0 = fabs(w0) > cut, k1 = fabs(w1) > cut;
-    const double f0 = k0 ? 1.0 / w0 : 0.0, f1 = k1 ? 1.0 / w1 : 0.0;
+    const double f0 = k0 ? fast_rcp(w0) : 0.0, f1 = k1 ? fast_rcp(w1) : 0.0;
     // eigenvectors: v0 = (c, -s), v1 = (s, c)
     inv[0] = fma(cs * f0, cs, sn * f1 * sn);
     inv[1] = fma(-cs * f0, sn, sn * f1 * cs);
@@ -201,22 +185,29 @@ STE_DEV int pinv_sym2(double a, double b, double c, double (&inv)[3]) {
 // ------------------------------------------------------------------------------------------ //
 // Process model: great-circle propagation on the sphere (non_linear_process.py:54-78).
 // dtR = dt / R_earth is hoisted by the caller (shared by the 9 sigma points of a step).
+//
+// The reference evaluates lat' = asin(s), s = sin(phi) cos(delta) + cos(phi) sin(delta) cos(alpha).
+// (east, north, s) is the unit vector of the new position in the frame of the old meridian, so
+// cos(lat') = hypot(east, north) and lat' = atan2(s, hypot(east, north)): the same angle, well
+// conditioned up to the poles, and it reuses the one-division atan2 (no separate asin code).
 // ------------------------------------------------------------------------------------------ //
 STE_DEV void geodetic_step(const double (&x)[4], double dt, double dtR, double sog_rate,
-                                              double cog_rate, double (&y)[4]) {
+                           double cog_rate, double (&y)[4]) {
     const double lam = x[0] * kDegToRad;
     const double phi = x[1] * kDegToRad;
     const double u = x[2];
     const double alpha = x[3] * kDegToRad;
     double sphi, cphi, sal, cal, sd, cd;
-    sincos(phi, &sphi, &cphi);
-    sincos(alpha, &sal, &cal);
-    sincos(u * dtR, &sd, &cd);
+    fast_sincos(phi, &sphi, &cphi);
+    fast_sincos(alpha, &sal, &cal);
+    fast_sincos(u * dtR, &sd, &cd);
     const double east = sd * sal;
     const double sdca = sd * cal;
     const double north = fma(cphi, cd, -sphi * sdca);
-    y[0] = (lam + atan2(east, north)) * kRadToDeg;
-    y[1] = asin(fma(sphi, cd, cphi * sdca)) * kRadToDeg;
+    const double up = fma(sphi, cd, cphi * sdca);
+    const double horiz = fast_sqrt(fma(east, east, north * north));
+    y[0] = (lam + fast_atan2(east, north)) * kRadToDeg;
+    y[1] = fast_atan2(up, horiz) * kRadToDeg;
     y[2] = fma(sog_rate, dt, u);
     y[3] = fma(cog_rate, dt, alpha * kRadToDeg);
 }

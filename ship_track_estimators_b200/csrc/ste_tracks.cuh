@@ -62,7 +62,7 @@ STE_DEV bool any_nonfinite(const double (&x)[4], const double (&P)[10]) {
 // Forward filter: KalmanFilterBase.run (kalman_filter.py:36-117).
 // ------------------------------------------------------------------------------------------ //
 template <bool POS_ONLY, bool GATING>
-STE_DEV void forward_track(const KernelArgs &a, const int t) {
+STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) {
     const int64_t ld = a.prob.ld;
     const int nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
     const Model model{a.prob.H, a.prob.Q, a.prob.R};
@@ -102,35 +102,32 @@ STE_DEV void forward_track(const KernelArgs &a, const int t) {
         }
     };
 
+    // Step -1 is the initial update with z[:, 0] (kalman_filter.py:81); steps 0..nt-1 predict and
+    // assimilate when the step ends on an observation time.  One rolled loop keeps a single
+    // instance of the predict and update code in the instruction cache.
     int ui = 0;
-    assimilate(0);  // kalman_filter.py:81
-
-    // inputs of step 0
     double dt = 0.0, sr = 0.0, cr = 0.0;
-    bool upd = false;
-    if (nt > 0) {
-        dt = a.in.dt[t];
-        sr = a.in.sog_rate[t];
-        cr = a.in.cog_rate[t];
-        upd = a.in.upd_mask ? (a.in.upd_mask[t] != 0) : (1 % k_sub == 0);
-    }
-    for (int s = 0; s < nt; ++s) {
-        double e[4] = {0.0, 0.0, 0.0, 0.0};
-        if (a.in.noise_pred) {
+    bool upd = true;
+#pragma unroll 1
+    for (int s = -1; s < nt; ++s) {
+        if (s >= 0) {
+            double e[4] = {0.0, 0.0, 0.0, 0.0};
+            if (a.in.noise_pred) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
-        }
-        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, nullptr, nullptr, ld);
-        const bool do_upd = upd;
-        if (do_upd) {
-            if (ui + 1 < a.prob.max_obs) {
-                ++ui;
-            } else {
-                status |= STE_STATUS_OBS_OVERRUN;
+                for (int r = 0; r < 4; ++r)
+                    e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
+            }
+            ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, ld);
+            if (upd) {
+                if (ui + 1 < a.prob.max_obs) {
+                    ++ui;
+                } else {
+                    status |= STE_STATUS_OBS_OVERRUN;
+                }
             }
         }
-        // prefetch the next step's inputs before the (long) update / store
+        const bool do_upd = upd;
+        // prefetch the next step's inputs before the update / store
         if (s + 1 < nt) {
             const int64_t o = (int64_t)(s + 1) * ld + t;
             dt = a.in.dt[o];
@@ -139,7 +136,7 @@ STE_DEV void forward_track(const KernelArgs &a, const int t) {
             cr = a.in.cog_rate[(int64_t)ui * ld + t];
         }
         if (do_upd) assimilate(ui);
-        store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, x, P);
+        if (s >= 0) store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, x, P);
     }
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
     a.out.status[t] = status;
@@ -149,7 +146,7 @@ STE_DEV void forward_track(const KernelArgs &a, const int t) {
 // ------------------------------------------------------------------------------------------ //
 // Backward smoother: UnscentedKalmanFilter.rts_step (unscented.py:267-351).
 // ------------------------------------------------------------------------------------------ //
-STE_DEV void backward_track(const KernelArgs &a, const int t) {
+STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc) {
     const int64_t ld = a.prob.ld;
     const int nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
     int rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
@@ -170,6 +167,7 @@ STE_DEV void backward_track(const KernelArgs &a, const int t) {
         cr = a.in.cog_rate[(int64_t)ri * ld + t];
     };
     if (nt > 0) fetch(nt - 1);
+#pragma unroll 1
     for (int step = nt - 1; step >= 0; --step) {
         double xc[4], Pc[10];
 #pragma unroll
@@ -184,7 +182,7 @@ STE_DEV void backward_track(const KernelArgs &a, const int t) {
                 e[r] = a.in.noise_bwd[((int64_t)step * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
         if (step > 0) fetch(step - 1);  // prefetch while this step computes
-        urtss_step(xc, Pc, xs, Ps, a.prob.Q, dtc, src, crc, e, status);
+        urtss_step(xc, Pc, xs, Ps, a.prob.Q, dtc, src, crc, e, status, sc);
         store_state(a.out.mean_s, a.out.cov_s, ld, step, t, xs, Ps);
     }
     if (any_nonfinite(xs, Ps)) status |= STE_STATUS_NONFINITE;

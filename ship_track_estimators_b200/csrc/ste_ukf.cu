@@ -14,16 +14,26 @@
 namespace ste {
 
 constexpr int kThreads = 128;
+// Minimum resident blocks per SM the register allocator must make room for (occupancy is bounded by
+// registers only: these kernels use 16 KB of shared memory per block and almost no bandwidth).
+#ifndef STE_FWD_MIN_BLOCKS
+#define STE_FWD_MIN_BLOCKS 4
+#endif
+#ifndef STE_BWD_MIN_BLOCKS
+#define STE_BWD_MIN_BLOCKS 4
+#endif
 
 template <bool POS_ONLY, bool GATING>
-__global__ void __launch_bounds__(kThreads) ukf_forward_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kThreads, STE_FWD_MIN_BLOCKS) ukf_forward_kernel(const __grid_constant__ KernelArgs a) {
+    __shared__ double scratch[kScratchSlots * kThreads];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t);
+    if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
 
-__global__ void __launch_bounds__(kThreads) urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kThreads, STE_BWD_MIN_BLOCKS) urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
+    __shared__ double scratch[kScratchSlots * kThreads];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < a.prob.n_tracks) backward_track(a, t);
+    if (t < a.prob.n_tracks) backward_track(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -71,7 +81,8 @@ __global__ void __launch_bounds__(kThreads) ukf_predict_kernel(const __grid_cons
         for (int r = 0; r < 4; ++r) e[r] = a.noise[r * ld + t] * sqrt(a.prob.Q[r * 5]);
     }
     int status = 0;
-    ukf_predict(x, P, a.prob.Q, a.dt[t], a.sog_rate[t], a.cog_rate[t], e, status,
+    __shared__ double scratch[kScratchSlots * kThreads];
+    ukf_predict(x, P, a.prob.Q, a.dt[t], a.sog_rate[t], a.cog_rate[t], e, status, Scratch{scratch + threadIdx.x, kThreads},
                 a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, ld);
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
     store_xP(a, t, x, P);
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) sigma_points_kernel(int n, int T, in
                 if (apq == 0.0) continue;
                 const double d = A[q * 8 + q] - A[p * 8 + p], b = apq + apq;
                 const double tt = (d >= 0.0 ? b : -b) / (fabs(d) + sqrt(fma(d, d, b * b)));
-                const double c = rsqrt_f64(fma(tt, tt, 1.0)), s = tt * c;
+                const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
                 for (int r = 0; r < n; ++r) {  // columns p, q of A and V
                     const double arp = A[r * 8 + p], arq = A[r * 8 + q];
                     A[r * 8 + p] = fma(c, arp, -s * arq);
@@ -188,6 +199,24 @@ __global__ void __launch_bounds__(kThreads) geodetic_kernel(int T, int64_t ld, c
     geodetic_step(x, d, d / kEarthRadiusKm, sog_rate[t], cog_rate[t], y);
 #pragma unroll
     for (int r = 0; r < 4; ++r) xout[r * ld + t] = y[r];
+}
+
+// accuracy probe for ste_fastmath.cuh (tests only): out0/out1 = f(a, b)
+__global__ void fastmath_probe_kernel(int kind, int n, const double *a, const double *b, double *out0, double *out1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r0 = 0.0, r1 = 0.0;
+    switch (kind) {
+        case 0: fast_sincos(a[i], &r0, &r1); break;
+        case 1: r0 = fast_atan2(a[i], b[i]); break;
+        case 2: r0 = fast_sqrt(a[i]); break;
+        case 3: r0 = fast_rsqrt(a[i]); break;
+        case 4: r0 = fast_rcp(a[i]); break;
+        case 5: r0 = fast_div(a[i], b[i]); break;
+        default: break;
+    }
+    out0[i] = r0;
+    out1[i] = r1;
 }
 
 __global__ void fp64_fma_probe_kernel(int iters, double *sink) {
@@ -373,6 +402,13 @@ int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const dou
     const dim3 grid((n_tracks + kThreads - 1) / kThreads), block(kThreads);
     geodetic_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_tracks, ld, x_in, dt, sog_rate, cog_rate, x_out);
     return check_launch("geodetic_kernel");
+}
+
+int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b, double *out0, double *out1, void *stream) {
+    if (kind < 0 || kind > 5 || n < 0 || !a || !b || !out0 || !out1) return fail(STE_ERR_INVALID_ARG, "bad fastmath probe arguments");
+    if (n == 0) return STE_OK;
+    fastmath_probe_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kind, n, a, b, out0, out1);
+    return check_launch("fastmath_probe_kernel");
 }
 
 int ste_probe_fp64_fma(int32_t blocks, int32_t threads, int32_t iters, double *sink, void *stream) {

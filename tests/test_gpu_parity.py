@@ -247,3 +247,49 @@ def test_empty_and_degenerate_batches(cuda, native_lib):
     p.H[0] = p.H[5] = 1.0
     assert native_lib.ste_ukf_forward_f64(C.byref(p), C.byref(i_), C.byref(o), None) == 0
     assert native_lib.ste_urtss_backward_f64(C.byref(p), C.byref(i_), C.byref(o), None) == 0
+
+
+def test_fastmath_accuracy(cuda, native_lib):
+    """The kernels' own fp64 elementary functions (csrc/ste_fastmath.cuh) against numpy, in ulps,
+    over the argument ranges the filter produces (and well beyond)."""
+    import torch
+
+    from ship_track_estimators_b200 import _native as nat
+
+    rng = np.random.default_rng(11)
+    n = 1 << 18
+
+    def run(kind, a, b=None):
+        b = a if b is None else b
+        ad, bd = (torch.from_numpy(np.ascontiguousarray(v)).to(cuda) for v in (a, b))
+        o0, o1 = torch.empty_like(ad), torch.empty_like(ad)
+        nat.check(native_lib.ste_probe_fastmath(kind, len(a), nat.ptr(ad), nat.ptr(bd), nat.ptr(o0), nat.ptr(o1), nat.current_stream()))
+        return o0.cpu().numpy(), o1.cpu().numpy()
+
+    def ulps(got, ref):
+        return np.max(np.abs(got - ref) / np.spacing(np.maximum(np.abs(ref), 1e-300)))
+
+    x = np.concatenate([rng.uniform(-10, 10, n), rng.uniform(-1e-3, 1e-3, n), rng.uniform(-1e5, 1e5, n), [0.0, np.pi / 2, -np.pi, 1e-300]])
+    s, c = run(0, x)
+    # absolute error relative to 1 ulp of the larger of |sin|, |cos| (both are computed from one reduction)
+    assert np.max(np.abs(s - np.sin(x))) <= 2.5e-16 and np.max(np.abs(c - np.cos(x))) <= 2.5e-16
+    small = np.abs(x) < 1.0
+    assert ulps(s[small], np.sin(x[small])) <= 2.0 and ulps(c[small], np.cos(x[small])) <= 2.0
+    big = np.array([1e6, -3e9, 1e22, np.inf, np.nan])
+    s, c = run(0, big)
+    np.testing.assert_allclose(s[:3], np.sin(big[:3]), rtol=1e-14)
+    assert np.isnan(s[3:]).all() and np.isnan(c[3:]).all()
+    yy = np.concatenate([rng.normal(size=n), rng.normal(size=n) * 1e-6, rng.normal(size=n), [0.0, 0.0, 1.0, -1.0, 0.0, -0.0]])
+    xx = np.concatenate([rng.normal(size=n), rng.normal(size=n), rng.normal(size=n) * 1e-6, [1.0, -1.0, 0.0, 0.0, 0.0, -1.0]])
+    got, _ = run(1, yy, xx)
+    ref = np.arctan2(yy, xx)
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) <= 4.5e-16
+    assert np.array_equal(np.signbit(got), np.signbit(ref))
+    pos = np.concatenate([rng.uniform(1e-12, 1e6, n), 10.0 ** rng.uniform(-200, 200, n)])
+    assert ulps(run(2, pos)[0], np.sqrt(pos)) <= 1.0
+    assert run(2, np.array([0.0]))[0][0] == 0.0
+    assert ulps(run(3, pos)[0], 1.0 / np.sqrt(pos)) <= 2.0
+    sgn = pos * rng.choice([-1.0, 1.0], len(pos))
+    assert ulps(run(4, sgn)[0], 1.0 / sgn) <= 1.5
+    num = rng.normal(size=len(pos))
+    assert ulps(run(5, num, sgn)[0], num / sgn) <= 1.0

@@ -18,9 +18,11 @@ extern "C" int emul_forward(const SteProblem *prob, const SteInputs *in, SteOutp
             if ((i >= 2 || j >= 2) && prob->R[i * 4 + j] != 0.0) pos = false;
         }
     const bool gating = prob->flags & STE_FLAG_GATING;
+    double scratch[kScratchSlots];
+    const Scratch sc{scratch, 1};
     for (int t = 0; t < prob->n_tracks; ++t) {
-        if (pos) { if (gating) forward_track<true, true>(a, t); else forward_track<true, false>(a, t); }
-        else     { if (gating) forward_track<false, true>(a, t); else forward_track<false, false>(a, t); }
+        if (pos) { if (gating) forward_track<true, true>(a, t, sc); else forward_track<true, false>(a, t, sc); }
+        else     { if (gating) forward_track<false, true>(a, t, sc); else forward_track<false, false>(a, t, sc); }
     }
     return 0;
 }
@@ -28,6 +30,8 @@ extern "C" int emul_forward(const SteProblem *prob, const SteInputs *in, SteOutp
 extern "C" int emul_backward(const SteProblem *prob, const SteInputs *in, SteOutputs *out) {
     KernelArgs a;
     a.prob = *prob; a.in = *in; a.out = *out;
-    for (int t = 0; t < prob->n_tracks; ++t) backward_track(a, t);
+    double scratch[kScratchSlots];
+    const Scratch sc{scratch, 1};
+    for (int t = 0; t < prob->n_tracks; ++t) backward_track(a, t, sc);
     return 0;
 }
