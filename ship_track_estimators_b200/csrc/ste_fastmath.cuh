@@ -18,9 +18,11 @@
 #include <cuda_runtime.h>
 #define STE_DEV __host__ __device__ __forceinline__
 #define STE_HD __host__ __device__
+#define STE_COLD __host__ __device__ __noinline__
 #else
 #define STE_DEV inline
 #define STE_HD
+#define STE_COLD __attribute__((noinline)) inline
 #endif
 
 #if defined(__CUDACC__)

@@ -35,12 +35,35 @@ STE_DEV void stash_root(const Scratch &sc, const double (&M)[10]) {
         for (int r = 0; r < 4; ++r) sc.at(kScratchRoot + c * 4 + r) = M[SYM(r, c)];
 }
 
-// offset of sigma point j from the mean: 0, +M[:,0..3], -M[:,0..3]  (unscented.py:100-105)
-STE_DEV void sigma_offset(const Scratch &sc, int j, double (&o)[4]) {
-    const int c = (j - 1) & 3;
-    const double sgn = (j == 0) ? 0.0 : (j <= 4 ? 1.0 : -1.0);
+// The rolled sigma-point loop visits the points in the order x, x+m_0, x-m_0, x+m_1, ... so that
+// the sincos of an offset column is computed once and reused by its mirror point.
+//   j = 0: centre;  j = 2c+1: x + m_c;  j = 2c+2: x - m_c
+// sigma_ref_index maps j to the reference's column index (unscented.py:100-105: X[:, 1+c] = x + m_c,
+// X[:, 5+c] = x - m_c).
+STE_DEV int sigma_ref_index(int j) { return j == 0 ? 0 : ((j & 1) ? 1 + (j >> 1) : 4 + (j >> 1)); }
+
+// Propagate sigma point j of (x, root in scratch).  `base` / `off` persist across iterations:
+// base = trig of the centre angles, off = trig of the current offset column.
+// o receives X_j - x, y the propagated point.
+STE_DEV void propagate_sigma(const Scratch &sc, int j, const double (&x)[4], double dt, double dtR, double sog_rate,
+                             double cog_rate, AngleTrig &base, AngleTrig &off, double (&o)[4], double (&xi)[4],
+                             double (&y)[4]) {
+    const bool plus = (j & 1) || j == 0;
+    const int c = (j - 1) >> 1;
+    double m[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) o[r] = sgn * sc.at(kScratchRoot + c * 4 + r);
+    for (int r = 0; r < 4; ++r) m[r] = (j == 0) ? x[r] : sc.at(kScratchRoot + c * 4 + r);
+    if (plus) off = angle_trig(m[1], m[3], m[2], dtR);   // centre angles at j = 0, offset column otherwise
+    // j = 0: base is still the zero angle (sin 0, cos 1), so base (+) off == off exactly and becomes
+    // the centre trig; afterwards base stays fixed and off cycles through the columns.
+    const AngleTrig cur = angle_add(base, off, plus);
+    if (j == 0) base = cur;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        o[r] = (j == 0) ? 0.0 : (plus ? m[r] : -m[r]);
+        xi[r] = x[r] + o[r];
+    }
+    geodetic_finish(xi, cur, dt, sog_rate, cog_rate, y);
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -66,18 +89,17 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
     double s2[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) s2[k] = 0.0;
+    AngleTrig base = {0.0, 1.0, 0.0, 1.0, 0.0, 1.0}, off = base;
 #pragma unroll 1
     for (int j = 0; j < 9; ++j) {
-        double xi[4], yi[4];
-        sigma_offset(sc, j, xi);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xi[r] += x[r];
-        geodetic_step(xi, dt, dtR, sog_rate, cog_rate, yi);
+        double o[4], xi[4], yi[4];
+        propagate_sigma(sc, j, x, dt, dtR, sog_rate, cog_rate, base, off, o, xi, yi);
         if (sig_prior) {
+            const int jr = sigma_ref_index(j);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                sig_prior[(r * 9 + j) * ld] = xi[r];
-                sig_post[(r * 9 + j) * ld] = yi[r];
+                sig_prior[(r * 9 + jr) * ld] = xi[r];
+                sig_post[(r * 9 + jr) * ld] = yi[r];
             }
         }
         if (j == 0) {
@@ -334,50 +356,53 @@ STE_DEV void ukf_update_position(double (&x)[4], double (&P)[10], const Model &m
 }
 
 // ------------------------------------------------------------------------------------------ //
-// One URTSS backward iteration (rts_step, :297-349).  (xf, Pf) filtered state at `step`,
-// (xs, Ps) smoothed state at step + 1 on entry, at `step` on return.
-//   x_b  = xf + sum W_i d_i (+ e),      d_i = f(X_i) - xf
-//   P_b  = sum W_i d_i d_i^T + Q         (about the FILTERED mean: reference quirk, :324-325)
-//   D    = sum W_i (X_i - xf)(f(X_i) - x_b)^T = sum W_i (X_i - xf) d_i^T
-//          (sum W_i (X_i - xf) = 0, so the reference point of the second factor is immaterial)
-//   K = D pinv(P_b);  xs = xf + K wrap(xs - x_b);  Ps = Pf + K (Ps - P_b) K^T
+// One URTSS backward iteration (rts_step, :297-349), in two phases so that the long sigma-point
+// loop runs with few live registers:
+//
+//  phase 1  urtss_moments   sigma points of the filtered state (xf, Pf) -> weighted sums
+//      x_b - xf = sum W_i d_i,            d_i = f(X_i) - xf
+//      P_b      = sum W_i d_i d_i^T + Q   (about the FILTERED mean: reference quirk, :324-325)
+//      Delta_c  = d(x + m_c) - d(x - m_c) (c = 0..3, parked in scratch)
+//  phase 2  urtss_gain      cross covariance, gain and the smoothed state
+//      D = sum W_i (X_i - xf)(f(X_i) - x_b)^T = Wi sum_c m_c Delta_c^T
+//          (X_0 - xf = 0 and sum W_i (X_i - xf) = 0, so neither x_b nor the centre point enters)
+//      K = D pinv(P_b) = Wi sum_c m_c (pinv(P_b) Delta_c)^T
+//      xs = xf + K wrap(xs - x_b);   Ps = Pf + K (Ps - P_b) K^T
+//
+// The smoothed state of step+1 (xs, Ps) is only touched in phase 2 and lives in scratch between
+// steps; Pf is re-read by the caller for phase 2 instead of being held across phase 1.
 // ------------------------------------------------------------------------------------------ //
-STE_DEV void urtss_step(const double (&xf)[4], const double (&Pf)[10], double (&xs)[4],
-                        double (&Ps)[10], const double *Q, double dt, double sog_rate,
-                        double cog_rate, const double (&e)[4], int &status, const Scratch &sc) {
+constexpr int kScratchXs = 16;      // 4 slots
+constexpr int kScratchPs = 20;      // 10 slots
+constexpr int kScratchDelta = 30;   // 16 slots: Delta_c[r] at kScratchDelta + c * 4 + r
+constexpr int kScratchSlotsBwd = 46;
+
+STE_DEV void urtss_moments(const double (&xf)[4], const double (&Pf)[10], const double *Q, double dt,
+                           double sog_rate, double cog_rate, double (&s1)[4], double (&Pb)[10], int &status,
+                           const Scratch &sc) {
     {
         double M[10];
         if (sqrt_psd4(Pf, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
         stash_root(sc, M);
     }
     const double dtR = dt / kEarthRadiusKm;
-    double s1[4] = {0.0, 0.0, 0.0, 0.0}, Pb[10], D[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s1[r] = 0.0;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = Q[r * 4 + q];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) D[k] = 0.0;
+    AngleTrig base = {0.0, 1.0, 0.0, 1.0, 0.0, 1.0}, off = base;
+    double dplus[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
     for (int j = 0; j < 9; ++j) {
         double o[4], xi[4], d[4];
-        sigma_offset(sc, j, o);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xi[r] = xf[r] + o[r];
-        geodetic_step(xi, dt, dtR, sog_rate, cog_rate, d);
+        propagate_sigma(sc, j, xf, dt, dtR, sog_rate, cog_rate, base, off, o, xi, d);
         const double w = (j == 0) ? kW0 : kWi;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             d[r] -= xf[r];
             s1[r] = fma(w, d[r], s1[r]);
-        }
-        // D += W_i (X_i - xf) d_i^T: sum_i W_i (X_i - xf) = 0, so subtracting x_b instead of xf
-        // from the propagated points (as the reference does, :328-330) changes nothing
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double wo = w * o[q];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) D[q * 4 + r] = fma(wo, d[r], D[q * 4 + r]);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -385,19 +410,47 @@ STE_DEV void urtss_step(const double (&xf)[4], const double (&Pf)[10], double (&
 #pragma unroll
             for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = fma(wd, d[q], Pb[SYM(r, q)]);
         }
+        if (j & 1) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dplus[r] = d[r];
+        } else if (j > 0) {
+            const int c = (j - 1) >> 1;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) sc.at(kScratchDelta + c * 4 + r) = dplus[r] - d[r];
+        }
     }
+}
+
+STE_DEV void urtss_gain(const double (&xf)[4], const double (&Pf)[10], const double (&s1)[4], const double (&Pb)[10],
+                        const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status, const Scratch &sc) {
     double Pbinv[10];
-    if (pinv_sym4(Pb, Pbinv) > 0) status |= STE_STATUS_RANK_DEFICIENT;
+    if (pinv_spd4(Pb, Pbinv) > 0) status |= STE_STATUS_RANK_DEFICIENT;
     double K[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 16; ++k) K[k] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double dl[4], v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) dl[r] = sc.at(kScratchDelta + c * 4 + r);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc = fma(D[i * 4 + k], Pbinv[SYM(k, j)], acc);
-            K[i * 4 + j] = acc;
+            for (int k = 0; k < 4; ++k) acc = fma(Pbinv[SYM(j, k)], dl[k], acc);
+            v[j] = acc;
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double wm = kWi * sc.at(kScratchRoot + c * 4 + i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) K[i * 4 + j] = fma(wm, v[j], K[i * 4 + j]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xs[r] = sc.at(kScratchXs + r);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) Ps[k] = sc.at(kScratchPs + k);
     double y[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) y[r] = xs[r] - (xf[r] + (s1[r] + e[r]));
@@ -411,16 +464,16 @@ STE_DEV void urtss_step(const double (&xf)[4], const double (&Pf)[10], double (&
     }
     xs[3] = py_mod360(xs[3]);  // :346
     // Ps <- Pf + K (Ps - Pb) K^T
-    double G[10], KG[16];
+    double KG[16];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) G[k] = Ps[k] - Pb[k];
+    for (int k = 0; k < 10; ++k) Ps[k] -= Pb[k];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc = fma(K[i * 4 + k], G[SYM(k, j)], acc);
+            for (int k = 0; k < 4; ++k) acc = fma(K[i * 4 + k], Ps[SYM(k, j)], acc);
             KG[i * 4 + j] = acc;
         }
 #pragma unroll
@@ -432,6 +485,10 @@ STE_DEV void urtss_step(const double (&xf)[4], const double (&Pf)[10], double (&
             for (int k = 0; k < 4; ++k) acc = fma(KG[i * 4 + k], K[j * 4 + k], acc);
             Ps[SYM(i, j)] = acc;
         }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sc.at(kScratchXs + r) = xs[r];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sc.at(kScratchPs + k) = Ps[k];
 }
 
 }  // namespace ste

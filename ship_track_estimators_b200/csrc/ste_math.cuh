@@ -79,12 +79,21 @@ STE_DEV void jacobi_rotate(double (&a)[10], double (&V)[16]) {
     }
 }
 
-STE_DEV void jacobi_eig4(double (&a)[10], double (&V)[16]) {
+// tol2: a pair (p,q) counts as converged when a_pq^2 <= tol2 |a_pp a_qq| (keeps the small
+// eigen-directions of badly scaled covariances accurate) or a_pq is negligible against the whole
+// matrix.  kJacobiTight drives the off-diagonals to rounding level; kJacobiLoose stops about one
+// sweep earlier and relies on the caller's first-order correction (sqrt_psd4).
+constexpr double kJacobiTight = 1e-33;
+constexpr double kJacobiLoose = 1e-17;
+
+template <bool INIT>
+STE_DEV void jacobi_eig4(double (&a)[10], double (&V)[16], double tol2) {
+    if (INIT) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    // Quadratic convergence: 4x4 matrices reach off ~ 1e-17 |A| in 4-6 sweeps.
-    // A pair (p,q) is converged when a_pq is negligible against sqrt(a_pp a_qq) (keeps the small
-    // eigen-directions of badly scaled covariances accurate) or against the whole matrix.
+        for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    }
+    // Quadratic convergence: nearly diagonal covariances need 2-3 sweeps.
+#pragma unroll 1
     for (int sweep = 0; sweep < 12; ++sweep) {
         const double dia = a[0] * a[0] + a[4] * a[4] + a[7] * a[7] + a[9] * a[9];
         const double floor2 = 1e-40 * dia;
@@ -94,7 +103,7 @@ STE_DEV void jacobi_eig4(double (&a)[10], double (&V)[16]) {
 #pragma unroll
             for (int q = p + 1; q < 4; ++q) {
                 const double o2 = a[SYM(p, q)] * a[SYM(p, q)];
-                more |= (o2 > 1e-33 * fabs(a[SYM(p, p)] * a[SYM(q, q)])) && (o2 > floor2);
+                more |= (o2 > tol2 * fabs(a[SYM(p, p)] * a[SYM(q, q)])) && (o2 > floor2);
             }
         if (!more) break;   // also leaves on NaN
         jacobi_rotate<0, 1>(a, V);
@@ -119,14 +128,39 @@ STE_DEV void sym_from_eig(const double (&V)[16], const double (&f)[4], double (&
         }
 }
 
-// M = Re sqrtm(scale * A): principal square root with negative eigenvalues contributing 0
-// (scipy returns a complex root there and numpy's float assignment drops the imaginary part,
-// unscented.py:104-105).  Returns true if a negative eigenvalue was clamped.
-STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
-    double a[10], V[16], f[4];
+// out = V S V^T for a symmetric middle matrix S (10 entries)
+STE_DEV void sym_congruence(const double (&V)[16], const double (&S)[10], double (&out)[10]) {
+    double T[16];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) a[i] = A[i] * scale;
-    jacobi_eig4(a, V);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) acc = fma(V[i * 4 + l], S[SYM(l, k)], acc);
+            T[i * 4 + k] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fma(T[i * 4 + k], V[j * 4 + k], acc);
+            out[SYM(i, j)] = acc;
+        }
+}
+
+// Rare continuation of sqrt_psd4 for (near-)singular or indefinite matrices: finish the Jacobi
+// iteration to rounding level and take the root of the clamped spectrum.  Kept out of line so the
+// hot loop stays small in the instruction cache.
+STE_COLD bool sqrt_psd4_finish(double *a_io, double *V_io, double *M_out) {
+    double a[10], V[16], f[4], M[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = a_io[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) V[i] = V_io[i];
+    jacobi_eig4<false>(a, V, kJacobiTight);
     const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
     const double wmax = fmax(fmax(fabs(w[0]), fabs(w[1])), fmax(fabs(w[2]), fabs(w[3])));
     bool clamped = false;
@@ -136,7 +170,40 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
         f[k] = fast_sqrt(fmax(w[k], 0.0));
     }
     sym_from_eig(V, f, M);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) M_out[i] = M[i];
     return clamped;
+}
+
+// M = Re sqrtm(scale * A): principal square root with negative eigenvalues contributing 0
+// (scipy returns a complex root there and numpy's float assignment drops the imaginary part,
+// unscented.py:104-105).  Returns true if a negative eigenvalue was clamped.
+//
+// Positive definite case (every filter step of a healthy track): Jacobi runs only until the
+// rotated matrix A' = V^T A V = D + E has |E_ij| <= ~3e-9 sqrt(d_i d_j); the root of D + E is then
+// sqrt(D) + X with X_ij = E_ij / (sqrt d_i + sqrt d_j) up to O(|E|^2) ~ 1e-17 relative (the
+// first-order Sylvester correction), which saves the last Jacobi sweep.
+STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
+    double a[10], V[16];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = A[i] * scale;
+    jacobi_eig4<true>(a, V, kJacobiLoose);
+    const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
+    const double wmax = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
+    const double wmin = fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
+    if (!(wmin > 1e-12 * wmax)) return sqrt_psd4_finish(a, V, M);
+    double S[10], s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s[k] = fast_sqrt(w[k]);
+        S[SYM(k, k)] = s[k];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) S[SYM(i, j)] = a[SYM(i, j)] * fast_rcp(s[i] + s[j]);
+    sym_congruence(V, S, M);
+    return false;
 }
 
 // Moore-Penrose inverse of a symmetric 4x4 with numpy's cutoff: singular values (|eigenvalues|)
@@ -145,7 +212,7 @@ STE_DEV int pinv_sym4(const double (&A)[10], double (&Ainv)[10]) {
     double a[10], V[16], f[4];
 #pragma unroll
     for (int i = 0; i < 10; ++i) a[i] = A[i];
-    jacobi_eig4(a, V);
+    jacobi_eig4<true>(a, V, kJacobiTight);
     const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
     const double wmax = fmax(fmax(fabs(w[0]), fabs(w[1])), fmax(fabs(w[2]), fabs(w[3])));
     const double cut = kPinvRcond * wmax;
@@ -158,6 +225,63 @@ STE_DEV int pinv_sym4(const double (&A)[10], double (&Ainv)[10]) {
     }
     sym_from_eig(V, f, Ainv);
     return dropped;
+}
+
+STE_COLD int pinv_sym4_cold(const double *A_in, double *Ainv_out) {
+    double A[10], Ainv[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) A[i] = A_in[i];
+    const int dropped = pinv_sym4(A, Ainv);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) Ainv_out[i] = Ainv[i];
+    return dropped;
+}
+
+// pinv of a symmetric 4x4 that is normally positive definite and well conditioned (the smoother's
+// P_b): root-free LDL^T, A^-1 = L^-T D^-1 L^-1, ~90 FP64 operations.  For a full-rank matrix the
+// pseudo-inverse IS the inverse.  If a pivot loses more than ~7 digits against its diagonal entry
+// (ill-conditioned, singular or indefinite matrix) the eigen-decomposition path with numpy's
+// cutoff semantics takes over.  Returns the number of dropped eigenvalues.
+STE_DEV int pinv_spd4(const double (&A)[10], double (&Ainv)[10]) {
+    const double a00 = A[0], a10 = A[1], a20 = A[2], a30 = A[3], a11 = A[4], a21 = A[5], a31 = A[6], a22 = A[7],
+                 a32 = A[8], a33 = A[9];
+    const double d0 = a00, r0 = fast_rcp(d0);
+    const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+    const double d1 = fma(-l10, a10, a11), r1 = fast_rcp(d1);
+    const double l21 = fma(-l20, a10, a21) * r1, l31 = fma(-l30, a10, a31) * r1;
+    const double d2 = fma(-l21 * d1, l21, fma(-l20, a20, a22)), r2 = fast_rcp(d2);
+    const double l32 = fma(-l31 * d1, l21, fma(-l30, a20, a32)) * r2;
+    const double d3 = fma(-l32 * d2, l32, fma(-l31 * d1, l31, fma(-l30, a30, a33)));
+    const double r3 = fast_rcp(d3);
+    const double kTol = 1e-7;
+    const bool ok = (d0 > 0.0) && (d1 > kTol * a11) && (d2 > kTol * a22) && (d3 > kTol * a33) && (d0 < 1e300);
+    if (!ok) {
+        double tmp_in[10], tmp_out[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) tmp_in[i] = A[i];
+        const int dropped = pinv_sym4_cold(tmp_in, tmp_out);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) Ainv[i] = tmp_out[i];
+        return dropped;
+    }
+    // N = L^-1 (unit lower triangular): n10, n20, n21, n30, n31, n32
+    const double n10 = -l10, n21 = -l21, n32 = -l32;
+    const double n20 = fma(l21, l10, -l20);
+    const double n31 = fma(l32, l21, -l31);
+    const double n30 = fma(-l32, n20, fma(l31, l10, -l30));
+    // A^-1 = N^T diag(r) N
+    const double t10 = n10 * r1, t20 = n20 * r2, t21 = n21 * r2, t30 = n30 * r3, t31 = n31 * r3, t32 = n32 * r3;
+    Ainv[SYM(3, 3)] = r3;
+    Ainv[SYM(2, 3)] = t32;
+    Ainv[SYM(1, 3)] = t31;
+    Ainv[SYM(0, 3)] = t30;
+    Ainv[SYM(2, 2)] = fma(t32, n32, r2);
+    Ainv[SYM(1, 2)] = fma(t31, n32, t21);
+    Ainv[SYM(0, 2)] = fma(t30, n32, t20);
+    Ainv[SYM(1, 1)] = fma(t31, n31, fma(t21, n21, r1));
+    Ainv[SYM(0, 1)] = fma(t30, n31, fma(t20, n21, t10));
+    Ainv[SYM(0, 0)] = fma(t30, n30, fma(t20, n20, fma(t10, n10, r0)));
+    return 0;
 }
 
 // Pseudo-inverse of a symmetric 2x2 [a b; b c] with the same cutoff rule (one Jacobi rotation
@@ -184,32 +308,63 @@ STE_DEV int pinv_sym2(double a, double b, double c, double (&inv)[3]) {
 
 // ------------------------------------------------------------------------------------------ //
 // Process model: great-circle propagation on the sphere (non_linear_process.py:54-78).
-// dtR = dt / R_earth is hoisted by the caller (shared by the 9 sigma points of a step).
 //
 // The reference evaluates lat' = asin(s), s = sin(phi) cos(delta) + cos(phi) sin(delta) cos(alpha).
 // (east, north, s) is the unit vector of the new position in the frame of the old meridian, so
 // cos(lat') = hypot(east, north) and lat' = atan2(s, hypot(east, north)): the same angle, well
 // conditioned up to the poles, and it reuses the one-division atan2 (no separate asin code).
+//
+// The nine sigma points of a step are x, x + m_c, x - m_c (c = 0..3).  Their three angles
+// (latitude, course, angular distance) are therefore theta_0 and theta_0 +/- eps_c, and
+//     sin(theta_0 +/- eps) = sin theta_0 cos eps +/- cos theta_0 sin eps          (same for cos)
+// so a step needs sincos of 3 centre angles and 12 offsets (15 evaluations) instead of 27; the
+// other points cost four multiply-adds per angle.  AngleTrig carries (sin, cos) of the three.
 // ------------------------------------------------------------------------------------------ //
+struct AngleTrig {
+    double sp, cp;   // latitude
+    double sa, ca;   // course over ground
+    double sd, cd;   // angular distance u dt / R
+};
+
+STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dtR) {
+    AngleTrig t;
+    fast_sincos(lat_deg * kDegToRad, &t.sp, &t.cp);
+    fast_sincos(cog_deg * kDegToRad, &t.sa, &t.ca);
+    fast_sincos(u * dtR, &t.sd, &t.cd);
+    return t;
+}
+
+// trig of (base + off) when plus, (base - off) otherwise
+STE_DEV AngleTrig angle_add(const AngleTrig &b, const AngleTrig &o, bool plus) {
+    const double sp = plus ? o.sp : -o.sp, sa = plus ? o.sa : -o.sa, sd = plus ? o.sd : -o.sd;
+    AngleTrig t;
+    t.sp = fma(b.sp, o.cp, b.cp * sp);
+    t.cp = fma(b.cp, o.cp, -b.sp * sp);
+    t.sa = fma(b.sa, o.ca, b.ca * sa);
+    t.ca = fma(b.ca, o.ca, -b.sa * sa);
+    t.sd = fma(b.sd, o.cd, b.cd * sd);
+    t.cd = fma(b.cd, o.cd, -b.sd * sd);
+    return t;
+}
+
+// x = [lon, lat, u, cog] of the sigma point, t = trig of its (lat, cog, u dt / R)
+STE_DEV void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt, double sog_rate,
+                             double cog_rate, double (&y)[4]) {
+    const double east = t.sd * t.sa;
+    const double sdca = t.sd * t.ca;
+    const double north = fma(t.cp, t.cd, -t.sp * sdca);
+    const double up = fma(t.sp, t.cd, t.cp * sdca);
+    const double horiz = fast_sqrt(fma(east, east, north * north));
+    y[0] = fma(x[0], kDegToRad, fast_atan2(east, north)) * kRadToDeg;
+    y[1] = fast_atan2(up, horiz) * kRadToDeg;
+    y[2] = fma(sog_rate, dt, x[2]);
+    y[3] = fma(cog_rate, dt, (x[3] * kDegToRad) * kRadToDeg);
+}
+
+// one stand-alone evaluation (geodetic_dynamics called directly, ste_geodetic_f64)
 STE_DEV void geodetic_step(const double (&x)[4], double dt, double dtR, double sog_rate,
                            double cog_rate, double (&y)[4]) {
-    const double lam = x[0] * kDegToRad;
-    const double phi = x[1] * kDegToRad;
-    const double u = x[2];
-    const double alpha = x[3] * kDegToRad;
-    double sphi, cphi, sal, cal, sd, cd;
-    fast_sincos(phi, &sphi, &cphi);
-    fast_sincos(alpha, &sal, &cal);
-    fast_sincos(u * dtR, &sd, &cd);
-    const double east = sd * sal;
-    const double sdca = sd * cal;
-    const double north = fma(cphi, cd, -sphi * sdca);
-    const double up = fma(sphi, cd, cphi * sdca);
-    const double horiz = fast_sqrt(fma(east, east, north * north));
-    y[0] = (lam + fast_atan2(east, north)) * kRadToDeg;
-    y[1] = fast_atan2(up, horiz) * kRadToDeg;
-    y[2] = fma(sog_rate, dt, u);
-    y[3] = fma(cog_rate, dt, alpha * kRadToDeg);
+    geodetic_finish(x, angle_trig(x[1], x[3], x[2], dtR), dt, sog_rate, cog_rate, y);
 }
 
 }  // namespace ste

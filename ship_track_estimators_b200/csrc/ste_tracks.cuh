@@ -146,6 +146,14 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
 // ------------------------------------------------------------------------------------------ //
 // Backward smoother: UnscentedKalmanFilter.rts_step (unscented.py:267-351).
 // ------------------------------------------------------------------------------------------ //
+STE_DEV void prefetch_l2(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc) {
     const int64_t ld = a.prob.ld;
     const int nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
@@ -153,41 +161,62 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
     rep = rep > 0 ? rep : 1;
     int status = 0;
 
-    double xs[4], Ps[10];
-    load_state(a.out.mean_f, a.out.cov_f, ld, nt, t, xs, Ps);
-    if (a.out.mean_s != a.out.mean_f || a.out.cov_s != a.out.cov_f)
-        store_state(a.out.mean_s, a.out.cov_s, ld, nt, t, xs, Ps);  // last state is untouched (:297)
-
-    double xf[4], Pf[10], dt = 0.0, sr = 0.0, cr = 0.0;
-    auto fetch = [&](int step) {
-        load_state(a.out.mean_f, a.out.cov_f, ld, step, t, xf, Pf);
-        dt = a.in.dt[(int64_t)step * ld + t];
-        const int ri = min_(step / rep, a.prob.max_obs - 1);
-        sr = a.in.sog_rate[(int64_t)ri * ld + t];
-        cr = a.in.cog_rate[(int64_t)ri * ld + t];
-    };
-    if (nt > 0) fetch(nt - 1);
+    {   // the last state is untouched by the smoother (:297); it seeds the carried (xs, Ps)
+        double xs[4], Ps[10];
+        load_state(a.out.mean_f, a.out.cov_f, ld, nt, t, xs, Ps);
+        if (a.out.mean_s != a.out.mean_f || a.out.cov_s != a.out.cov_f)
+            store_state(a.out.mean_s, a.out.cov_s, ld, nt, t, xs, Ps);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sc.at(kScratchXs + r) = xs[r];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sc.at(kScratchPs + k) = Ps[k];
+    }
+    bool bad = false;
 #pragma unroll 1
     for (int step = nt - 1; step >= 0; --step) {
-        double xc[4], Pc[10];
+        const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
+        const double *cf = a.out.cov_f + ((int64_t)step * 16) * ld + t;
+        double xf[4], s1[4], Pb[10];
+        const double dt = a.in.dt[(int64_t)step * ld + t];
+        const int ri = min_(step / rep, a.prob.max_obs - 1);
+        const double sr = a.in.sog_rate[(int64_t)ri * ld + t];
+        const double cr = a.in.cog_rate[(int64_t)ri * ld + t];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) xc[r] = xf[r];
+        for (int r = 0; r < 4; ++r) xf[r] = mf[r * ld];
+        {
+            double Pf[10];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) Pc[k] = Pf[k];
-        const double dtc = dt, src = sr, crc = cr;
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+            if (step > 0) {   // pull the next (earlier) state towards L2 while this step computes
+#pragma unroll
+                for (int r = 0; r < 4; ++r) prefetch_l2(mf + (r - 4) * ld);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = i; j < 4; ++j) prefetch_l2(cf + (i * 4 + j - 16) * ld);
+                prefetch_l2(a.in.dt + (int64_t)(step - 1) * ld + t);
+            }
+            urtss_moments(xf, Pf, a.prob.Q, dt, sr, cr, s1, Pb, status, sc);
+        }
         double e[4] = {0.0, 0.0, 0.0, 0.0};
         if (a.in.noise_bwd) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 e[r] = a.in.noise_bwd[((int64_t)step * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
-        if (step > 0) fetch(step - 1);  // prefetch while this step computes
-        urtss_step(xc, Pc, xs, Ps, a.prob.Q, dtc, src, crc, e, status, sc);
+        double Pf[10], xs[4], Ps[10];   // Pf again (L2-resident) rather than held across phase 1
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+        urtss_gain(xf, Pf, s1, Pb, e, xs, Ps, status, sc);
         store_state(a.out.mean_s, a.out.cov_s, ld, step, t, xs, Ps);
+        bad |= any_nonfinite(xs, Ps);
     }
-    if (any_nonfinite(xs, Ps)) status |= STE_STATUS_NONFINITE;
+    if (bad) status |= STE_STATUS_NONFINITE;
     a.out.status[t] |= status;
 }
-
 
 }  // namespace ste

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kThreads, STE_FWD_MIN_BLOCKS) ukf_forward_kern
 }
 
 __global__ void __launch_bounds__(kThreads, STE_BWD_MIN_BLOCKS) urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
-    __shared__ double scratch[kScratchSlots * kThreads];
+    extern __shared__ double scratch[];   // kScratchSlotsBwd * kThreads doubles (46 KB: opt-in size)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.prob.n_tracks) backward_track(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
@@ -338,7 +338,10 @@ int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutpu
     a.in = *in;
     a.out = *out;
     const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
-    urtss_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    const size_t smem = sizeof(double) * kScratchSlotsBwd * kThreads;
+    if (cudaFuncSetAttribute(urtss_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(urtss_backward_kernel)");
+    urtss_backward_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(a);
     return check_launch("urtss_backward_kernel");
 }
 

@@ -30,7 +30,7 @@ extern "C" int emul_forward(const SteProblem *prob, const SteInputs *in, SteOutp
 extern "C" int emul_backward(const SteProblem *prob, const SteInputs *in, SteOutputs *out) {
     KernelArgs a;
     a.prob = *prob; a.in = *in; a.out = *out;
-    double scratch[kScratchSlots];
+    double scratch[kScratchSlotsBwd];
     const Scratch sc{scratch, 1};
     for (int t = 0; t < prob->n_tracks; ++t) backward_track(a, t, sc);
     return 0;
