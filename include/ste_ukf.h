@@ -149,9 +149,16 @@ int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const dou
                      const double *sog_rate, const double *cog_rate, double *x_out, void *stream);
 
 /* Test hook: evaluates the library's own fp64 elementary functions (csrc/ste_fastmath.cuh) on n
- * arguments.  kind 0 sincos(a) -> (out0, out1); 1 atan2(a, b); 2 sqrt(a); 3 rsqrt(a); 4 1/a; 5 a/b. */
+ * arguments.  kind 0 sincos(a), |a| <= 105615 -> (out0, out1); 1 atan2(a, b); 2 sqrt(a); 3 rsqrt(a); 4 1/a; 5 a/b;
+ * 6 atan2(a, b) for b >= 0. */
 int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b, double *out0,
                        double *out1, void *stream);
+
+/* Measurement helper: one block of `warps` warps runs `iters` rounds of `chains` (1..8) independent
+ * dependent-DFMA chains per thread; cycles[0] (device int64) receives the clock64 span.  Gives the
+ * DFMA latency (warps = chains = 1) and the issue interval of the FP64 pipe. */
+int ste_probe_fp64_latency(int32_t warps, int32_t iters, int32_t chains, double *sink,
+                           long long *cycles, void *stream);
 
 /* Measurement helper for the roofline report: runs `iters` dependent-free DFMA rounds on every
  * thread of `blocks` x `threads` and writes one double per thread to sink (device, blocks*threads).

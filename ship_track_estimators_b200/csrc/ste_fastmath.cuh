@@ -132,11 +132,11 @@ STE_DEV double fast_div(double num, double den) {
 }
 
 // ---- sin and cos together --------------------------------------------------------------------- //
+// Branch-free; valid for |x| <= kSinCosMaxArg (three-term Cody-Waite reduction).  Callers check
+// the range once per filter step and take the library ("cold") path otherwise.
+constexpr double kSinCosMaxArg = 105615.0;
+
 STE_DEV void fast_sincos(double x, double *sn, double *cs) {
-    if (!(fabs(x) <= kTrigK[5])) {  // huge or NaN: library path (never taken by sane tracks)
-        sincos(x, sn, cs);
-        return;
-    }
     // n = rint(x * 2/pi) through the magic-number trick; the low word of t holds n (two's complement)
     const double t = fma(x, kTrigK[3], kTrigK[4]);
     const uint32_t q = (uint32_t)f64_bits(t);
@@ -170,14 +170,18 @@ STE_DEV void fast_sincos(double x, double *sn, double *cs) {
 // ---- atan2 ------------------------------------------------------------------------------------- //
 // One division: with mn = min(|y|,|x|), mx = max(|y|,|x|) the argument is reduced to
 // q = mn/mx (mn <= tan(pi/8) mx) or q = (mn - mx)/(mn + mx) (then atan = pi/4 + atan q), |q| <= 0.4143.
+// Branch-free for finite arguments; (0, 0) -> 0 (the sign conventions of atan2(+-0, -0) are not
+// reproduced, the filter never needs them); non-finite input gives NaN.
+// X_NONNEG: the caller guarantees x >= 0 (latitude from (up, horizontal)).
+template <bool X_NONNEG>
 STE_DEV double fast_atan2(double y, double x) {
-    const double ay = fabs(y), ax = fabs(x);
+    const double ay = fabs(y), ax = X_NONNEG ? x : fabs(x);
     const bool swap = ay > ax;
     const double mx = swap ? ay : ax, mn = swap ? ax : ay;
-    if (!(mx < 1e300) || !(mx > 1e-300)) return atan2(y, x);  // zeros, infinities, NaN: library semantics
     const bool big = mn > kTanPiEighth * mx;
     const double num = big ? mn - mx : mn;
-    const double den = big ? mn + mx : mx;
+    double den = big ? mn + mx : mx;
+    den = (f64_bits(mx) << 1) != 0 ? den : 1.0;          // (0, 0): 0 / 1
     const double q = fast_div(num, den);
     const double z = q * q, w = z * z;
     double s1 = fma(w, kAtanC[10], kAtanC[8]);
@@ -190,10 +194,15 @@ STE_DEV double fast_atan2(double y, double x) {
     s2 = fma(w, s2, kAtanC[1]);
     s1 = fma(w, s1, kAtanC[0]);
     const double p = fma(-q, fma(z, s1, w * s2), q);   // atan(q) = q - q (z s1 + w s2)
-    double r = big ? kPiQuarter + p : p;               // angle of (mx, mn) in [0, pi/4]
-    r = swap ? kPiHalf - r : r;
-    r = (x < 0.0) ? kPi - r : r;
-    return copysign(r, y);
+    // angle of (mx, mn) in [0, pi/4], then undo the reflections; r = off + sgn * p
+    double off = big ? kPiQuarter : 0.0;
+    double sg = 1.0;
+    if (swap) { off = kPiHalf - off; sg = -sg; }
+    if (!X_NONNEG) {
+        if ((int64_t)f64_bits(x) < 0) { off = kPi - off; sg = -sg; }
+    }
+    const double r = fma(sg, p, off);
+    return f64_from_bits(f64_bits(r) | (f64_bits(y) & 0x8000000000000000ull));   // copysign(r >= 0, y)
 }
 
 }  // namespace ste

@@ -35,35 +35,21 @@ STE_DEV void stash_root(const Scratch &sc, const double (&M)[10]) {
         for (int r = 0; r < 4; ++r) sc.at(kScratchRoot + c * 4 + r) = M[SYM(r, c)];
 }
 
-// The rolled sigma-point loop visits the points in the order x, x+m_0, x-m_0, x+m_1, ... so that
-// the sincos of an offset column is computed once and reused by its mirror point.
-//   j = 0: centre;  j = 2c+1: x + m_c;  j = 2c+2: x - m_c
-// sigma_ref_index maps j to the reference's column index (unscented.py:100-105: X[:, 1+c] = x + m_c,
-// X[:, 5+c] = x - m_c).
-STE_DEV int sigma_ref_index(int j) { return j == 0 ? 0 : ((j & 1) ? 1 + (j >> 1) : 4 + (j >> 1)); }
+// The rolled sigma-point loop walks the four columns of the root; each iteration propagates the
+// mirror pair x + m_c, x - m_c together: the sincos of the offset column is computed once, and
+// the two independent evaluations interleave in the FP64 pipe (DFMA latency ~9 cycles, issue
+// interval 2: a warp needs 4-5 independent operations in flight to keep the pipe busy).
+// Reference column order (unscented.py:100-105): X[:, 0] = x, X[:, 1+c] = x + m_c, X[:, 5+c] = x - m_c.
 
-// Propagate sigma point j of (x, root in scratch).  `base` / `off` persist across iterations:
-// base = trig of the centre angles, off = trig of the current offset column.
-// o receives X_j - x, y the propagated point.
-STE_DEV void propagate_sigma(const Scratch &sc, int j, const double (&x)[4], double dt, double dtR, double sog_rate,
-                             double cog_rate, AngleTrig &base, AngleTrig &off, double (&o)[4], double (&xi)[4],
-                             double (&y)[4]) {
-    const bool plus = (j & 1) || j == 0;
-    const int c = (j - 1) >> 1;
-    double m[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) m[r] = (j == 0) ? x[r] : sc.at(kScratchRoot + c * 4 + r);
-    if (plus) off = angle_trig(m[1], m[3], m[2], dtR);   // centre angles at j = 0, offset column otherwise
-    // j = 0: base is still the zero angle (sin 0, cos 1), so base (+) off == off exactly and becomes
-    // the centre trig; afterwards base stays fixed and off cycles through the columns.
-    const AngleTrig cur = angle_add(base, off, plus);
-    if (j == 0) base = cur;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        o[r] = (j == 0) ? 0.0 : (plus ? m[r] : -m[r]);
-        xi[r] = x[r] + o[r];
-    }
-    geodetic_finish(xi, cur, dt, sog_rate, cog_rate, y);
+// Range of the branch-free trigonometry for this step: every angle the nine sigma points can
+// produce stays below kSinCosMaxArg.  |m_rc| <= sqrt(lambda_max(3P)) <= sqrt(3 trace P).
+STE_DEV bool step_in_fast_range(const double (&x)[4], const double (&P)[10], double dtR) {
+    const double tr3 = 3.0 * (P[SYM(0, 0)] + P[SYM(1, 1)] + P[SYM(2, 2)] + P[SYM(3, 3)]);
+    const double lim = 1.0e4;   // radians; two orders of magnitude inside kSinCosMaxArg
+    // offsets bounded by sqrt(tr3): compare squares to avoid the root
+    const double oa = tr3 * (kDegToRad * kDegToRad), od = tr3 * (dtR * dtR);
+    return (fabs(x[1]) * kDegToRad < lim) && (fabs(x[3]) * kDegToRad < lim) && (fabs(x[2] * dtR) < lim) &&
+           (oa < lim * lim) && (od < lim * lim);   // false on NaN
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -73,49 +59,61 @@ STE_DEV void propagate_sigma(const Scratch &sc, int j, const double (&x)[4], dou
 //   d_i = f(X_i) - c,  mu = Wi * sum d_i,   mean = c + mu            (W0 + 8 Wi = 1, d_0 = 0)
 //   P'  = sum_i W_i (f(X_i) - mean - e)(...)^T + Q = Wi * sum d_i d_i^T - mu mu^T + e e^T + Q
 // with e the additive noise the reference adds to the mean BEFORE forming deviations (:198-205).
-// This needs no storage for the 9 propagated points.
+// This needs no storage for the 9 propagated points.  The root M must already be in scratch.
 // ------------------------------------------------------------------------------------------ //
-STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, double dt,
-                         double sog_rate, double cog_rate, const double (&e)[4],
-                         int &status, const Scratch &sc, double *sig_prior, double *sig_post, int64_t ld) {
-    {
-        double M[10];
-        if (sqrt_psd4(P, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
-        stash_root(sc, M);
+template <bool LIB>
+STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, double dt, double dtR,
+                             double sog_rate, double cog_rate, const double (&e)[4], const Scratch &sc,
+                             double *sig_prior, double *sig_post, int64_t ld) {
+    const AngleTrig base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
+    double c[4];
+    geodetic_finish<LIB>(x, base, dt, sog_rate, cog_rate, c);
+    if (sig_prior) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            sig_prior[(r * 9) * ld] = x[r];
+            sig_post[(r * 9) * ld] = c[r];
+        }
     }
-    const double dtR = dt / kEarthRadiusKm;
-    double c[4] = {0.0, 0.0, 0.0, 0.0};
     double s1[4] = {0.0, 0.0, 0.0, 0.0};
     double s2[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) s2[k] = 0.0;
-    AngleTrig base = {0.0, 1.0, 0.0, 1.0, 0.0, 1.0}, off = base;
 #pragma unroll 1
-    for (int j = 0; j < 9; ++j) {
-        double o[4], xi[4], yi[4];
-        propagate_sigma(sc, j, x, dt, dtR, sog_rate, cog_rate, base, off, o, xi, yi);
-        if (sig_prior) {
-            const int jr = sigma_ref_index(j);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                sig_prior[(r * 9 + jr) * ld] = xi[r];
-                sig_post[(r * 9 + jr) * ld] = yi[r];
-            }
-        }
-        if (j == 0) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) c[r] = yi[r];
-        }
-        double d[4];
+    for (int col = 0; col < 4; ++col) {
+        double m[4], xp[4], xm[4], yp[4], ym[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            d[r] = yi[r] - c[r];
-            s1[r] += d[r];
+            m[r] = sc.at(kScratchRoot + col * 4 + r);
+            xp[r] = x[r] + m[r];
+            xm[r] = x[r] - m[r];
+        }
+        {
+            const AngleTrig off = angle_trig<LIB>(m[1], m[3], m[2], dtR);
+            AngleTrig tp, tm;
+            angle_add_pair(base, off, tp, tm);
+            geodetic_finish<LIB>(xp, tp, dt, sog_rate, cog_rate, yp);
+            geodetic_finish<LIB>(xm, tm, dt, sog_rate, cog_rate, ym);
+        }
+        if (sig_prior) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                sig_prior[(r * 9 + 1 + col) * ld] = xp[r];
+                sig_post[(r * 9 + 1 + col) * ld] = yp[r];
+                sig_prior[(r * 9 + 5 + col) * ld] = xm[r];
+                sig_post[(r * 9 + 5 + col) * ld] = ym[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            yp[r] -= c[r];
+            ym[r] -= c[r];
+            s1[r] += yp[r] + ym[r];
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int q = r; q < 4; ++q) s2[SYM(r, q)] = fma(d[r], d[q], s2[SYM(r, q)]);
+            for (int q = r; q < 4; ++q) s2[SYM(r, q)] = fma(yp[r], yp[q], fma(ym[r], ym[q], s2[SYM(r, q)]));
     }
     double mu[4];
 #pragma unroll
@@ -128,6 +126,50 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
 #pragma unroll
         for (int q = r; q < 4; ++q)
             P[SYM(r, q)] = fma(kWi, s2[SYM(r, q)], fma(-mu[r], mu[q], fma(e[r], e[q], Q[r * 4 + q])));
+}
+
+// library-math version of the same step for out-of-range arguments; out of line (never hot)
+STE_COLD void predict_moments_cold(double *x_io, double *P_out, const double *Q, double dt, double dtR, double sog_rate,
+                                   double cog_rate, const double *e_in, Scratch sc, double *sig_prior, double *sig_post,
+                                   int64_t ld) {
+    double x[4], P[10], e[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        x[r] = x_io[r];
+        e[r] = e_in[r];
+    }
+    predict_moments<true>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, ld);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x_io[r] = x[r];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) P_out[k] = P[k];
+}
+
+STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, double dt,
+                         double sog_rate, double cog_rate, const double (&e)[4],
+                         int &status, const Scratch &sc, double *sig_prior, double *sig_post, int64_t ld) {
+    const double dtR = dt * (1.0 / kEarthRadiusKm);
+    const bool fast = step_in_fast_range(x, P, dtR);
+    {
+        double M[10];
+        if (sqrt_psd4(P, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
+        stash_root(sc, M);
+    }
+    if (fast) {
+        predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, ld);
+    } else {
+        double xt[4], Pt[10], et[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            xt[r] = x[r];
+            et[r] = e[r];
+        }
+        predict_moments_cold(xt, Pt, Q, dt, dtR, sog_rate, cog_rate, et, sc, sig_prior, sig_post, ld);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[r] = xt[r];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) P[k] = Pt[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -362,7 +404,8 @@ STE_DEV void ukf_update_position(double (&x)[4], double (&P)[10], const Model &m
 //  phase 1  urtss_moments   sigma points of the filtered state (xf, Pf) -> weighted sums
 //      x_b - xf = sum W_i d_i,            d_i = f(X_i) - xf
 //      P_b      = sum W_i d_i d_i^T + Q   (about the FILTERED mean: reference quirk, :324-325)
-//      Delta_c  = d(x + m_c) - d(x - m_c) (c = 0..3, parked in scratch)
+//      Delta_c  = d(x + m_c) - d(x - m_c) (c = 0..3, parked in scratch; mirror pairs are
+//                 propagated together, see predict_moments)
 //  phase 2  urtss_gain      cross covariance, gain and the smoothed state
 //      D = sum W_i (X_i - xf)(f(X_i) - x_b)^T = Wi sum_c m_c Delta_c^T
 //          (X_0 - xf = 0 and sum W_i (X_i - xf) = 0, so neither x_b nor the centre point enters)
@@ -377,47 +420,88 @@ constexpr int kScratchPs = 20;      // 10 slots
 constexpr int kScratchDelta = 30;   // 16 slots: Delta_c[r] at kScratchDelta + c * 4 + r
 constexpr int kScratchSlotsBwd = 46;
 
+template <bool LIB>
+STE_DEV void urtss_moments_impl(const double (&xf)[4], const double *Q, double dt, double dtR, double sog_rate,
+                                double cog_rate, double (&s1)[4], double (&Pb)[10], const Scratch &sc) {
+    const AngleTrig base = angle_trig<LIB>(xf[1], xf[3], xf[2], dtR);
+    {
+        double d0[4];
+        geodetic_finish<LIB>(xf, base, dt, sog_rate, cog_rate, d0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            d0[r] -= xf[r];
+            s1[r] = kW0 * d0[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = fma(kW0 * d0[r], d0[q], Q[r * 4 + q]);
+    }
+#pragma unroll 1
+    for (int col = 0; col < 4; ++col) {
+        double m[4], xp[4], xm[4], dp[4], dm[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            m[r] = sc.at(kScratchRoot + col * 4 + r);
+            xp[r] = xf[r] + m[r];
+            xm[r] = xf[r] - m[r];
+        }
+        {
+            const AngleTrig off = angle_trig<LIB>(m[1], m[3], m[2], dtR);
+            AngleTrig tp, tm;
+            angle_add_pair(base, off, tp, tm);
+            geodetic_finish<LIB>(xp, tp, dt, sog_rate, cog_rate, dp);
+            geodetic_finish<LIB>(xm, tm, dt, sog_rate, cog_rate, dm);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            dp[r] -= xf[r];
+            dm[r] -= xf[r];
+            s1[r] = fma(kWi, dp[r] + dm[r], s1[r]);
+            sc.at(kScratchDelta + col * 4 + r) = dp[r] - dm[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double wp = kWi * dp[r], wm = kWi * dm[r];
+#pragma unroll
+            for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = fma(wp, dp[q], fma(wm, dm[q], Pb[SYM(r, q)]));
+        }
+    }
+}
+
+STE_COLD void urtss_moments_cold(const double *xf_in, const double *Q, double dt, double dtR, double sog_rate,
+                                 double cog_rate, double *s1_out, double *Pb_out, Scratch sc) {
+    double xf[4], s1[4], Pb[10];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xf[r] = xf_in[r];
+    urtss_moments_impl<true>(xf, Q, dt, dtR, sog_rate, cog_rate, s1, Pb, sc);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s1_out[r] = s1[r];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) Pb_out[k] = Pb[k];
+}
+
 STE_DEV void urtss_moments(const double (&xf)[4], const double (&Pf)[10], const double *Q, double dt,
                            double sog_rate, double cog_rate, double (&s1)[4], double (&Pb)[10], int &status,
                            const Scratch &sc) {
+    const double dtR = dt * (1.0 / kEarthRadiusKm);
+    const bool fast = step_in_fast_range(xf, Pf, dtR);
     {
         double M[10];
         if (sqrt_psd4(Pf, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
         stash_root(sc, M);
     }
-    const double dtR = dt / kEarthRadiusKm;
+    if (fast) {
+        urtss_moments_impl<false>(xf, Q, dt, dtR, sog_rate, cog_rate, s1, Pb, sc);
+    } else {
+        double xt[4], st[4], Pt[10];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) s1[r] = 0.0;
+        for (int r = 0; r < 4; ++r) xt[r] = xf[r];
+        urtss_moments_cold(xt, Q, dt, dtR, sog_rate, cog_rate, st, Pt, sc);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r) s1[r] = st[r];
 #pragma unroll
-        for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = Q[r * 4 + q];
-    AngleTrig base = {0.0, 1.0, 0.0, 1.0, 0.0, 1.0}, off = base;
-    double dplus[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-    for (int j = 0; j < 9; ++j) {
-        double o[4], xi[4], d[4];
-        propagate_sigma(sc, j, xf, dt, dtR, sog_rate, cog_rate, base, off, o, xi, d);
-        const double w = (j == 0) ? kW0 : kWi;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            d[r] -= xf[r];
-            s1[r] = fma(w, d[r], s1[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const double wd = w * d[r];
-#pragma unroll
-            for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = fma(wd, d[q], Pb[SYM(r, q)]);
-        }
-        if (j & 1) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) dplus[r] = d[r];
-        } else if (j > 0) {
-            const int c = (j - 1) >> 1;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) sc.at(kScratchDelta + c * 4 + r) = dplus[r] - d[r];
-        }
+        for (int k = 0; k < 10; ++k) Pb[k] = Pt[k];
     }
 }
 

@@ -52,14 +52,22 @@ STE_DEV void jacobi_rotate(double (&a)[10], double (&V)[16]) {
     const double apq = a[SYM(P_, Q_)];
     const double app = a[SYM(P_, P_)];
     const double aqq = a[SYM(Q_, Q_)];
-    // t = tan(rotation angle), the smaller root of t^2 + 2 theta t - 1 = 0, theta = (aqq-app)/(2apq)
+    // Rotation angle theta in (-pi/4, pi/4] with tan 2 theta = 2 a_pq / (a_qq - a_pp):
+    //   cos 2theta = |d| / h,  sin 2theta = sign(d) b / h,   h = hypot(d, b)
+    //   cos theta = sqrt((1 + cos 2theta) / 2),  sin theta = sin 2theta / (2 cos theta),  t = tan theta
+    // two reciprocal square roots, no division; sin theta keeps full RELATIVE accuracy for tiny
+    // rotations because it is a product of accurately rounded factors.
     const double d = aqq - app;
     const double b = apq + apq;
-    const double h = fast_sqrt(fma(d, d, b * b));
-    double t = fast_div(d >= 0.0 ? b : -b, fabs(d) + h);   // sign(d) * b / (|d| + sqrt(d^2 + b^2))
-    t = (apq == 0.0) ? 0.0 : t;                             // also covers d == b == 0 (0/0 -> NaN)
-    const double c = fast_rsqrt(fma(t, t, 1.0));
-    const double s = t * c;
+    const double rh = fast_rsqrt(fma(d, d, b * b));
+    const double c2t = fabs(d) * rh;
+    const double s2t = (d >= 0.0 ? b : -b) * rh;
+    const double cc = fma(0.5, c2t, 0.5);
+    const double rc = fast_rsqrt(cc);
+    const bool skip = (apq == 0.0);                       // also covers d == b == 0 (NaN from 0 * inf)
+    const double c = skip ? 1.0 : cc * rc;
+    const double s = skip ? 0.0 : (0.5 * s2t) * rc;
+    const double t = s * (skip ? 1.0 : rc);
     a[SYM(P_, P_)] = fma(-t, apq, app);
     a[SYM(Q_, Q_)] = fma(t, apq, aqq);
     a[SYM(P_, Q_)] = 0.0;
@@ -317,8 +325,11 @@ STE_DEV int pinv_sym2(double a, double b, double c, double (&inv)[3]) {
 // The nine sigma points of a step are x, x + m_c, x - m_c (c = 0..3).  Their three angles
 // (latitude, course, angular distance) are therefore theta_0 and theta_0 +/- eps_c, and
 //     sin(theta_0 +/- eps) = sin theta_0 cos eps +/- cos theta_0 sin eps          (same for cos)
-// so a step needs sincos of 3 centre angles and 12 offsets (15 evaluations) instead of 27; the
-// other points cost four multiply-adds per angle.  AngleTrig carries (sin, cos) of the three.
+// so a step needs sincos of 3 centre angles and 12 offsets (15 evaluations) instead of 27.
+// AngleTrig carries (sin, cos) of the three angles.
+//
+// LIB = false: the branch-free functions of ste_fastmath.cuh (hot path; the caller has checked
+// the argument range for this step).  LIB = true: the CUDA math library, same formulas (cold path).
 // ------------------------------------------------------------------------------------------ //
 struct AngleTrig {
     double sp, cp;   // latitude
@@ -326,37 +337,50 @@ struct AngleTrig {
     double sd, cd;   // angular distance u dt / R
 };
 
+template <bool LIB>
 STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dtR) {
     AngleTrig t;
-    fast_sincos(lat_deg * kDegToRad, &t.sp, &t.cp);
-    fast_sincos(cog_deg * kDegToRad, &t.sa, &t.ca);
-    fast_sincos(u * dtR, &t.sd, &t.cd);
+    if (LIB) {
+        sincos(lat_deg * kDegToRad, &t.sp, &t.cp);
+        sincos(cog_deg * kDegToRad, &t.sa, &t.ca);
+        sincos(u * dtR, &t.sd, &t.cd);
+    } else {
+        fast_sincos(lat_deg * kDegToRad, &t.sp, &t.cp);
+        fast_sincos(cog_deg * kDegToRad, &t.sa, &t.ca);
+        fast_sincos(u * dtR, &t.sd, &t.cd);
+    }
     return t;
 }
 
-// trig of (base + off) when plus, (base - off) otherwise
-STE_DEV AngleTrig angle_add(const AngleTrig &b, const AngleTrig &o, bool plus) {
-    const double sp = plus ? o.sp : -o.sp, sa = plus ? o.sa : -o.sa, sd = plus ? o.sd : -o.sd;
-    AngleTrig t;
-    t.sp = fma(b.sp, o.cp, b.cp * sp);
-    t.cp = fma(b.cp, o.cp, -b.sp * sp);
-    t.sa = fma(b.sa, o.ca, b.ca * sa);
-    t.ca = fma(b.ca, o.ca, -b.sa * sa);
-    t.sd = fma(b.sd, o.cd, b.cd * sd);
-    t.cd = fma(b.cd, o.cd, -b.sd * sd);
-    return t;
+// trig of (base + off) and (base - off) from the four shared products per angle
+STE_DEV void angle_add_pair(const AngleTrig &b, const AngleTrig &o, AngleTrig &plus, AngleTrig &minus) {
+    double sc_, cs_, cc_, ss_;
+    sc_ = b.sp * o.cp; cs_ = b.cp * o.sp; cc_ = b.cp * o.cp; ss_ = b.sp * o.sp;
+    plus.sp = sc_ + cs_; minus.sp = sc_ - cs_; plus.cp = cc_ - ss_; minus.cp = cc_ + ss_;
+    sc_ = b.sa * o.ca; cs_ = b.ca * o.sa; cc_ = b.ca * o.ca; ss_ = b.sa * o.sa;
+    plus.sa = sc_ + cs_; minus.sa = sc_ - cs_; plus.ca = cc_ - ss_; minus.ca = cc_ + ss_;
+    sc_ = b.sd * o.cd; cs_ = b.cd * o.sd; cc_ = b.cd * o.cd; ss_ = b.sd * o.sd;
+    plus.sd = sc_ + cs_; minus.sd = sc_ - cs_; plus.cd = cc_ - ss_; minus.cd = cc_ + ss_;
 }
 
 // x = [lon, lat, u, cog] of the sigma point, t = trig of its (lat, cog, u dt / R)
+template <bool LIB>
 STE_DEV void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt, double sog_rate,
                              double cog_rate, double (&y)[4]) {
     const double east = t.sd * t.sa;
     const double sdca = t.sd * t.ca;
     const double north = fma(t.cp, t.cd, -t.sp * sdca);
     const double up = fma(t.sp, t.cd, t.cp * sdca);
-    const double horiz = fast_sqrt(fma(east, east, north * north));
-    y[0] = fma(x[0], kDegToRad, fast_atan2(east, north)) * kRadToDeg;
-    y[1] = fast_atan2(up, horiz) * kRadToDeg;
+    double dlon, lat;
+    if (LIB) {
+        dlon = atan2(east, north);
+        lat = atan2(up, sqrt(fma(east, east, north * north)));
+    } else {
+        dlon = fast_atan2<false>(east, north);
+        lat = fast_atan2<true>(up, fast_sqrt(fma(east, east, north * north)));
+    }
+    y[0] = fma(x[0], kDegToRad, dlon) * kRadToDeg;
+    y[1] = lat * kRadToDeg;
     y[2] = fma(sog_rate, dt, x[2]);
     y[3] = fma(cog_rate, dt, (x[3] * kDegToRad) * kRadToDeg);
 }
@@ -364,7 +388,12 @@ STE_DEV void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt
 // one stand-alone evaluation (geodetic_dynamics called directly, ste_geodetic_f64)
 STE_DEV void geodetic_step(const double (&x)[4], double dt, double dtR, double sog_rate,
                            double cog_rate, double (&y)[4]) {
-    geodetic_finish(x, angle_trig(x[1], x[3], x[2], dtR), dt, sog_rate, cog_rate, y);
+    const bool in_range = fabs(x[1]) * kDegToRad <= kSinCosMaxArg && fabs(x[3]) * kDegToRad <= kSinCosMaxArg &&
+                          fabs(x[2] * dtR) <= kSinCosMaxArg;
+    if (in_range)
+        geodetic_finish<false>(x, angle_trig<false>(x[1], x[3], x[2], dtR), dt, sog_rate, cog_rate, y);
+    else
+        geodetic_finish<true>(x, angle_trig<true>(x[1], x[3], x[2], dtR), dt, sog_rate, cog_rate, y);
 }
 
 }  // namespace ste

@@ -208,7 +208,8 @@ __global__ void fastmath_probe_kernel(int kind, int n, const double *a, const do
     double r0 = 0.0, r1 = 0.0;
     switch (kind) {
         case 0: fast_sincos(a[i], &r0, &r1); break;
-        case 1: r0 = fast_atan2(a[i], b[i]); break;
+        case 1: r0 = fast_atan2<false>(a[i], b[i]); break;
+        case 6: r0 = fast_atan2<true>(a[i], b[i]); break;
         case 2: r0 = fast_sqrt(a[i]); break;
         case 3: r0 = fast_rsqrt(a[i]); break;
         case 4: r0 = fast_rcp(a[i]); break;
@@ -217,6 +218,27 @@ __global__ void fastmath_probe_kernel(int kind, int n, const double *a, const do
     }
     out0[i] = r0;
     out1[i] = r1;
+}
+
+// dependent-chain DFMA latency: `CHAINS` independent chains per thread, clock64 timed
+template <int CHAINS>
+__global__ void fp64_latency_probe_kernel(int iters, double *sink, long long *cycles) {
+    double acc[CHAINS];
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-12;
+#pragma unroll
+    for (int k = 0; k < CHAINS; ++k) acc[k] = 0.1 * k;
+    const long long t0 = clock64();
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < CHAINS; ++k) acc[k] = fma(acc[k], a, b);
+    }
+    const long long t1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < CHAINS; ++k) s += acc[k];
+    sink[threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
 }
 
 __global__ void fp64_fma_probe_kernel(int iters, double *sink) {
@@ -408,10 +430,24 @@ int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const dou
 }
 
 int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b, double *out0, double *out1, void *stream) {
-    if (kind < 0 || kind > 5 || n < 0 || !a || !b || !out0 || !out1) return fail(STE_ERR_INVALID_ARG, "bad fastmath probe arguments");
+    if (kind < 0 || kind > 6 || n < 0 || !a || !b || !out0 || !out1) return fail(STE_ERR_INVALID_ARG, "bad fastmath probe arguments");
     if (n == 0) return STE_OK;
     fastmath_probe_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kind, n, a, b, out0, out1);
     return check_launch("fastmath_probe_kernel");
+}
+
+int ste_probe_fp64_latency(int32_t warps, int32_t iters, int32_t chains, double *sink, long long *cycles, void *stream) {
+    if (warps < 1 || warps > 32 || iters < 1 || chains < 1 || chains > 8 || !sink || !cycles)
+        return fail(STE_ERR_INVALID_ARG, "bad latency probe arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (chains) {
+        case 1: fp64_latency_probe_kernel<1><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
+        case 2: fp64_latency_probe_kernel<2><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
+        case 4: fp64_latency_probe_kernel<4><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
+        case 8: fp64_latency_probe_kernel<8><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
+        default: return fail(STE_ERR_INVALID_ARG, "chains must be 1, 2, 4 or 8");
+    }
+    return check_launch("fp64_latency_probe_kernel");
 }
 
 int ste_probe_fp64_fma(int32_t blocks, int32_t threads, int32_t iters, double *sink, void *stream) {

@@ -7,6 +7,8 @@ Dev tool (round-1 profiling)."""
 import collections, csv, os, re, sys
 
 sass_csv, disasm, kernel_sub, per = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
+# "mangled-substring|demangled-substring" selects the nvdisasm section and the ncu kernel separately
+dis_sub, csv_sub = (kernel_sub.split("|") + [kernel_sub])[:2]
 SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ship_track_estimators_b200", "csrc")
 
 # function line ranges per source file
@@ -37,7 +39,7 @@ def func_of(path, line):
 chains, cur_chain, in_kernel, pending_new = {}, [], False, True
 for l in open(disasm):
     if l.startswith(".text."):
-        in_kernel = kernel_sub in l
+        in_kernel = dis_sub in l
         continue
     if not in_kernel:
         continue
@@ -60,7 +62,7 @@ rows = list(csv.reader(open(sass_csv)))
 hdr, take, counts = None, False, {}
 for r in rows:
     if r and r[0] == "Kernel Name":
-        take = kernel_sub in r[1] and not counts
+        take = csv_sub in r[1] and not counts
         hdr = None
     elif r and r[0] == "Address":
         hdr = {n: i for i, n in enumerate(r)}
