@@ -54,6 +54,8 @@ extern "C" {
 #define STE_STATUS_OBS_OVERRUN 0x8   /* more update times matched than observations exist           */
                                      /* (the reference raises IndexError; the host binding does too) */
 #define STE_STATUS_RANK_DEFICIENT 0x10 /* a pseudo-inverse dropped a non-structural singular value  */
+#define STE_STATUS_SMOOTH_RECOMPUTE 0x100 /* informational: the step grid of this track does not let  */
+                                     /* the smoother reuse the filter's statistics; it recomputes   */
 
 /*
  * Problem description shared by all tracks of a launch ("tile").
@@ -110,6 +112,11 @@ typedef struct SteOutputs {
     uint8_t *gate_iters; /* [max_obs][ld] robustification iterations per update, or NULL              */
     double *gate_lambda; /* [max_obs][ld] final lambda factor per update, or NULL                     */
     double *gate_scale;  /* [max_obs][ld] accumulated scale of R (product of lambdas), or NULL        */
+    double *smooth_stats; /* [max_steps][30][ld] or NULL.  Written by the forward pass, read by the   */
+                         /* backward pass: per predict step the noise-free predicted-mean offset (4), */
+                         /* the predicted covariance about the filtered mean (10 unique) and the      */
+                         /* cross covariance (16) that rts_step recomputes from the same sigma points */
+                         /* (unscented.py:299-330).  NULL: the backward pass recomputes them.         */
 } SteOutputs;
 
 /* library / device -------------------------------------------------------------------------- */

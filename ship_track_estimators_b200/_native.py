@@ -21,6 +21,8 @@ STE_STATUS_INDEFINITE = 0x2
 STE_STATUS_GATE_CAP = 0x4
 STE_STATUS_OBS_OVERRUN = 0x8
 STE_STATUS_RANK_DEFICIENT = 0x10
+STE_STATUS_SMOOTH_RECOMPUTE = 0x100
+STATS_PLANES = 30
 
 _dptr = C.c_void_p  # device pointers travel as plain integers
 
@@ -72,6 +74,7 @@ class SteOutputs(C.Structure):
         ("gate_iters", _dptr),
         ("gate_lambda", _dptr),
         ("gate_scale", _dptr),
+        ("smooth_stats", _dptr),
     ]
 
 

@@ -279,6 +279,7 @@ class TrackResults:
     gate_iters: Optional[torch.Tensor] = None
     gate_lambda: Optional[torch.Tensor] = None
     gate_scale: Optional[torch.Tensor] = None
+    smooth_stats: Optional[torch.Tensor] = None  # [N][30][T] device-side tape between the two passes (not a result)
     n_steps_host: Optional[np.ndarray] = None
 
     _TENSORS = ("mean_f", "cov_f", "mean_s", "cov_s", "status", "n_updates", "gate_iters", "gate_lambda", "gate_scale")
@@ -369,8 +370,12 @@ class BatchedUKF:
         i.noise_pred, i.noise_upd, i.noise_bwd = nat.ptr(b.noise_pred), nat.ptr(b.noise_upd), nat.ptr(b.noise_bwd)
         return i
 
-    def allocate(self, b: TrackBatch, smoother: bool = True, in_place: bool = False) -> TrackResults:
-        """Output buffers for a tile (caller-owned, reusable across tiles of the same shape)."""
+    def allocate(self, b: TrackBatch, smoother: bool = True, in_place: bool = False, reuse_stats: bool = True) -> TrackResults:
+        """Output buffers for a tile (caller-owned, reusable across tiles of the same shape).
+
+        ``reuse_stats``: also allocate the 240 B/step tape on which the forward pass leaves the
+        smoother's sigma-point statistics, so the backward pass does not recompute them (the
+        reference does).  ``False`` trades that memory for ~2x the smoother's arithmetic."""
         dev, T, S = b.device, b.n_tracks, b.max_steps + 1
         f64 = dict(dtype=torch.float64, device=dev)
         mean_f = torch.empty(S, 4, T, **f64)
@@ -383,6 +388,8 @@ class BatchedUKF:
             status=torch.zeros(T, dtype=torch.int32, device=dev), n_updates=torch.zeros(T, dtype=torch.int32, device=dev),
             n_steps_host=b.n_steps_host,
         )
+        if smoother and reuse_stats:
+            res.smooth_stats = torch.empty(max(b.max_steps, 1), nat.STATS_PLANES, T, **f64)
         if self.model.gating:
             res.gate_iters = torch.zeros(b.max_obs, T, dtype=torch.uint8, device=dev)
             res.gate_lambda = torch.ones(b.max_obs, T, **f64)
@@ -396,6 +403,7 @@ class BatchedUKF:
         o.status, o.n_updates = nat.ptr(r.status), nat.ptr(r.n_updates)
         o.gate_iters, o.gate_lambda = nat.ptr(r.gate_iters), nat.ptr(r.gate_lambda)
         o.gate_scale = nat.ptr(r.gate_scale)
+        o.smooth_stats = nat.ptr(r.smooth_stats)
         return o
 
     def _check_rows(self, b: TrackBatch):

@@ -32,6 +32,15 @@
 #define STE_CONST static const
 #endif
 
+// streaming (evict-first) global accesses for write-once / read-once per-step state
+#if defined(__CUDA_ARCH__)
+#define STE_STORE_STREAM(p, v) __stcs((p), (v))
+#define STE_LOAD_STREAM(p) __ldcs(p)
+#else
+#define STE_STORE_STREAM(p, v) (*(p) = (v))
+#define STE_LOAD_STREAM(p) (*(p))
+#endif
+
 namespace ste {
 
 // ---- coefficient tables (constant bank on the device) ---------------------------------------- //

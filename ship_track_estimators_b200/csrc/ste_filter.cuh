@@ -26,7 +26,17 @@ struct Scratch {
     STE_DEV double &at(int slot) const { return base[(long)slot * stride]; }
 };
 constexpr int kScratchRoot = 0;   // 16 slots: M[r][c] at kScratchRoot + c * 4 + r (column-major)
-constexpr int kScratchSlots = 16;
+constexpr int kScratchSlots = 16;          // single-step kernels: the root only
+constexpr int kScratchDeltaFwd = 16;       // forward filter with smoother statistics: Delta_c, 16 slots
+constexpr int kScratchSlotsFwd = 32;
+
+// Smoother statistics ("tape") the forward pass can emit for every predict, so that the backward
+// pass need not regenerate and re-propagate the sigma points of the same filtered state (the
+// reference recomputes them, unscented.py:299-330; they are the same numbers).  Per step, 30 planes:
+//   [0..3]   delta = sum W_i f(X_i) - x          noise-free predicted mean minus the filtered mean
+//   [4..13]  P_b   = sum W_i d_i d_i^T + Q        about the filtered mean (10 unique entries)
+//   [14..29] D     = sum W_i (X_i - x) f(X_i)^T   cross covariance, row-major
+constexpr int kStatsPlanes = 30;
 
 STE_DEV void stash_root(const Scratch &sc, const double (&M)[10]) {
 #pragma unroll
@@ -64,7 +74,7 @@ STE_DEV bool step_in_fast_range(const double (&x)[4], const double (&P)[10], dou
 template <bool LIB>
 STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, double dt, double dtR,
                              double sog_rate, double cog_rate, const double (&e)[4], const Scratch &sc,
-                             double *sig_prior, double *sig_post, int64_t ld) {
+                             double *sig_prior, double *sig_post, double *stats, int64_t ld) {
     const AngleTrig base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
     double c[4];
     geodetic_finish<LIB>(x, base, dt, sog_rate, cog_rate, c);
@@ -104,6 +114,10 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
                 sig_post[(r * 9 + 5 + col) * ld] = ym[r];
             }
         }
+        if (stats) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) sc.at(kScratchDeltaFwd + col * 4 + r) = yp[r] - ym[r];
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             yp[r] -= c[r];
@@ -115,30 +129,56 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
 #pragma unroll
             for (int q = r; q < 4; ++q) s2[SYM(r, q)] = fma(yp[r], yp[q], fma(ym[r], ym[q], s2[SYM(r, q)]));
     }
-    double mu[4];
+    double mu[4], delta[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         mu[r] = kWi * s1[r];
+        delta[r] = (c[r] - x[r]) + mu[r];
         x[r] = c[r] + (mu[r] + e[r]);
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int q = r; q < 4; ++q)
-            P[SYM(r, q)] = fma(kWi, s2[SYM(r, q)], fma(-mu[r], mu[q], fma(e[r], e[q], Q[r * 4 + q])));
+        for (int q = r; q < 4; ++q) {
+            const double cov = fma(kWi, s2[SYM(r, q)], fma(-mu[r], mu[q], Q[r * 4 + q]));   // about the mean, + Q
+            P[SYM(r, q)] = fma(e[r], e[q], cov);
+            if (stats) STE_STORE_STREAM(stats + (4 + SYM(r, q)) * ld, fma(delta[r], delta[q], cov));   // about x
+        }
+    if (stats) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) STE_STORE_STREAM(stats + r * ld, delta[r]);
+        // D = Wi sum_c m_c Delta_c^T: the centre point has X_0 - x = 0 and sum W_i (X_i - x) = 0
+        double D[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) D[k] = 0.0;
+#pragma unroll
+        for (int col = 0; col < 4; ++col) {
+            double dl[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dl[r] = sc.at(kScratchDeltaFwd + col * 4 + r);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double wm = kWi * sc.at(kScratchRoot + col * 4 + q);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) D[q * 4 + r] = fma(wm, dl[r], D[q * 4 + r]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) STE_STORE_STREAM(stats + (14 + k) * ld, D[k]);
+    }
 }
 
 // library-math version of the same step for out-of-range arguments; out of line (never hot)
 STE_COLD void predict_moments_cold(double *x_io, double *P_out, const double *Q, double dt, double dtR, double sog_rate,
                                    double cog_rate, const double *e_in, Scratch sc, double *sig_prior, double *sig_post,
-                                   int64_t ld) {
+                                   double *stats, int64_t ld) {
     double x[4], P[10], e[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         x[r] = x_io[r];
         e[r] = e_in[r];
     }
-    predict_moments<true>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, ld);
+    predict_moments<true>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld);
 #pragma unroll
     for (int r = 0; r < 4; ++r) x_io[r] = x[r];
 #pragma unroll
@@ -147,7 +187,8 @@ STE_COLD void predict_moments_cold(double *x_io, double *P_out, const double *Q,
 
 STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, double dt,
                          double sog_rate, double cog_rate, const double (&e)[4],
-                         int &status, const Scratch &sc, double *sig_prior, double *sig_post, int64_t ld) {
+                         int &status, const Scratch &sc, double *sig_prior, double *sig_post, double *stats,
+                         int64_t ld) {
     const double dtR = dt * (1.0 / kEarthRadiusKm);
     const bool fast = step_in_fast_range(x, P, dtR);
     {
@@ -156,7 +197,7 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
         stash_root(sc, M);
     }
     if (fast) {
-        predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, ld);
+        predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld);
     } else {
         double xt[4], Pt[10], et[4];
 #pragma unroll
@@ -164,7 +205,7 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
             xt[r] = x[r];
             et[r] = e[r];
         }
-        predict_moments_cold(xt, Pt, Q, dt, dtR, sog_rate, cog_rate, et, sc, sig_prior, sig_post, ld);
+        predict_moments_cold(xt, Pt, Q, dt, dtR, sog_rate, cog_rate, et, sc, sig_prior, sig_post, stats, ld);
 #pragma unroll
         for (int r = 0; r < 4; ++r) x[r] = xt[r];
 #pragma unroll
@@ -505,6 +546,54 @@ STE_DEV void urtss_moments(const double (&xf)[4], const double (&Pf)[10], const 
     }
 }
 
+// xs <- xf + K wrap(xs - x_b), Ps <- Pf + K (Ps - P_b) K^T with (xs, Ps) carried in scratch (:337-349)
+STE_DEV void urtss_apply(const double (&xf)[4], const double (&Pf)[10], const double (&xb_minus_xf)[4],
+                         const double (&Pb)[10], const double (&K)[16], double (&xs)[4], double (&Ps)[10],
+                         const Scratch &sc) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xs[r] = sc.at(kScratchXs + r);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) Ps[k] = sc.at(kScratchPs + k);
+    double y[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) y[r] = xs[r] - (xf[r] + xb_minus_xf[r]);
+    y[3] = wrap180(y[3]);  // :340
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double acc = xf[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc = fma(K[i * 4 + k], y[k], acc);
+        xs[i] = acc;
+    }
+    xs[3] = py_mod360(xs[3]);  // :346
+    double KG[16];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) Ps[k] -= Pb[k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fma(K[i * 4 + k], Ps[SYM(k, j)], acc);
+            KG[i * 4 + j] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) {
+            double acc = Pf[SYM(i, j)];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fma(KG[i * 4 + k], K[j * 4 + k], acc);
+            Ps[SYM(i, j)] = acc;
+        }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sc.at(kScratchXs + r) = xs[r];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sc.at(kScratchPs + k) = Ps[k];
+}
+
+// phase 2 after urtss_moments (root and Delta_c in scratch)
 STE_DEV void urtss_gain(const double (&xf)[4], const double (&Pf)[10], const double (&s1)[4], const double (&Pb)[10],
                         const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status, const Scratch &sc) {
     double Pbinv[10];
@@ -531,48 +620,37 @@ STE_DEV void urtss_gain(const double (&xf)[4], const double (&Pf)[10], const dou
             for (int j = 0; j < 4; ++j) K[i * 4 + j] = fma(wm, v[j], K[i * 4 + j]);
         }
     }
+    double xb[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) xs[r] = sc.at(kScratchXs + r);
+    for (int r = 0; r < 4; ++r) xb[r] = s1[r] + e[r];
+    urtss_apply(xf, Pf, xb, Pb, K, xs, Ps, sc);
+}
+
+// One backward iteration from the statistics the forward pass stored for this step (kStatsPlanes
+// planes at `stats`): no sigma points, no square root - a pseudo-inverse and three small products.
+STE_DEV void urtss_step_from_stats(const double (&xf)[4], const double (&Pf)[10], const double *stats, int64_t ld,
+                                   const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status,
+                                   const Scratch &sc) {
+    double xb[4], Pb[10], D[16];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) Ps[k] = sc.at(kScratchPs + k);
-    double y[4];
+    for (int r = 0; r < 4; ++r) xb[r] = STE_LOAD_STREAM(stats + r * ld) + e[r];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) y[r] = xs[r] - (xf[r] + (s1[r] + e[r]));
-    y[3] = wrap180(y[3]);  // :340
+    for (int k = 0; k < 10; ++k) Pb[k] = STE_LOAD_STREAM(stats + (4 + k) * ld);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double acc = xf[i];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc = fma(K[i * 4 + k], y[k], acc);
-        xs[i] = acc;
-    }
-    xs[3] = py_mod360(xs[3]);  // :346
-    // Ps <- Pf + K (Ps - Pb) K^T
-    double KG[16];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) Ps[k] -= Pb[k];
+    for (int k = 0; k < 16; ++k) D[k] = STE_LOAD_STREAM(stats + (14 + k) * ld);
+    double Pbinv[10];
+    if (pinv_spd4(Pb, Pbinv) > 0) status |= STE_STATUS_RANK_DEFICIENT;
+    double K[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc = fma(K[i * 4 + k], Ps[SYM(k, j)], acc);
-            KG[i * 4 + j] = acc;
+            for (int k = 0; k < 4; ++k) acc = fma(D[i * 4 + k], Pbinv[SYM(k, j)], acc);
+            K[i * 4 + j] = acc;
         }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = i; j < 4; ++j) {
-            double acc = Pf[SYM(i, j)];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc = fma(KG[i * 4 + k], K[j * 4 + k], acc);
-            Ps[SYM(i, j)] = acc;
-        }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) sc.at(kScratchXs + r) = xs[r];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) sc.at(kScratchPs + k) = Ps[k];
+    urtss_apply(xf, Pf, xb, Pb, K, xs, Ps, sc);
 }
 
 }  // namespace ste

@@ -8,14 +8,6 @@
 
 namespace ste {
 
-#if defined(__CUDA_ARCH__)
-#define STE_STORE_STREAM(p, v) __stcs((p), (v))
-#define STE_LOAD_STREAM(p) __ldcs(p)
-#else
-#define STE_STORE_STREAM(p, v) (*(p) = (v))
-#define STE_LOAD_STREAM(p) (*(p))
-#endif
-
 template <typename T>
 STE_DEV T min_(T a, T b) { return a < b ? a : b; }
 
@@ -108,16 +100,30 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
     int ui = 0;
     double dt = 0.0, sr = 0.0, cr = 0.0;
     bool upd = true;
+    // The smoother statistics are valid for the backward pass only if it would read the same
+    // rates: it indexes them by step / rate_repeat (unscented.py:287-311), the filter by the
+    // update index.  They agree on every regular step grid; a track where they do not is flagged
+    // and smoothed by recomputation.
+    int rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
+    rep = rep > 0 ? rep : 1;
+    int ri = 0, rc = 0;
+    bool consistent = true;
 #pragma unroll 1
     for (int s = -1; s < nt; ++s) {
         if (s >= 0) {
+            consistent &= (min_(ri, a.prob.max_obs - 1) == ui);
+            if (++rc == rep) {
+                rc = 0;
+                ++ri;
+            }
+            double *stats = a.out.smooth_stats ? a.out.smooth_stats + ((int64_t)s * kStatsPlanes) * ld + t : nullptr;
             double e[4] = {0.0, 0.0, 0.0, 0.0};
             if (a.in.noise_pred) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
                     e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
             }
-            ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, ld);
+            ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld);
             if (upd) {
                 if (ui + 1 < a.prob.max_obs) {
                     ++ui;
@@ -139,6 +145,7 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
         if (s >= 0) store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, x, P);
     }
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
+    if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;
     a.out.status[t] = status;
     if (a.out.n_updates) a.out.n_updates[t] = ui + 1;
 }
@@ -171,47 +178,62 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
 #pragma unroll
         for (int k = 0; k < 10; ++k) sc.at(kScratchPs + k) = Ps[k];
     }
+    // Statistics stored by the forward pass replace the sigma-point recomputation for every step
+    // but step 0: state 0 is the PRIOR (kalman_filter.py:76-81), which the filter never predicted
+    // from (it predicted from the prior's update), so its statistics do not exist.
+    const bool use_stats = a.out.smooth_stats && !(a.out.status[t] & STE_STATUS_SMOOTH_RECOMPUTE);
     bool bad = false;
 #pragma unroll 1
     for (int step = nt - 1; step >= 0; --step) {
         const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
         const double *cf = a.out.cov_f + ((int64_t)step * 16) * ld + t;
-        double xf[4], s1[4], Pb[10];
-        const double dt = a.in.dt[(int64_t)step * ld + t];
-        const int ri = min_(step / rep, a.prob.max_obs - 1);
-        const double sr = a.in.sog_rate[(int64_t)ri * ld + t];
-        const double cr = a.in.cog_rate[(int64_t)ri * ld + t];
+        double xf[4], xs[4], Ps[10];
 #pragma unroll
         for (int r = 0; r < 4; ++r) xf[r] = mf[r * ld];
-        {
-            double Pf[10];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
-            if (step > 0) {   // pull the next (earlier) state towards L2 while this step computes
-#pragma unroll
-                for (int r = 0; r < 4; ++r) prefetch_l2(mf + (r - 4) * ld);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = i; j < 4; ++j) prefetch_l2(cf + (i * 4 + j - 16) * ld);
-                prefetch_l2(a.in.dt + (int64_t)(step - 1) * ld + t);
-            }
-            urtss_moments(xf, Pf, a.prob.Q, dt, sr, cr, s1, Pb, status, sc);
-        }
         double e[4] = {0.0, 0.0, 0.0, 0.0};
         if (a.in.noise_bwd) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 e[r] = a.in.noise_bwd[((int64_t)step * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
-        double Pf[10], xs[4], Ps[10];   // Pf again (L2-resident) rather than held across phase 1
+        if (use_stats && step > 0) {
+            double Pf[10];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
-        urtss_gain(xf, Pf, s1, Pb, e, xs, Ps, status, sc);
+                for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+            urtss_step_from_stats(xf, Pf, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, e, xs, Ps,
+                                  status, sc);
+        } else {
+            double s1[4], Pb[10];
+            const double dt = a.in.dt[(int64_t)step * ld + t];
+            const int ri = min_(step / rep, a.prob.max_obs - 1);
+            const double sr = a.in.sog_rate[(int64_t)ri * ld + t];
+            const double cr = a.in.cog_rate[(int64_t)ri * ld + t];
+            {
+                double Pf[10];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+                if (step > 0) {   // pull the next (earlier) state towards L2 while this step computes
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) prefetch_l2(mf + (r - 4) * ld);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = i; j < 4; ++j) prefetch_l2(cf + (i * 4 + j - 16) * ld);
+                    prefetch_l2(a.in.dt + (int64_t)(step - 1) * ld + t);
+                }
+                urtss_moments(xf, Pf, a.prob.Q, dt, sr, cr, s1, Pb, status, sc);
+            }
+            double Pf[10];   // again (L2-resident) rather than held across the sigma-point loop
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+            urtss_gain(xf, Pf, s1, Pb, e, xs, Ps, status, sc);
+        }
         store_state(a.out.mean_s, a.out.cov_s, ld, step, t, xs, Ps);
         bad |= any_nonfinite(xs, Ps);
     }

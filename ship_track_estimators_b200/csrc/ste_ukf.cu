@@ -25,7 +25,7 @@ constexpr int kThreads = 128;
 
 template <bool POS_ONLY, bool GATING>
 __global__ void __launch_bounds__(kThreads, STE_FWD_MIN_BLOCKS) ukf_forward_kernel(const __grid_constant__ KernelArgs a) {
-    __shared__ double scratch[kScratchSlots * kThreads];
+    __shared__ double scratch[kScratchSlotsFwd * kThreads];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kThreads) ukf_predict_kernel(const __grid_cons
     int status = 0;
     __shared__ double scratch[kScratchSlots * kThreads];
     ukf_predict(x, P, a.prob.Q, a.dt[t], a.sog_rate[t], a.cog_rate[t], e, status, Scratch{scratch + threadIdx.x, kThreads},
-                a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, ld);
+                a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, nullptr, ld);
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
     store_xP(a, t, x, P);
     if (a.status) a.status[t] = status;

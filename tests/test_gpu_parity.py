@@ -194,6 +194,15 @@ def test_full_size_properties(cuda, native_lib):
         assert (torch.diagonal(M, dim1=1, dim2=2) > 0).all()
     # smoothing cannot increase the variance of the position estimate on these well-observed tracks
     assert (a.cov_s[:, 0] <= a.cov_f[:, 0] * (1 + 1e-9)).all()
+    # smoother statistics reused from the forward pass vs recomputed from the sigma points (what the
+    # reference does): the same quantities up to rounding
+    nr = ukf.run(batch, res=ukf.allocate(batch, reuse_stats=False))
+    assert nr.smooth_stats is None and a.smooth_stats is not None
+    dm = nr.mean_s - a.mean_s
+    dm[:, 3] = torch.remainder(dm[:, 3] + 180.0, 360.0) - 180.0
+    assert float((dm.abs() / a.mean_s.abs().clamp(min=1.0)).max()) <= 1e-10
+    assert float(((nr.cov_s - a.cov_s).abs() / a.cov_s.abs().amax(dim=1, keepdim=True)).max()) <= 1e-10
+    assert torch.equal(nr.mean_f, a.mean_f) and torch.equal(nr.cov_f, a.cov_f)
     # in place
     c = ukf.run(batch, in_place=True)
     assert c.mean_s is c.mean_f

@@ -18,7 +18,7 @@ extern "C" int emul_forward(const SteProblem *prob, const SteInputs *in, SteOutp
             if ((i >= 2 || j >= 2) && prob->R[i * 4 + j] != 0.0) pos = false;
         }
     const bool gating = prob->flags & STE_FLAG_GATING;
-    double scratch[kScratchSlots];
+    double scratch[kScratchSlotsFwd];
     const Scratch sc{scratch, 1};
     for (int t = 0; t < prob->n_tracks; ++t) {
         if (pos) { if (gating) forward_track<true, true>(a, t, sc); else forward_track<true, false>(a, t, sc); }
