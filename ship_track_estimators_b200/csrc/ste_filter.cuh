@@ -28,7 +28,8 @@ struct Scratch {
 constexpr int kScratchRoot = 0;   // 16 slots: M[r][c] at kScratchRoot + c * 4 + r (column-major)
 constexpr int kScratchSlots = 16;          // single-step kernels: the root only
 constexpr int kScratchDeltaFwd = 16;       // forward filter with smoother statistics: Delta_c, 16 slots
-constexpr int kScratchSlotsFwd = 32;
+constexpr int kScratchObs = 32;            // 4 slots: the observation staged for this step's update
+constexpr int kScratchSlotsFwd = 36;
 
 // Smoother statistics ("tape") the forward pass can emit for every predict, so that the backward
 // pass need not regenerate and re-propagate the sigma points of the same filtered state (the

@@ -348,8 +348,13 @@ STE_DEV void angle_add_pair(const AngleTrig &b, const AngleTrig &o, AngleTrig &p
 }
 
 // x = [lon, lat, u, cog] of the sigma point, t = trig of its (lat, cog, u dt / R)
+#ifdef STE_FINISH_NOINLINE
+#define STE_FINISH_ATTR STE_COLD
+#else
+#define STE_FINISH_ATTR STE_DEV
+#endif
 template <bool LIB>
-STE_DEV void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt, double sog_rate,
+STE_FINISH_ATTR void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt, double sog_rate,
                              double cog_rate, double (&y)[4]) {
     const double east = t.sd * t.sa;
     const double sdca = t.sd * t.ca;

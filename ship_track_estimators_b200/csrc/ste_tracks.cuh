@@ -11,6 +11,22 @@ namespace ste {
 template <typename T>
 STE_DEV T min_(T a, T b) { return a < b ? a : b; }
 
+// Asynchronous 8-byte global -> shared copy (LDGSTS): stages an input for later in the step
+// without holding a register across the long sigma-point loop.  The host sandbox copies directly.
+STE_DEV void stage_async(double *smem_dst, const double *gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
+#else
+    *smem_dst = *gmem_src;
+#endif
+}
+STE_DEV void stage_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 struct KernelArgs {
     SteProblem prob;
     SteInputs in;
@@ -71,10 +87,22 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
     int status = 0;
     store_state(a.out.mean_f, a.out.cov_f, ld, 0, t, x, P);  // the prior (kalman_filter.py:76-77)
 
+    // observation rows are staged into scratch by stage_obs() a whole predict ahead of their use
+    auto stage_obs = [&](int ui) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if ((!POS_ONLY || r < 2) && a.in.z[r]) stage_async(&sc.at(kScratchObs + r), a.in.z[r] + (int64_t)ui * ld + t);
+        }
+    };
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sc.at(kScratchObs + r) = 0.0;   // absent rows read as 0
+    stage_obs(0);
+
     auto assimilate = [&](int ui) {
         double z[4], un[4];
+        stage_wait();
 #pragma unroll
-        for (int r = 0; r < 4; ++r) z[r] = a.in.z[r] ? a.in.z[r][(int64_t)ui * ld + t] : 0.0;
+        for (int r = 0; r < 4; ++r) z[r] = sc.at(kScratchObs + r);
         const double *noise = nullptr;
         if (a.in.noise_upd) {
 #pragma unroll
@@ -110,6 +138,9 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
     bool consistent = true;
 #pragma unroll 1
     for (int s = -1; s < nt; ++s) {
+#if defined(STE_STEP_SYNC) && defined(__CUDA_ARCH__)
+        __syncthreads();   // experiment: keep the warps of a block in phase (uniform track lengths only)
+#endif
         if (s >= 0) {
             consistent &= (min_(ri, a.prob.max_obs - 1) == ui);
             if (++rc == rep) {
@@ -117,6 +148,7 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
                 ++ri;
             }
             double *stats = a.out.smooth_stats ? a.out.smooth_stats + ((int64_t)s * kStatsPlanes) * ld + t : nullptr;
+            if (upd && ui + 1 < a.prob.max_obs) stage_obs(ui + 1);   // lands while the predict runs
             double e[4] = {0.0, 0.0, 0.0, 0.0};
             if (a.in.noise_pred) {
 #pragma unroll

@@ -13,11 +13,14 @@
 
 namespace ste {
 
-constexpr int kThreads = 128;
+#ifndef STE_THREADS
+#define STE_THREADS 128
+#endif
+constexpr int kThreads = STE_THREADS;
 // Minimum resident blocks per SM the register allocator must make room for (occupancy is bounded by
 // registers only: these kernels use 16 KB of shared memory per block and almost no bandwidth).
 #ifndef STE_FWD_MIN_BLOCKS
-#define STE_FWD_MIN_BLOCKS 4
+#define STE_FWD_MIN_BLOCKS 3
 #endif
 #ifndef STE_BWD_MIN_BLOCKS
 #define STE_BWD_MIN_BLOCKS 4
