@@ -33,6 +33,10 @@ if REPO not in sys.path:
 
 N_STEPS = 1024
 BYTES_FWD, BYTES_BWD = 200.0, 344.0  # algorithmic bytes per track-step at k = 1
+# FP64 operations the kernels issue per track-step, counted from SASS with ncu (profiles/r01_*):
+# 2 * DFMA + DMUL + DADD, forward (with smoother statistics) and backward (from statistics).
+FLOPS_FWD, FLOPS_BWD = 3721.0, 572.0
+FP64_INSTR_FWD, FP64_INSTR_BWD = 2449.0, 320.0  # DFMA + DMUL + DADD + DSETP warp-instructions per track-step
 MODEL = dict(H=[1.0, 1.0, 0.0, 0.0], R=[1e-3, 1e-3, 0.0, 0.0], Q=[1e-2, 1e-2, 1e-4, 1e-4], P=[1.0, 1.0, 1.0, 1.0])
 METRIC = "track-steps/sec (UKF+URTSS fp64)"
 UNIT = "track-steps/s"
@@ -177,6 +181,15 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic():
+    """DRAM bytes per track-step of each kernel from the committed ncu capture (or None)."""
+    path = os.path.join(REPO, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return None
+
+
 def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -298,6 +311,9 @@ def run_gpu_arm(args):
         dom_bytes, dom_ms = (BYTES_BWD, b_ms) if b_ms >= f_ms else (BYTES_FWD, f_ms)
         achieved = dom_bytes * tile_steps / (dom_ms * 1e-3) / 1e9
         step_gbs = (BYTES_FWD + BYTES_BWD) * tile_steps / ((f_ms + b_ms) * 1e-3) / 1e9
+        traffic = measured_traffic()
+        dom_key = "backward" if b_ms >= f_ms else "forward"
+        traffic_launch = traffic[dom_key]["dram_bytes_per_track_step"] * tile_steps if traffic else None
         # FP64 pipe: probe the DFMA peak on this GPU, compare with the counted instructions
         blocks, threads, iters = 148 * 16, 256, 20000
         sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
@@ -314,10 +330,19 @@ def run_gpu_arm(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, T),
             "roofline": {
                 "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_track_step": dom_bytes,
+                "traffic": traffic_launch, "traffic_source": (traffic or {}).get("source"),
+                "peak_source": peak_src, "algorithmic_bytes_per_track_step": dom_bytes,
                 "kernel_ms": dom_ms, "forward_ms": f_ms, "backward_ms": b_ms,
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_track_step": BYTES_FWD + BYTES_BWD},
-                "fp64_pipe": {"peak_tflops_measured": fp64_peak, "note": "DFMA probe (ste_probe_fp64_fma); see DESIGN.md for the per-step instruction counts"},
+                "fp64_pipe": {
+                    "peak_tflops_measured": fp64_peak,
+                    "achieved_tflops_step": (FLOPS_FWD + FLOPS_BWD) * tile_steps / ((f_ms + b_ms) * 1e-3) / 1e12,
+                    "achieved_tflops_forward": FLOPS_FWD * tile_steps / (f_ms * 1e-3) / 1e12,
+                    "frac_forward": FLOPS_FWD * tile_steps / (f_ms * 1e-3) / 1e12 / fp64_peak,
+                    "pipe_busy_forward": FP64_INSTR_FWD * tile_steps / 32.0 * 2.05 / (f_ms * 1e-3 * 592 * 1.965e9),
+                    "note": "flops = 2*DFMA + DMUL + DADD counted with ncu (profiles/); peak = DFMA probe (ste_probe_fp64_fma); "
+                            "pipe_busy = FP64 warp-instructions x 2.05 cycles issue interval over 592 sub-partitions at 1965 MHz",
+                },
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"], "d2h_bytes_per_step": moved["d2h_bytes"],
                     "tile_tracks": Te, "steps": e2e_steps, "outputs": "filtered+smoothed means and full 4x4 covariances to pinned host"},

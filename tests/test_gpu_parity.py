@@ -322,3 +322,35 @@ def test_out_of_range_arguments_take_the_library_path(cuda, native_lib):
     xr, Pr, _, _ = O.predict(x, P, Q_DEF, 1.0, 0.0, 0.0, O.ZeroNoise())
     np.testing.assert_allclose(ukf.x[:3, 0], xr[:3], rtol=1e-10)
     assert cov_err(ukf.P[None], Pr[None]) <= 1e-7  # sin/cos of 1e6 rad: the argument itself carries ~1e-10 rad of rounding
+
+
+def test_cli_end_to_end_matches_golden(cuda, native_lib, tmp_path, monkeypatch):
+    """`track_estimator -i input.json -t ships.csv -s 01203823 -ic primary.id -lat lat -lon lon -rts`
+    (reference examples/cli_example/run.sh) with the noise pinned to zero: the six output files
+    against the reference-generated fixture of the same ship."""
+    import json
+
+    from test_host_dropin import write_track_csv
+    from ship_track_estimators_b200 import ship_track as st_mod
+    from ship_track_estimators_b200.cli import main_cli
+    from ship_track_estimators_b200.utils import haversine_formula, heading
+
+    tr = load_golden("c1_single_ship")[0][0]
+    csv = str(tmp_path / "ships.csv")
+    write_track_csv(csv, "01203823", tr["z"][0], tr["z"][1], tr["dts"])
+    (tmp_path / "input.json").write_text(json.dumps(
+        {"dim": 4, "H": [1, 1, 0, 0], "R": [0.001, 0.001, 0, 0], "Q": [1e-2, 1e-2, 1e-4, 1e-4], "P": [1.0, 1.0, 1.0, 1.0], "dt": -1, "nsteps": 2}))
+    # the fixture was generated with the haversine / great-circle heading pair (geographiclib is absent)
+    monkeypatch.setattr(main_cli, "ShipTrack", lambda: st_mod.ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading))
+    monkeypatch.setattr(np.random, "normal", lambda loc=0.0, scale=1.0, size=None: np.zeros(size))
+    monkeypatch.chdir(tmp_path)
+    main_cli.track_estimator(["-i", "input.json", "-o", "output", "-t", csv, "-s", "01203823", "-ic", "primary.id",
+                              "-lat", "lat", "-lon", "lon", "-rts"])
+    got = {k: np.loadtxt(tmp_path / f"output_01203823_{k}.txt") for k in
+           ("predictions", "variances", "predictions_smoothed", "variances_smoothed", "dts")}
+    assert np.array_equal(got["dts"], tr["dt_array"])
+    assert np.array_equal(np.loadtxt(tmp_path / "original_01203823_track.txt"), np.array((tr["z"][0], tr["z"][1])).T)
+    assert mean_err(got["predictions"], tr["means"]) <= 1e-9 and mean_err(got["predictions_smoothed"], tr["means_s"]) <= 1e-9
+    for key, ref in (("variances", tr["covs"]), ("variances_smoothed", tr["covs_s"])):
+        d = np.diagonal(ref, axis1=1, axis2=2)
+        assert np.max(np.abs(got[key] - d) / np.max(np.abs(d), axis=1, keepdims=True)) <= 1e-9

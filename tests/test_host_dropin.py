@@ -1,0 +1,91 @@
+"""CPU: the host-side drop-ins around the hot path (ShipTrack ingest, CLI parsing, JSON settings).
+Known answers: SURVEY.md section 9.3 (generated from the reference) and the golden fixture of
+BASELINE config 1, whose derived inputs were produced by the reference's own ShipTrack."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from _helpers import load_golden
+from ship_track_estimators_b200.cli.argument_parser import create_parser
+from ship_track_estimators_b200.cli.main_cli import _get_input_matrix, get_input_settings
+from ship_track_estimators_b200.ship_track import ShipTrack
+from ship_track_estimators_b200.utils import haversine_formula, heading
+
+
+def write_track_csv(path, ship_id, lon, lat, dts_hours, id_col="primary.id", extra_rows=()):
+    """A CSV in the reference's data format (yr, mo, dy, hr columns) for the given fixes."""
+    when = pd.Timestamp("1880-03-01") + pd.to_timedelta(np.concatenate(([0.0], np.cumsum(dts_hours))), unit="h")
+    rows = [dict(**{id_col: ship_id}, yr=d.year, mo=d.month, dy=d.day, hr=d.hour, lat=la, lon=lo) for d, lo, la in zip(when, lon, lat)]
+    rows[1:1] = list(extra_rows)
+    # like the reference's historical file, the id column also holds a non-numeric value (there: an
+    # embedded header row), which keeps pandas from parsing ids such as "01203823" as integers
+    rows.append(dict(**{id_col: "id.tidy"}, yr=1880, mo=1, dy=1, hr=0, lat=0.0, lon=0.0))
+    pd.DataFrame(rows).to_csv(path, index=False)
+
+
+def test_ship_track_known_answers(tmp_path):
+    lon = [-30.5, -31.5, -32.5, -33.5, -33.5]; lat = [-0.5, -3.5, -6.5, -8.5, -11.5]
+    csv = str(tmp_path / "t.csv")
+    write_track_csv(csv, "A7", lon, lat, [24, 24, 24, 12], id_col="id",
+                    extra_rows=[dict(id="other", yr=1880, mo=1, dy=1, hr=3, lat=1.0, lon=2.0)])
+    st = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
+    out = st.read_csv(csv, ship_id="A7")
+    assert out[0] is st.lat and np.array_equal(st.dts, [24.0, 24.0, 24.0, 12.0]) and len(st.dates) == 5
+    z = st.get_measurements(include_sog=True, include_cog=True)
+    st.calculate_cog_rate(); st.calculate_sog_rate()
+    assert z.shape == (4, 5) and np.array_equal(z[0], lon)
+    np.testing.assert_allclose(st.sog, [14.666569517825678, 14.66188856000385, 10.35378642995031, 27.829872698318386, 27.829872698318386], rtol=1e-14)
+    np.testing.assert_allclose(st.cog, [198.40941994487474, 198.32831442189988, 206.30510826660182, 180, 180], rtol=1e-14)
+    np.testing.assert_allclose(st.sog_rate, [0, -1.9503990924281864e-04, -1.7950425541889756e-01, 7.2817026118200323e-01, 0], rtol=1e-10)
+    np.testing.assert_allclose(st.cog_rate, [0, -0.00337939679061942, 0.33236641019591434, -1.0960461777750758, 0], rtol=1e-10)
+    assert st.get_measurements().shape == (2, 5)
+    rev = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
+    rev.read_csv(csv, ship_id="A7", reverse=True)
+    assert np.array_equal(rev.lon, lon[::-1]) and np.array_equal(rev.dts, [12.0, 24.0, 24.0, 24.0])
+    with pytest.raises(ValueError, match="No data found"):
+        ShipTrack().read_csv(csv, ship_id="nobody")
+
+
+def test_ship_track_reproduces_reference_derived_inputs(tmp_path):
+    """BASELINE config 1 (ship 01203823): rebuilding the CSV rows from the fixture and ingesting
+    them gives the z / rates the reference's ShipTrack produced."""
+    tr = load_golden("c1_single_ship")[0][0]
+    csv = str(tmp_path / "ship.csv")
+    write_track_csv(csv, "01203823", tr["z"][0], tr["z"][1], tr["dts"])
+    st = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
+    st.read_csv(csv, ship_id="01203823", id_col="primary.id")
+    z = st.get_measurements(include_sog=True, include_cog=True)
+    st.calculate_cog_rate(); st.calculate_sog_rate()
+    np.testing.assert_allclose(st.dts, tr["dts"], rtol=0, atol=0)
+    np.testing.assert_allclose(z, tr["z"], rtol=1e-13)
+    np.testing.assert_allclose(st.sog_rate, tr["sog_rate"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(st.cog_rate, tr["cog_rate"], rtol=1e-9, atol=1e-13)
+
+
+def test_cli_flags_and_settings(tmp_path):
+    args = create_parser().parse_args(["-t", "d.csv", "-s", "01203823", "-ic", "primary.id", "-lat", "lat", "-lon", "lon", "-rts"])
+    assert (args.input_file, args.output_prefix, args.track_file, args.ship_id) == ("input.json", "output", "d.csv", "01203823")
+    assert args.apply_rts_smoother and not args.reverse and args.id_col == "primary.id" and args.lat_id == "lat"
+    with pytest.raises(SystemExit):
+        create_parser().parse_args(["-s", "x"])  # -t is required
+    cfg = {"dim": 4, "H": [1, 1, 0, 0], "R": [0.001, 0.001, 0, 0], "Q": [1e-2, 1e-2, 1e-4, 1e-4], "P": [1.0, 1.0, 1.0, 1.0], "dt": -1, "nsteps": 2}
+    dim, dt, nsteps, H, Q, R, P, sm = get_input_settings(cfg)
+    assert (dim, dt, nsteps, sm) == (4, -1, 2, None)
+    assert np.array_equal(H, np.diag([1, 1, 0, 0])) and np.array_equal(R, np.diag([0.001, 0.001, 0, 0]))
+    full = dict(cfg, P=np.eye(4).tolist(), smooth=2)
+    assert np.array_equal(get_input_settings(full)[6], np.eye(4)) and get_input_settings(full)[7] == 2
+    for missing in ("dim", "dt", "nsteps", "H"):
+        with pytest.raises(KeyError):
+            get_input_settings({k: v for k, v in cfg.items() if k != missing})
+    with pytest.raises(AssertionError):
+        _get_input_matrix({"H": [1, 1, 0]}, "H", 4)
+    with pytest.raises(AssertionError):
+        _get_input_matrix({"H": [[1, 0], [0, 1], [0, 0], [0, 0]]}, "H", 4)
+    p = tmp_path / "input.json"
+    p.write_text(json.dumps(cfg))
+    from ship_track_estimators_b200.cli.json_loader import load_input_json
+
+    assert load_input_json(str(p)) == cfg
