@@ -29,7 +29,8 @@ constexpr int kScratchRoot = 0;   // 16 slots: M[r][c] at kScratchRoot + c * 4 +
 constexpr int kScratchSlots = 16;          // single-step kernels: the root only
 constexpr int kScratchDeltaFwd = 16;       // forward filter with smoother statistics: Delta_c, 16 slots
 constexpr int kScratchObs = 32;            // 4 slots: the observation staged for this step's update
-constexpr int kScratchSlotsFwd = 36;
+constexpr int kScratchIn = 36;             // 3 slots: dt, sog_rate, cog_rate staged for the next step
+constexpr int kScratchSlotsFwd = 40;
 
 // Smoother statistics ("tape") the forward pass can emit for every predict, so that the backward
 // pass need not regenerate and re-propagate the sigma points of the same filtered state (the

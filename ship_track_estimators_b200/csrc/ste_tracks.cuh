@@ -122,12 +122,7 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
         }
     };
 
-    // Step -1 is the initial update with z[:, 0] (kalman_filter.py:81); steps 0..nt-1 predict and
-    // assimilate when the step ends on an observation time.  One rolled loop keeps a single
-    // instance of the predict and update code in the instruction cache.
     int ui = 0;
-    double dt = 0.0, sr = 0.0, cr = 0.0;
-    bool upd = true;
     // The smoother statistics are valid for the backward pass only if it would read the same
     // rates: it indexes them by step / rate_repeat (unscented.py:287-311), the filter by the
     // update index.  They agree on every regular step grid; a track where they do not is flagged
@@ -136,45 +131,57 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
     rep = rep > 0 ? rep : 1;
     int ri = 0, rc = 0;
     bool consistent = true;
+
+    // Inputs of step s (dt, the two rates, the observation of its update) are staged into shared
+    // scratch with cp.async one whole step ahead: no register is held across the sigma-point loop
+    // and the DRAM latency hides behind ~4000 instructions of the previous step.
+    auto stage_step = [&](int s, int rate_index) {
+        stage_async(&sc.at(kScratchIn + 0), a.in.dt + (int64_t)s * ld + t);
+        stage_async(&sc.at(kScratchIn + 1), a.in.sog_rate + (int64_t)rate_index * ld + t);
+        stage_async(&sc.at(kScratchIn + 2), a.in.cog_rate + (int64_t)rate_index * ld + t);
+    };
+    auto step_updates = [&](int s) -> bool {
+        return a.in.upd_mask ? (a.in.upd_mask[(int64_t)s * ld + t] != 0) : ((s + 1) % k_sub == 0);
+    };
+    bool upd_next = false;
+    if (nt > 0) {
+        stage_step(0, 0);
+        upd_next = step_updates(0);
+    }
+    assimilate(0);   // kalman_filter.py:81 (waits for the staged copies, including step 0's inputs)
+
 #pragma unroll 1
-    for (int s = -1; s < nt; ++s) {
+    for (int s = 0; s < nt; ++s) {
 #if defined(STE_STEP_SYNC) && defined(__CUDA_ARCH__)
         __syncthreads();   // experiment: keep the warps of a block in phase (uniform track lengths only)
 #endif
-        if (s >= 0) {
-            consistent &= (min_(ri, a.prob.max_obs - 1) == ui);
-            if (++rc == rep) {
-                rc = 0;
-                ++ri;
-            }
-            double *stats = a.out.smooth_stats ? a.out.smooth_stats + ((int64_t)s * kStatsPlanes) * ld + t : nullptr;
-            if (upd && ui + 1 < a.prob.max_obs) stage_obs(ui + 1);   // lands while the predict runs
-            double e[4] = {0.0, 0.0, 0.0, 0.0};
-            if (a.in.noise_pred) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
-            }
-            ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld);
-            if (upd) {
-                if (ui + 1 < a.prob.max_obs) {
-                    ++ui;
-                } else {
-                    status |= STE_STATUS_OBS_OVERRUN;
-                }
-            }
+        const bool upd = upd_next;
+        const double dt = sc.at(kScratchIn + 0), sr = sc.at(kScratchIn + 1), cr = sc.at(kScratchIn + 2);
+        consistent &= (min_(ri, a.prob.max_obs - 1) == ui);
+        if (++rc == rep) {
+            rc = 0;
+            ++ri;
         }
-        const bool do_upd = upd;
-        // prefetch the next step's inputs before the update / store
+        const bool advance = upd && (ui + 1 < a.prob.max_obs);
+        if (upd && !advance) status |= STE_STATUS_OBS_OVERRUN;
+        // stage what this step's update and the next step's predict will read
+        if (advance) stage_obs(ui + 1);
         if (s + 1 < nt) {
-            const int64_t o = (int64_t)(s + 1) * ld + t;
-            dt = a.in.dt[o];
-            upd = a.in.upd_mask ? (a.in.upd_mask[o] != 0) : ((s + 2) % k_sub == 0);
-            sr = a.in.sog_rate[(int64_t)ui * ld + t];
-            cr = a.in.cog_rate[(int64_t)ui * ld + t];
+            stage_step(s + 1, ui + (advance ? 1 : 0));
+            upd_next = step_updates(s + 1);
         }
-        if (do_upd) assimilate(ui);
-        if (s >= 0) store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, x, P);
+        double *stats = a.out.smooth_stats ? a.out.smooth_stats + ((int64_t)s * kStatsPlanes) * ld + t : nullptr;
+        double e[4] = {0.0, 0.0, 0.0, 0.0};
+        if (a.in.noise_pred) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
+        }
+        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld);
+        if (advance) ++ui;
+        if (upd) assimilate(ui);
+        else stage_wait();   // the next step's inputs must have landed before they are read
+        store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, x, P);
     }
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
     if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;

@@ -68,13 +68,14 @@ for r in rows:
         hdr = {n: i for i, n in enumerate(r)}
     elif take and hdr and r:
         try:
-            counts[int(r[hdr["Address"]], 16) if r[hdr["Address"]].startswith("0x") else int(r[hdr["Address"]])] = (float(r[hdr["Instructions Executed"]]), r[hdr["Source"]])
+            counts[int(r[hdr["Address"]], 16) if r[hdr["Address"]].startswith("0x") else int(r[hdr["Address"]])] = (float(r[hdr["Instructions Executed"]]), r[hdr["Source"]], float(r[hdr["# Samples"]] or 0), {k: float(r[i] or 0) for k, i in hdr.items() if k.startswith("stall_") and "Not Issued" not in k})
         except ValueError:
             pass
 base = min(counts) if counts else 0
 inner, path_tot, fp64_inner = collections.Counter(), collections.Counter(), collections.Counter()
 tot = 0
-for addr, (n, src) in counts.items():
+samples, stall_by = collections.Counter(), collections.defaultdict(collections.Counter)
+for addr, (n, src, smp, stl) in counts.items():
     ch = chains.get(addr - base, [])
     names = [func_of(p, ln) for p, ln, _ in ch] or ["?"]
     # collapse consecutive duplicates, innermost first
@@ -84,6 +85,10 @@ for addr, (n, src) in counts.items():
             dedup.append(x)
     inner[dedup[0]] += n
     path_tot[" < ".join(dedup[:4])] += n
+    key3 = " < ".join(dedup[:3])
+    samples[key3] += smp
+    for k, v in stl.items():
+        stall_by[key3][k] += v
     op = re.match(r"(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", src.strip())
     if op and op.group(1) in ("DFMA", "DMUL", "DADD", "DSETP"):
         fp64_inner[" < ".join(dedup[:4])] += n
@@ -95,3 +100,9 @@ for k, v in inner.most_common(20):
 print("-- by inline path (innermost < callers), all / FP64-pipe")
 for k, v in path_tot.most_common(40):
     print(f"   {k:90s} {v/per:8.1f} {fp64_inner[k]/per:8.1f}")
+
+tot_s = sum(samples.values())
+print("-- stall samples by inline path (share of all samples; top stall reasons)")
+for k, v in samples.most_common(16):
+    top = ", ".join(f"{a[6:]} {100*b/max(v,1):.0f}%" for a, b in stall_by[k].most_common(4))
+    print(f"   {k:72s} {100*v/tot_s:5.1f}%   {top}")
