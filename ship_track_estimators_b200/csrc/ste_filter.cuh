@@ -101,7 +101,7 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
             xm[r] = x[r] - m[r];
         }
         {
-            const AngleTrig off = angle_trig<LIB>(m[1], m[3], m[2], dtR);
+            const AngleTrig off = offset_trig<LIB>(m[1], m[3], m[2], dtR);
             AngleTrig tp, tm;
             angle_add_pair(base, off, tp, tm);
             geodetic_finish<LIB>(xp, tp, dt, sog_rate, cog_rate, yp);
@@ -490,7 +490,7 @@ STE_DEV void urtss_moments_impl(const double (&xf)[4], const double *Q, double d
             xm[r] = xf[r] - m[r];
         }
         {
-            const AngleTrig off = angle_trig<LIB>(m[1], m[3], m[2], dtR);
+            const AngleTrig off = offset_trig<LIB>(m[1], m[3], m[2], dtR);
             AngleTrig tp, tm;
             angle_add_pair(base, off, tp, tm);
             geodetic_finish<LIB>(xp, tp, dt, sog_rate, cog_rate, dp);

@@ -336,6 +336,20 @@ STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dt
     return t;
 }
 
+// trig of the three offset angles of one root column; takes the short series when all three are small
+template <bool LIB>
+STE_DEV AngleTrig offset_trig(double dlat_deg, double dcog_deg, double du, double dtR) {
+    const double a = dlat_deg * kDegToRad, b = dcog_deg * kDegToRad, c = du * dtR;
+    if (!LIB && fabs(a) <= kSmallAngle && fabs(b) <= kSmallAngle && fabs(c) <= kSmallAngle) {
+        AngleTrig t;
+        small_sincos(a, &t.sp, &t.cp);
+        small_sincos(b, &t.sa, &t.ca);
+        small_sincos(c, &t.sd, &t.cd);
+        return t;
+    }
+    return angle_trig<LIB>(dlat_deg, dcog_deg, du, dtR);
+}
+
 // trig of (base + off) and (base - off) from the four shared products per angle
 STE_DEV void angle_add_pair(const AngleTrig &b, const AngleTrig &o, AngleTrig &plus, AngleTrig &minus) {
     double sc_, cs_, cc_, ss_;
