@@ -103,41 +103,82 @@ STE_DEV double seed_rsqrt(double x) {
 #endif
 }
 
-// ---- reciprocal, reciprocal square root, square root, division ------------------------------- //
-// MUFU seed (~20 bits) + Newton steps in the FP64 pipe; no denormal / special-case slow paths:
-// callers guarantee finite, normal, non-zero arguments (or guard the result themselves).
-STE_DEV double fast_rcp(double x) {
-    double y = seed_rcp(x);
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+// ---- lock-step ("vector in a thread") forms ------------------------------------------------------ //
+// Every routine below evaluates N independent arguments stage by stage.  Written this way the N
+// dependency chains sit next to each other in program order and ptxas issues them interleaved:
+// a DFMA has ~9 cycles of latency and a 2-cycle issue interval, so one chain alone leaves the FP64
+// pipe idle three quarters of the time (profiles/: the scalar forms ran chain after chain).
+#define STE_LANES _Pragma("unroll") for (int l = 0; l < N; ++l)
+
+// reciprocal, reciprocal square root, square root, division: MUFU seed (~20 bits) + Newton steps in
+// the FP64 pipe; no denormal / special-case slow paths: callers guarantee finite, normal, non-zero
+// arguments (or guard the result themselves).
+template <int N>
+STE_DEV void fast_rcp_v(const double (&x)[N], double (&y)[N]) {
+    double e[N];
+    STE_LANES y[l] = seed_rcp(x[l]);
+    STE_LANES e[l] = fma(-x[l], y[l], 1.0);
+    STE_LANES y[l] = fma(y[l], e[l], y[l]);
+    STE_LANES e[l] = fma(-x[l], y[l], 1.0);
+    STE_LANES y[l] = fma(y[l], e[l], y[l]);
 }
 
-STE_DEV double fast_rsqrt(double x) {
-    double y = seed_rsqrt(x);
-    // y <- y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2 : cubic convergence, 2^-20 -> 2^-60
-    const double t = x * y;
-    const double e = fma(-t, y, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    return fma(y * e, p, y);
+// y <- y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2 : cubic convergence, 2^-20 -> 2^-60
+template <int N>
+STE_DEV void fast_rsqrt_v(const double (&x)[N], double (&y)[N]) {
+    double t[N], e[N], p[N];
+    STE_LANES y[l] = seed_rsqrt(x[l]);
+    STE_LANES t[l] = x[l] * y[l];
+    STE_LANES e[l] = fma(-t[l], y[l], 1.0);
+    STE_LANES p[l] = fma(0.375, e[l], 0.5);
+    STE_LANES t[l] = y[l] * e[l];
+    STE_LANES y[l] = fma(t[l], p[l], y[l]);
 }
 
 // sqrt for x >= 0 (x == 0 -> 0)
-STE_DEV double fast_sqrt(double x) {
-    const double y = fast_rsqrt(x);
-    double s = x * y;
-    const double r = fma(-s, s, x);   // residual of the rounded product
-    s = fma(0.5 * y, r, s);
-    return (x > 0.0) ? s : 0.0;
+template <int N>
+STE_DEV void fast_sqrt_v(const double (&x)[N], double (&s)[N]) {
+    double y[N], r[N];
+    fast_rsqrt_v<N>(x, y);
+    STE_LANES s[l] = x[l] * y[l];
+    STE_LANES r[l] = fma(-s[l], s[l], x[l]);   // residual of the rounded product
+    STE_LANES y[l] = 0.5 * y[l];
+    STE_LANES s[l] = fma(y[l], r[l], s[l]);
+    STE_LANES s[l] = (x[l] > 0.0) ? s[l] : 0.0;
 }
 
+template <int N>
+STE_DEV void fast_div_v(const double (&num)[N], const double (&den)[N], double (&q)[N]) {
+    double r[N], rem[N];
+    fast_rcp_v<N>(den, r);
+    STE_LANES q[l] = num[l] * r[l];
+    STE_LANES rem[l] = fma(-den[l], q[l], num[l]);
+    STE_LANES q[l] = fma(rem[l], r[l], q[l]);
+}
+
+STE_DEV double fast_rcp(double x) {
+    const double xv[1] = {x};
+    double y[1];
+    fast_rcp_v<1>(xv, y);
+    return y[0];
+}
+STE_DEV double fast_rsqrt(double x) {
+    const double xv[1] = {x};
+    double y[1];
+    fast_rsqrt_v<1>(xv, y);
+    return y[0];
+}
+STE_DEV double fast_sqrt(double x) {
+    const double xv[1] = {x};
+    double y[1];
+    fast_sqrt_v<1>(xv, y);
+    return y[0];
+}
 STE_DEV double fast_div(double num, double den) {
-    const double r = fast_rcp(den);
-    const double q = num * r;
-    const double rem = fma(-den, q, num);
-    return fma(rem, r, q);
+    const double n[1] = {num}, d[1] = {den};
+    double q[1];
+    fast_div_v<1>(n, d, q);
+    return q[0];
 }
 
 // ---- sin and cos together --------------------------------------------------------------------- //
@@ -145,53 +186,58 @@ STE_DEV double fast_div(double num, double den) {
 // the range once per filter step and take the library ("cold") path otherwise.
 constexpr double kSinCosMaxArg = 105615.0;
 
-STE_DEV void fast_sincos(double x, double *sn, double *cs) {
+template <int N>
+STE_DEV void fast_sincos_v(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
+    double t[N], n[N], r[N], z[N], ps[N], pc[N], s[N], c[N];
+    uint32_t q[N];
     // n = rint(x * 2/pi) through the magic-number trick; the low word of t holds n (two's complement)
-    const double t = fma(x, kTrigK[3], kTrigK[4]);
-    const uint32_t q = (uint32_t)f64_bits(t);
-    const double n = t - kTrigK[4];
-    double r = fma(-n, kTrigK[0], x);
-    r = fma(-n, kTrigK[1], r);
-    r = fma(-n, kTrigK[2], r);
-    const double z = r * r;
+    STE_LANES t[l] = fma(x[l], kTrigK[3], kTrigK[4]);
+    STE_LANES q[l] = (uint32_t)f64_bits(t[l]);
+    STE_LANES n[l] = t[l] - kTrigK[4];
+    STE_LANES r[l] = fma(-n[l], kTrigK[0], x[l]);
+    STE_LANES r[l] = fma(-n[l], kTrigK[1], r[l]);
+    STE_LANES r[l] = fma(-n[l], kTrigK[2], r[l]);
+    STE_LANES z[l] = r[l] * r[l];
     // sin(r) = r + r z (S1 + z (S2 + ... )) ; cos(r) = 1 - z/2 + z^2 (C1 + z (C2 + ...))
-    double ps = fma(z, kSinC[5], kSinC[4]);
-    double pc = fma(z, kCosC[5], kCosC[4]);
-    ps = fma(z, ps, kSinC[3]);
-    pc = fma(z, pc, kCosC[3]);
-    ps = fma(z, ps, kSinC[2]);
-    pc = fma(z, pc, kCosC[2]);
-    ps = fma(z, ps, kSinC[1]);
-    pc = fma(z, pc, kCosC[1]);
-    ps = fma(z, ps, kSinC[0]);
-    pc = fma(z, pc, kCosC[0]);
-    const double s = fma(r * z, ps, r);
-    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    STE_LANES { ps[l] = fma(z[l], kSinC[5], kSinC[4]); pc[l] = fma(z[l], kCosC[5], kCosC[4]); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[3]); pc[l] = fma(z[l], pc[l], kCosC[3]); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[2]); pc[l] = fma(z[l], pc[l], kCosC[2]); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[1]); pc[l] = fma(z[l], pc[l], kCosC[1]); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[0]); pc[l] = fma(z[l], pc[l], kCosC[0]); }
+    STE_LANES { s[l] = fma(r[l] * z[l], ps[l], r[l]); c[l] = fma(z[l] * z[l], pc[l], fma(-0.5, z[l], 1.0)); }
     // quadrant: q & 1 swaps, bit 1 of q / (q + 1) flips the signs (integer pipe)
-    const bool swap = q & 1u;
-    const double so = swap ? c : s;
-    const double co = swap ? s : c;
-    const uint64_t fs = (uint64_t)(q & 2u) << 62, fc = (uint64_t)((q + 1u) & 2u) << 62;
-    *sn = f64_from_bits(f64_bits(so) ^ fs);
-    *cs = f64_from_bits(f64_bits(co) ^ fc);
+    STE_LANES {
+        const bool swap = q[l] & 1u;
+        const double so = swap ? c[l] : s[l];
+        const double co = swap ? s[l] : c[l];
+        const uint64_t fs = (uint64_t)(q[l] & 2u) << 62, fc = (uint64_t)((q[l] + 1u) & 2u) << 62;
+        sn[l] = f64_from_bits(f64_bits(so) ^ fs);
+        cs[l] = f64_from_bits(f64_bits(co) ^ fc);
+    }
 }
 
-// sin and cos of a SMALL angle, |x| <= kSmallAngle: no range reduction, series cut after the terms
+// sin and cos of SMALL angles, |x| <= kSmallAngle: no range reduction, series cut after the terms
 // that still matter at that size (next omitted terms: 2.3e-17 relative for sin, 1.7e-18 for cos).
 // The sigma-point offsets of a converged filter are a few degrees at most.
 constexpr double kSmallAngle = 0.125;
 
-STE_DEV void small_sincos(double x, double *sn, double *cs) {
-    const double z = x * x;
-    double ps = fma(z, kSinC[3], kSinC[2]);
-    double pc = fma(z, kCosC[4], kCosC[3]);
-    ps = fma(z, ps, kSinC[1]);
-    pc = fma(z, pc, kCosC[2]);
-    ps = fma(z, ps, kSinC[0]);
-    pc = fma(z, pc, kCosC[1]);
-    pc = fma(z, pc, kCosC[0]);
-    *sn = fma(x * z, ps, x);
-    *cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+template <int N>
+STE_DEV void small_sincos_v(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
+    double z[N], ps[N], pc[N];
+    STE_LANES z[l] = x[l] * x[l];
+    STE_LANES { ps[l] = fma(z[l], kSinC[3], kSinC[2]); pc[l] = fma(z[l], kCosC[4], kCosC[3]); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[1]); pc[l] = fma(z[l], pc[l], kCosC[2]); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[0]); pc[l] = fma(z[l], pc[l], kCosC[1]); }
+    STE_LANES pc[l] = fma(z[l], pc[l], kCosC[0]);
+    STE_LANES { sn[l] = fma(x[l] * z[l], ps[l], x[l]); cs[l] = fma(z[l] * z[l], pc[l], fma(-0.5, z[l], 1.0)); }
+}
+
+STE_DEV void fast_sincos(double x, double *sn, double *cs) {
+    const double xv[1] = {x};
+    double s[1], c[1];
+    fast_sincos_v<1>(xv, s, c);
+    *sn = s[0];
+    *cs = c[0];
 }
 
 // ---- atan2 ------------------------------------------------------------------------------------- //
@@ -199,37 +245,50 @@ STE_DEV void small_sincos(double x, double *sn, double *cs) {
 // q = mn/mx (mn <= tan(pi/8) mx) or q = (mn - mx)/(mn + mx) (then atan = pi/4 + atan q), |q| <= 0.4143.
 // Branch-free for finite arguments; (0, 0) -> 0 (the sign conventions of atan2(+-0, -0) are not
 // reproduced, the filter never needs them); non-finite input gives NaN.
-// X_NONNEG: the caller guarantees x >= 0 (latitude from (up, horizontal)).
+template <int N>
+STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&out)[N]) {
+    double mx[N], mn[N], num[N], den[N], q[N], z[N], w[N], s1[N], s2[N], p[N], off[N], sg[N];
+    bool swap[N], big[N];
+    STE_LANES {
+        const double ay = fabs(y[l]), ax = fabs(x[l]);
+        swap[l] = ay > ax;
+        mx[l] = swap[l] ? ay : ax;
+        mn[l] = swap[l] ? ax : ay;
+    }
+    STE_LANES {
+        big[l] = mn[l] > kTanPiEighth * mx[l];
+        num[l] = big[l] ? mn[l] - mx[l] : mn[l];
+        const double d = big[l] ? mn[l] + mx[l] : mx[l];
+        den[l] = (f64_bits(mx[l]) << 1) != 0 ? d : 1.0;          // (0, 0): 0 / 1
+    }
+    fast_div_v<N>(num, den, q);
+    STE_LANES z[l] = q[l] * q[l];
+    STE_LANES w[l] = z[l] * z[l];
+    STE_LANES { s1[l] = fma(w[l], kAtanC[10], kAtanC[8]); s2[l] = fma(w[l], kAtanC[9], kAtanC[7]); }
+    STE_LANES { s1[l] = fma(w[l], s1[l], kAtanC[6]); s2[l] = fma(w[l], s2[l], kAtanC[5]); }
+    STE_LANES { s1[l] = fma(w[l], s1[l], kAtanC[4]); s2[l] = fma(w[l], s2[l], kAtanC[3]); }
+    STE_LANES { s1[l] = fma(w[l], s1[l], kAtanC[2]); s2[l] = fma(w[l], s2[l], kAtanC[1]); }
+    STE_LANES s1[l] = fma(w[l], s1[l], kAtanC[0]);
+    STE_LANES p[l] = fma(-q[l], fma(z[l], s1[l], w[l] * s2[l]), q[l]);   // atan(q) = q - q (z s1 + w s2)
+    // angle of (mx, mn) in [0, pi/4], then undo the reflections: r = off + sg * p
+    STE_LANES {
+        off[l] = big[l] ? kPiQuarter : 0.0;
+        sg[l] = 1.0;
+        if (swap[l]) { off[l] = kPiHalf - off[l]; sg[l] = -1.0; }
+        if ((int64_t)f64_bits(x[l]) < 0) { off[l] = kPi - off[l]; sg[l] = -sg[l]; }
+    }
+    STE_LANES {
+        const double r = fma(sg[l], p[l], off[l]);
+        out[l] = f64_from_bits(f64_bits(r) | (f64_bits(y[l]) & 0x8000000000000000ull));   // copysign(r >= 0, y)
+    }
+}
+
 template <bool X_NONNEG>
 STE_DEV double fast_atan2(double y, double x) {
-    const double ay = fabs(y), ax = X_NONNEG ? x : fabs(x);
-    const bool swap = ay > ax;
-    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
-    const bool big = mn > kTanPiEighth * mx;
-    const double num = big ? mn - mx : mn;
-    double den = big ? mn + mx : mx;
-    den = (f64_bits(mx) << 1) != 0 ? den : 1.0;          // (0, 0): 0 / 1
-    const double q = fast_div(num, den);
-    const double z = q * q, w = z * z;
-    double s1 = fma(w, kAtanC[10], kAtanC[8]);
-    double s2 = fma(w, kAtanC[9], kAtanC[7]);
-    s1 = fma(w, s1, kAtanC[6]);
-    s2 = fma(w, s2, kAtanC[5]);
-    s1 = fma(w, s1, kAtanC[4]);
-    s2 = fma(w, s2, kAtanC[3]);
-    s1 = fma(w, s1, kAtanC[2]);
-    s2 = fma(w, s2, kAtanC[1]);
-    s1 = fma(w, s1, kAtanC[0]);
-    const double p = fma(-q, fma(z, s1, w * s2), q);   // atan(q) = q - q (z s1 + w s2)
-    // angle of (mx, mn) in [0, pi/4], then undo the reflections; r = off + sgn * p
-    double off = big ? kPiQuarter : 0.0;
-    double sg = 1.0;
-    if (swap) { off = kPiHalf - off; sg = -sg; }
-    if (!X_NONNEG) {
-        if ((int64_t)f64_bits(x) < 0) { off = kPi - off; sg = -sg; }
-    }
-    const double r = fma(sg, p, off);
-    return f64_from_bits(f64_bits(r) | (f64_bits(y) & 0x8000000000000000ull));   // copysign(r >= 0, y)
+    const double yv[1] = {y}, xv[1] = {x};
+    double o[1];
+    fast_atan2_v<1>(yv, xv, o);
+    return o[0];
 }
 
 }  // namespace ste

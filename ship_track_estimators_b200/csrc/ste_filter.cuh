@@ -93,7 +93,11 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
     for (int k = 0; k < 10; ++k) s2[k] = 0.0;
 #pragma unroll 1
     for (int col = 0; col < 4; ++col) {
-        double m[4], xp[4], xm[4], yp[4], ym[4];
+#if defined(STE_STEP_SYNC) && (STE_STEP_SYNC >= 2) && defined(__CUDA_ARCH__)
+        __syncthreads();
+#endif
+        double m[4], xx[2][4], yy[2][4];
+        double (&xp)[4] = xx[0], (&xm)[4] = xx[1], (&yp)[4] = yy[0], (&ym)[4] = yy[1];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             m[r] = sc.at(kScratchRoot + col * 4 + r);
@@ -102,10 +106,9 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
         }
         {
             const AngleTrig off = offset_trig<LIB>(m[1], m[3], m[2], dtR);
-            AngleTrig tp, tm;
-            angle_add_pair(base, off, tp, tm);
-            geodetic_finish<LIB>(xp, tp, dt, sog_rate, cog_rate, yp);
-            geodetic_finish<LIB>(xm, tm, dt, sog_rate, cog_rate, ym);
+            AngleTrig tt[2];
+            angle_add_pair(base, off, tt[0], tt[1]);
+            geodetic_finish_n<LIB, 2>(xx, tt, dt, sog_rate, cog_rate, yy);
         }
         if (sig_prior) {
 #pragma unroll
@@ -482,7 +485,8 @@ STE_DEV void urtss_moments_impl(const double (&xf)[4], const double *Q, double d
     }
 #pragma unroll 1
     for (int col = 0; col < 4; ++col) {
-        double m[4], xp[4], xm[4], dp[4], dm[4];
+        double m[4], xx[2][4], dd[2][4];
+        double (&xp)[4] = xx[0], (&xm)[4] = xx[1], (&dp)[4] = dd[0], (&dm)[4] = dd[1];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             m[r] = sc.at(kScratchRoot + col * 4 + r);
@@ -491,10 +495,9 @@ STE_DEV void urtss_moments_impl(const double (&xf)[4], const double *Q, double d
         }
         {
             const AngleTrig off = offset_trig<LIB>(m[1], m[3], m[2], dtR);
-            AngleTrig tp, tm;
-            angle_add_pair(base, off, tp, tm);
-            geodetic_finish<LIB>(xp, tp, dt, sog_rate, cog_rate, dp);
-            geodetic_finish<LIB>(xm, tm, dt, sog_rate, cog_rate, dm);
+            AngleTrig tt[2];
+            angle_add_pair(base, off, tt[0], tt[1]);
+            geodetic_finish_n<LIB, 2>(xx, tt, dt, sog_rate, cog_rate, dd);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {

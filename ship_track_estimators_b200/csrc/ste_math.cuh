@@ -47,29 +47,35 @@ STE_DEV double wrap180(double a) { return py_mod360(a + 180.0) - 180.0; }
 // Rotations on an exactly-zero off-diagonal are the identity, so structurally block-diagonal
 // inputs (S = H P H^T + R with zero rows/columns) keep their exact zeros and unit eigenvectors.
 // ------------------------------------------------------------------------------------------ //
+// Rotation parameters for L disjoint index pairs at once (lock-step: the L dependency chains
+// interleave in the FP64 pipe).  Angle theta in (-pi/4, pi/4] with tan 2 theta = 2 a_pq / (a_qq - a_pp):
+//   cos 2theta = |d| / h,  sin 2theta = sign(d) b / h,   h = hypot(d, b)
+//   cos theta = sqrt((1 + cos 2theta) / 2),  sin theta = sin 2theta / (2 cos theta),  t = tan theta
+// two reciprocal square roots, no division; sin theta keeps full RELATIVE accuracy for tiny
+// rotations because it is a product of accurately rounded factors.
+template <int N>
+STE_DEV void jacobi_params(const double (&app)[N], const double (&aqq)[N], const double (&apq)[N], double (&c)[N],
+                           double (&s)[N], double (&t)[N]) {
+    double d[N], b[N], v[N], rh[N], cc[N], rc[N];
+    STE_LANES { d[l] = aqq[l] - app[l]; b[l] = apq[l] + apq[l]; }
+    STE_LANES v[l] = fma(d[l], d[l], b[l] * b[l]);
+    fast_rsqrt_v<N>(v, rh);
+    STE_LANES cc[l] = fma(0.5, fabs(d[l]) * rh[l], 0.5);
+    fast_rsqrt_v<N>(cc, rc);
+    STE_LANES {
+        const bool skip = (apq[l] == 0.0);                 // also covers d == b == 0 (NaN from 0 * inf)
+        const double s2t = (d[l] >= 0.0 ? b[l] : -b[l]) * rh[l];
+        c[l] = skip ? 1.0 : cc[l] * rc[l];
+        s[l] = skip ? 0.0 : (0.5 * s2t) * rc[l];
+        t[l] = s[l] * (skip ? 1.0 : rc[l]);
+    }
+}
+
 template <int P_, int Q_>
-STE_DEV void jacobi_rotate(double (&a)[10], double (&V)[16]) {
+STE_DEV void jacobi_apply(double (&a)[10], double (&V)[16], double c, double s, double t) {
     const double apq = a[SYM(P_, Q_)];
-    const double app = a[SYM(P_, P_)];
-    const double aqq = a[SYM(Q_, Q_)];
-    // Rotation angle theta in (-pi/4, pi/4] with tan 2 theta = 2 a_pq / (a_qq - a_pp):
-    //   cos 2theta = |d| / h,  sin 2theta = sign(d) b / h,   h = hypot(d, b)
-    //   cos theta = sqrt((1 + cos 2theta) / 2),  sin theta = sin 2theta / (2 cos theta),  t = tan theta
-    // two reciprocal square roots, no division; sin theta keeps full RELATIVE accuracy for tiny
-    // rotations because it is a product of accurately rounded factors.
-    const double d = aqq - app;
-    const double b = apq + apq;
-    const double rh = fast_rsqrt(fma(d, d, b * b));
-    const double c2t = fabs(d) * rh;
-    const double s2t = (d >= 0.0 ? b : -b) * rh;
-    const double cc = fma(0.5, c2t, 0.5);
-    const double rc = fast_rsqrt(cc);
-    const bool skip = (apq == 0.0);                       // also covers d == b == 0 (NaN from 0 * inf)
-    const double c = skip ? 1.0 : cc * rc;
-    const double s = skip ? 0.0 : (0.5 * s2t) * rc;
-    const double t = s * (skip ? 1.0 : rc);
-    a[SYM(P_, P_)] = fma(-t, apq, app);
-    a[SYM(Q_, Q_)] = fma(t, apq, aqq);
+    a[SYM(P_, P_)] = fma(-t, apq, a[SYM(P_, P_)]);
+    a[SYM(Q_, Q_)] = fma(t, apq, a[SYM(Q_, Q_)]);
     a[SYM(P_, Q_)] = 0.0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -85,6 +91,24 @@ STE_DEV void jacobi_rotate(double (&a)[10], double (&V)[16]) {
         V[r * 4 + P_] = fma(c, vrp, -s * vrq);
         V[r * 4 + Q_] = fma(s, vrp, c * vrq);
     }
+}
+
+// two rotations on disjoint index pairs {P1,Q1}, {P2,Q2}: they commute, so their parameters are
+// taken from the same matrix and computed side by side
+template <int P1, int Q1, int P2, int Q2>
+STE_DEV void jacobi_rotate2(double (&a)[10], double (&V)[16]) {
+    const double app[2] = {a[SYM(P1, P1)], a[SYM(P2, P2)]}, aqq[2] = {a[SYM(Q1, Q1)], a[SYM(Q2, Q2)]},
+                 apq[2] = {a[SYM(P1, Q1)], a[SYM(P2, Q2)]};
+    double c[2], s[2], t[2];
+    jacobi_params<2>(app, aqq, apq, c, s, t);
+    jacobi_apply<P1, Q1>(a, V, c[0], s[0], t[0]);
+    jacobi_apply<P2, Q2>(a, V, c[1], s[1], t[1]);
+}
+
+STE_DEV void jacobi_sweep(double (&a)[10], double (&V)[16]) {
+    jacobi_rotate2<0, 1, 2, 3>(a, V);
+    jacobi_rotate2<0, 2, 1, 3>(a, V);
+    jacobi_rotate2<0, 3, 1, 2>(a, V);
 }
 
 // tol2: a pair (p,q) counts as converged when a_pq^2 <= tol2 |a_pp a_qq| (keeps the small
@@ -112,12 +136,7 @@ STE_DEV void jacobi_eig4(double (&a)[10], double (&V)[16], double tol2) {
                 more |= (o2 > tol2 * fabs(a[SYM(p, p)] * a[SYM(q, q)])) && (o2 > floor2);
             }
         if (!more) break;   // also leaves on NaN
-        jacobi_rotate<0, 1>(a, V);
-        jacobi_rotate<2, 3>(a, V);
-        jacobi_rotate<0, 2>(a, V);
-        jacobi_rotate<1, 3>(a, V);
-        jacobi_rotate<0, 3>(a, V);
-        jacobi_rotate<1, 2>(a, V);
+        jacobi_sweep(a, V);
     }
 }
 
@@ -175,12 +194,7 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
     for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
 #pragma unroll 1
     for (int sweep = 0; sweep < 2; ++sweep) {
-        jacobi_rotate<0, 1>(a, V);
-        jacobi_rotate<2, 3>(a, V);
-        jacobi_rotate<0, 2>(a, V);
-        jacobi_rotate<1, 3>(a, V);
-        jacobi_rotate<0, 3>(a, V);
-        jacobi_rotate<1, 2>(a, V);
+        jacobi_sweep(a, V);
     }
     const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
     const double wmax = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
@@ -329,9 +343,10 @@ STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dt
         sincos(cog_deg * kDegToRad, &t.sa, &t.ca);
         sincos(u * dtR, &t.sd, &t.cd);
     } else {
-        fast_sincos(lat_deg * kDegToRad, &t.sp, &t.cp);
-        fast_sincos(cog_deg * kDegToRad, &t.sa, &t.ca);
-        fast_sincos(u * dtR, &t.sd, &t.cd);
+        const double ang[3] = {lat_deg * kDegToRad, cog_deg * kDegToRad, u * dtR};
+        double sn[3], cs[3];
+        fast_sincos_v<3>(ang, sn, cs);
+        t.sp = sn[0]; t.cp = cs[0]; t.sa = sn[1]; t.ca = cs[1]; t.sd = sn[2]; t.cd = cs[2];
     }
     return t;
 }
@@ -339,12 +354,12 @@ STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dt
 // trig of the three offset angles of one root column; takes the short series when all three are small
 template <bool LIB>
 STE_DEV AngleTrig offset_trig(double dlat_deg, double dcog_deg, double du, double dtR) {
-    const double a = dlat_deg * kDegToRad, b = dcog_deg * kDegToRad, c = du * dtR;
-    if (!LIB && fabs(a) <= kSmallAngle && fabs(b) <= kSmallAngle && fabs(c) <= kSmallAngle) {
+    const double ang[3] = {dlat_deg * kDegToRad, dcog_deg * kDegToRad, du * dtR};
+    if (!LIB && fabs(ang[0]) <= kSmallAngle && fabs(ang[1]) <= kSmallAngle && fabs(ang[2]) <= kSmallAngle) {
         AngleTrig t;
-        small_sincos(a, &t.sp, &t.cp);
-        small_sincos(b, &t.sa, &t.ca);
-        small_sincos(c, &t.sd, &t.cd);
+        double sn[3], cs[3];
+        small_sincos_v<3>(ang, sn, cs);
+        t.sp = sn[0]; t.cp = cs[0]; t.sa = sn[1]; t.ca = cs[1]; t.sd = sn[2]; t.cd = cs[2];
         return t;
     }
     return angle_trig<LIB>(dlat_deg, dcog_deg, du, dtR);
@@ -361,31 +376,52 @@ STE_DEV void angle_add_pair(const AngleTrig &b, const AngleTrig &o, AngleTrig &p
     plus.sd = sc_ + cs_; minus.sd = sc_ - cs_; plus.cd = cc_ - ss_; minus.cd = cc_ + ss_;
 }
 
-// x = [lon, lat, u, cog] of the sigma point, t = trig of its (lat, cog, u dt / R)
-#ifdef STE_FINISH_NOINLINE
-#define STE_FINISH_ATTR STE_COLD
-#else
-#define STE_FINISH_ATTR STE_DEV
-#endif
-template <bool LIB>
-STE_FINISH_ATTR void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt, double sog_rate,
-                             double cog_rate, double (&y)[4]) {
-    const double east = t.sd * t.sa;
-    const double sdca = t.sd * t.ca;
-    const double north = fma(t.cp, t.cd, -t.sp * sdca);
-    const double up = fma(t.sp, t.cd, t.cp * sdca);
-    double dlon, lat;
-    if (LIB) {
-        dlon = atan2(east, north);
-        lat = atan2(up, sqrt(fma(east, east, north * north)));
-    } else {
-        dlon = fast_atan2<false>(east, north);
-        lat = fast_atan2<true>(up, fast_sqrt(fma(east, east, north * north)));
+// Propagate NP sigma points at once: x[i] = [lon, lat, u, cog], t[i] = trig of its (lat, cog, u dt/R).
+// All 2*NP angles (longitude increments, latitudes) go through one lock-step atan2.
+template <bool LIB, int NP>
+STE_DEV void geodetic_finish_n(const double (&x)[NP][4], const AngleTrig (&t)[NP], double dt, double sog_rate,
+                               double cog_rate, double (&y)[NP][4]) {
+    double ay[2 * NP], ax[2 * NP], ang[2 * NP], h2[NP], h[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const double east = t[i].sd * t[i].sa;
+        const double sdca = t[i].sd * t[i].ca;
+        const double north = fma(t[i].cp, t[i].cd, -t[i].sp * sdca);
+        ay[i] = east;
+        ax[i] = north;
+        ay[NP + i] = fma(t[i].sp, t[i].cd, t[i].cp * sdca);   // up
+        h2[i] = fma(east, east, north * north);
     }
-    y[0] = fma(x[0], kDegToRad, dlon) * kRadToDeg;
-    y[1] = lat * kRadToDeg;
-    y[2] = fma(sog_rate, dt, x[2]);
-    y[3] = fma(cog_rate, dt, (x[3] * kDegToRad) * kRadToDeg);
+    if (LIB) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) ax[NP + i] = sqrt(h2[i]);
+#pragma unroll
+        for (int i = 0; i < 2 * NP; ++i) ang[i] = atan2(ay[i], ax[i]);
+    } else {
+        fast_sqrt_v<NP>(h2, h);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) ax[NP + i] = h[i];
+        fast_atan2_v<2 * NP>(ay, ax, ang);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        y[i][0] = fma(x[i][0], kDegToRad, ang[i]) * kRadToDeg;
+        y[i][1] = ang[NP + i] * kRadToDeg;
+        y[i][2] = fma(sog_rate, dt, x[i][2]);
+        y[i][3] = fma(cog_rate, dt, (x[i][3] * kDegToRad) * kRadToDeg);
+    }
+}
+
+template <bool LIB>
+STE_DEV void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt, double sog_rate,
+                             double cog_rate, double (&y)[4]) {
+    double xs[1][4], ys[1][4];
+    AngleTrig ts[1] = {t};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xs[0][r] = x[r];
+    geodetic_finish_n<LIB, 1>(xs, ts, dt, sog_rate, cog_rate, ys);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) y[r] = ys[0][r];
 }
 
 // one stand-alone evaluation (geodetic_dynamics called directly, ste_geodetic_f64)
