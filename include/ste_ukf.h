@@ -155,6 +155,16 @@ int ste_sigma_points_f64(int32_t n, int32_t n_tracks, int64_t ld, double scale, 
 int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const double *dt,
                      const double *sog_rate, const double *cog_rate, double *x_out, void *stream);
 
+/* Derived filter inputs from raw fixes for T tracks: ShipTrack.calculate_sog / calculate_cog /
+ * calculate_sog_rate / calculate_cog_rate (ship_track.py:197-304) with the spherical pair
+ * haversine_formula / heading (utils.py:75-147) and, when smooth_width > 1, the CLI's box smoothing
+ * of SOG and COG (utils.py:150-172, main_cli.py:99-104: np.convolve(y, ones(w)/w, "same")).
+ * lon, lat [max_obs][ld] degrees; dts [max_obs-1][ld] hours; n_obs [T] fixes per track or NULL;
+ * outputs sog (km/h), cog (deg), sog_rate, cog_rate [max_obs][ld] (rows >= n_obs[t] are zeroed). */
+int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t smooth_width,
+                          const double *lon, const double *lat, const double *dts, const int32_t *n_obs,
+                          double *sog, double *cog, double *sog_rate, double *cog_rate, void *stream);
+
 /* Test hook: evaluates the library's own fp64 elementary functions (csrc/ste_fastmath.cuh) on n
  * arguments.  kind 0 sincos(a), |a| <= 105615 -> (out0, out1); 1 atan2(a, b); 2 sqrt(a); 3 rsqrt(a); 4 1/a; 5 a/b;
  * 6 atan2(a, b) for b >= 0. */

@@ -204,6 +204,87 @@ __global__ void __launch_bounds__(kThreads) geodetic_kernel(int T, int64_t ld, c
     for (int r = 0; r < 4; ++r) xout[r * ld + t] = y[r];
 }
 
+// ------------------------------------------------------------------------------------------ //
+// Derived filter inputs from raw fixes: what ShipTrack computes per
+// ship on the host (ship_track.py:197-304) with the spherical pair haversine_formula / heading
+// (utils.py:75-147), plus the CLI's optional box smoothing of SOG and COG (utils.py:150-172,
+// main_cli.py:99-104).  One thread per track, sequential over its fixes; not a hot path, so the
+// CUDA math library is used as is.  The rate arrays double as scratch for the unsmoothed values.
+// ------------------------------------------------------------------------------------------ //
+__device__ __forceinline__ void leg_speed_course(double lon1, double lat1, double lon2, double lat2, double dt,
+                                                 double &sog, double &cog) {
+    const double l1 = lon1 * kDegToRad, p1 = lat1 * kDegToRad, l2 = lon2 * kDegToRad, p2 = lat2 * kDegToRad;
+    const double dphi = p2 - p1, dlam = l2 - l1;
+    const double sh = sin(dphi / 2.0), sl = sin(dlam / 2.0);
+    const double cp1 = cos(p1), cp2 = cos(p2);
+    const double a = sh * sh + cp1 * cp2 * (sl * sl);
+    const double dist = (2.0 * atan2(sqrt(a), sqrt(1.0 - a))) * kEarthRadiusKm;   // utils.py:104-111
+    sog = dist / dt;                                                                 // ship_track.py:213-217
+    const double east = sin(dlam) * cp2;
+    const double north = cp1 * sin(p2) - sin(p1) * cp2 * cos(dlam);
+    cog = py_mod360(atan2(east, north) * kRadToDeg + 360.0);                       // utils.py:139-145
+}
+
+__global__ void __launch_bounds__(kThreads) derive_inputs_kernel(int T, int max_obs, int64_t ld, int width,
+                                                                 const double *lon, const double *lat, const double *dts,
+                                                                 const int32_t *n_obs, double *sog, double *cog,
+                                                                 double *sog_rate, double *cog_rate) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int n = n_obs ? min(n_obs[t], max_obs) : max_obs;
+    const bool smoothing = width > 1;
+    double *raw_s = smoothing ? sog_rate : sog, *raw_c = smoothing ? cog_rate : cog;
+    auto at = [&](const double *p, int i) { return p[(int64_t)i * ld + t]; };
+    auto put = [&](double *p, int i, double v) { p[(int64_t)i * ld + t] = v; };
+    // pass 1: one value per leg, the last one repeated ("stationary from the end point onwards")
+    double s = 0.0, c = 0.0;
+    for (int i = 0; i + 1 < n; ++i) {
+        leg_speed_course(at(lon, i), at(lat, i), at(lon, i + 1), at(lat, i + 1), at(dts, i), s, c);
+        put(raw_s, i, s);
+        put(raw_c, i, c);
+    }
+    if (n > 0) {
+        put(raw_s, n - 1, s);
+        put(raw_c, n - 1, c);
+    }
+    // pass 2: np.convolve(y, ones(w) / w, mode="same") with zero padding: out[i] = sum_tap y[i + start - tap] / w
+    if (smoothing) {
+        const int start = (width - 1) / 2;
+        const double inv_w = 1.0 / (double)width;
+        for (int i = 0; i < n; ++i) {
+            double as = 0.0, ac = 0.0;
+            for (int tap = width - 1; tap >= 0; --tap) {
+                const int j = i + start - tap;
+                if (j >= 0 && j < n) {
+                    as = fma(at(raw_s, j), inv_w, as);
+                    ac = fma(at(raw_c, j), inv_w, ac);
+                }
+            }
+            put(sog, i, as);
+            put(cog, i, ac);
+        }
+    }
+    // pass 3: backward differences with a leading zero (ship_track.py:242-248, 296-302)
+    double ps = n > 0 ? at(sog, 0) : 0.0, pc = n > 0 ? at(cog, 0) : 0.0;
+    if (n > 0) {
+        put(sog_rate, 0, 0.0);
+        put(cog_rate, 0, 0.0);
+    }
+    for (int i = 1; i < n; ++i) {
+        const double vs = at(sog, i), vc = at(cog, i), d = at(dts, i - 1);
+        put(sog_rate, i, (vs - ps) / d);
+        put(cog_rate, i, (vc - pc) / d);
+        ps = vs;
+        pc = vc;
+    }
+    for (int i = n; i < max_obs; ++i) {   // padding rows of ragged tiles
+        put(sog, i, 0.0);
+        put(cog, i, 0.0);
+        put(sog_rate, i, 0.0);
+        put(cog_rate, i, 0.0);
+    }
+}
+
 // accuracy probe for ste_fastmath.cuh (tests only): out0/out1 = f(a, b)
 __global__ void fastmath_probe_kernel(int kind, int n, const double *a, const double *b, double *out0, double *out1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -430,6 +511,19 @@ int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const dou
     const dim3 grid((n_tracks + kThreads - 1) / kThreads), block(kThreads);
     geodetic_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_tracks, ld, x_in, dt, sog_rate, cog_rate, x_out);
     return check_launch("geodetic_kernel");
+}
+
+int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t smooth_width, const double *lon,
+                          const double *lat, const double *dts, const int32_t *n_obs, double *sog, double *cog,
+                          double *sog_rate, double *cog_rate, void *stream) {
+    if (n_tracks < 0 || max_obs < 2 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / max_obs / ld");
+    if (smooth_width < 0 || smooth_width > 64) return fail(STE_ERR_INVALID_ARG, "smooth_width outside [0, 64]");
+    if (!lon || !lat || !dts || !sog || !cog || !sog_rate || !cog_rate) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if (n_tracks == 0) return STE_OK;
+    const dim3 grid((n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    derive_inputs_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_tracks, max_obs, ld, smooth_width, lon, lat, dts, n_obs, sog,
+                                                                  cog, sog_rate, cog_rate);
+    return check_launch("derive_inputs_kernel");
 }
 
 int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b, double *out0, double *out1, void *stream) {

@@ -354,3 +354,42 @@ def test_cli_end_to_end_matches_golden(cuda, native_lib, tmp_path, monkeypatch):
     for key, ref in (("variances", tr["covs"]), ("variances_smoothed", tr["covs_s"])):
         d = np.diagonal(ref, axis1=1, axis2=2)
         assert np.max(np.abs(got[key] - d) / np.max(np.abs(d), axis=1, keepdims=True)) <= 1e-9
+
+
+@pytest.mark.parametrize("width", [0, 2, 3, 5])
+def test_derived_inputs_on_device(width, cuda, native_lib):
+    """SOG / COG / rates (+ box smoothing) for a ragged tile on the device against
+    the reference's formulas evaluated per track with numpy (utils.haversine_formula / heading /
+    smooth restate reference utils.py:75-172; ShipTrack restates ship_track.py:197-304)."""
+    import torch
+
+    from ship_track_estimators_b200.derive import batch_from_fixes, derive_inputs
+    from ship_track_estimators_b200.ship_track import ShipTrack
+    from ship_track_estimators_b200.synthetic import make_tracks
+    from ship_track_estimators_b200.utils import haversine_formula, heading, smooth
+
+    T, nobs = 37, 41
+    syn = make_tracks(T, nobs, seed=5, device="cpu", nobs_min=7, dts_choices=(1, 2, 3, 6, 12))
+    got = derive_inputs(syn.lon.to(cuda), syn.lat.to(cuda), syn.dts.to(cuda), syn.nobs.to(cuda), smooth_width=width)
+    for t in range(T):
+        m = int(syn.nobs[t])
+        st = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
+        st.lon, st.lat, st.dts = syn.lon[:m, t].numpy(), syn.lat[:m, t].numpy(), syn.dts[: m - 1, t].numpy()
+        st.calculate_sog(); st.calculate_cog()
+        if width > 1:
+            st.sog, st.cog = smooth(st.sog, width), smooth(st.cog, width)
+        st.calculate_sog_rate(); st.calculate_cog_rate()
+        for name, ref in (("sog", st.sog), ("cog", st.cog), ("sog_rate", st.sog_rate), ("cog_rate", st.cog_rate)):
+            g = getattr(got, name)[:m, t].cpu().numpy()
+            scale = max(1.0, float(np.max(np.abs(ref))))
+            assert np.max(np.abs(g - ref)) <= 1e-11 * scale, (name, t, width)
+            assert float(getattr(got, name)[m:, t].abs().sum()) == 0.0
+    if width == 0:
+        # and straight into the filter: same results as the host-derived inputs
+        from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+
+        ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+        a = ukf.run(batch_from_fixes(syn.lon.to(cuda), syn.lat.to(cuda), syn.dts.to(cuda), syn.nobs.to(cuda), substeps=2))
+        b = ukf.run(TrackBatch.from_synthetic(syn, substeps=2).to(cuda))
+        for t in range(0, T, 6):
+            assert_track_close(a.track(t), b.track(t), tol=1e-9, label=f"derived inputs track {t}", unc=np.zeros(4))
