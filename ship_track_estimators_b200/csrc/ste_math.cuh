@@ -153,16 +153,14 @@ STE_DEV void sym_from_eig(const double (&V)[16], const double (&f)[4], double (&
         }
 }
 
-// Rare continuation of sqrt_psd4 for (near-)singular or indefinite matrices: finish the Jacobi
-// iteration to rounding level and take the root of the clamped spectrum.  Kept out of line so the
-// hot loop stays small in the instruction cache.
-STE_COLD bool sqrt_psd4_finish(double *a_io, double *V_io, double *M_out) {
-    double a[10], V[16], f[4], M[10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) a[i] = a_io[i];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) V[i] = V_io[i];
-    jacobi_eig4<false>(a, V, kJacobiTight);
+// Rare path of sqrt_psd4 for slowly converging, (near-)singular or indefinite matrices: a fresh
+// Jacobi iteration to rounding level and the root of the clamped spectrum.  Out of line, and fed
+// BY VALUE, so that the hot path keeps its matrices in registers (taking the address of the hot
+// arrays made the compiler mirror them on the stack every step).
+STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double a4, double a5, double a6, double a7,
+                             double a8, double a9, double *M_out) {
+    double a[10] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9}, V[16], f[4], M[10];
+    jacobi_eig4<true>(a, V, kJacobiTight);
     const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
     const double wmax = fmax(fmax(fabs(w[0]), fabs(w[1])), fmax(fabs(w[2]), fabs(w[3])));
     bool clamped = false;
@@ -204,7 +202,14 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
     for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int q = p + 1; q < 4; ++q) done &= (a[SYM(p, q)] * a[SYM(p, q)] <= 1e-30 * (w[p] * w[q]));
-    if (!done) return sqrt_psd4_finish(a, V, M);
+    if (!done) {
+        double Mt[10];
+        const bool clamped = sqrt_psd4_cold(A[0] * scale, A[1] * scale, A[2] * scale, A[3] * scale, A[4] * scale, A[5] * scale,
+                                            A[6] * scale, A[7] * scale, A[8] * scale, A[9] * scale, Mt);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) M[i] = Mt[i];
+        return clamped;
+    }
     double f[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) f[k] = fast_sqrt(w[k]);
