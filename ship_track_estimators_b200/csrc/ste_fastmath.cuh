@@ -41,6 +41,9 @@
 #define STE_LOAD_STREAM(p) (*(p))
 #endif
 
+#define STE_PRAGMA_(x) _Pragma(#x)
+#define STE_UNROLL(n) STE_PRAGMA_(unroll n)
+
 namespace ste {
 
 // ---- coefficient tables (constant bank on the device) ---------------------------------------- //

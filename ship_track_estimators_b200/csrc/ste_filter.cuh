@@ -91,7 +91,10 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
     double s2[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) s2[k] = 0.0;
-#pragma unroll 1
+#ifndef STE_PAIR_UNROLL
+#define STE_PAIR_UNROLL 1
+#endif
+    STE_UNROLL(STE_PAIR_UNROLL)
     for (int col = 0; col < 4; ++col) {
 #if defined(STE_STEP_SYNC) && (STE_STEP_SYNC >= 2) && defined(__CUDA_ARCH__)
         __syncthreads();

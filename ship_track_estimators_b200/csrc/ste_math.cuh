@@ -190,7 +190,10 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
     for (int i = 0; i < 10; ++i) a[i] = A[i] * scale;
 #pragma unroll
     for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-#pragma unroll 1
+#ifndef STE_SWEEP_UNROLL
+#define STE_SWEEP_UNROLL 1
+#endif
+    STE_UNROLL(STE_SWEEP_UNROLL)
     for (int sweep = 0; sweep < 2; ++sweep) {
         jacobi_sweep(a, V);
     }
