@@ -133,52 +133,60 @@ def workload_config(args, per_gpu_tracks):
         "tile_tracks_per_gpu": per_gpu_tracks, "job_tracks": 16 * 1024 * 1024,
         "H": MODEL["H"], "R": MODEL["R"], "Q": MODEL["Q"], "P0": MODEL["P"],
         "cache": "inputs+outputs per step are GBs (>> 126 MB L2); two input tiles alternate",
+        "cov_storage": "full16" if getattr(args, "full_cov", False) else "packed10 (symmetric 4x4 stored as its 10 unique entries)",
         "parallelism": f"tracks sharded over {args.gpus} GPU(s), no data-path collective",
     }
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one background
+    `nvidia-smi -lms 50` process, read when the region ends)."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._thr = index, [], threading.Event(), None
-
-    def _loop(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
-        self._thr = threading.Thread(target=self._loop, daemon=True)
-        self._thr.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)  # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        self._thr.join(timeout=10)
+        if self.proc is None:
+            return
+        time.sleep(0.1)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        self.rows = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.strip()]
 
     def summary(self):
         sm, reasons, mx = [], set(), None
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
+                clk, mx_ = float(r[0]), float(r[1])
             except (ValueError, IndexError):
                 continue
+            mx = mx_
+            if clk < 0.5 * mx_:   # idle samples before / after the kernels
+                continue
+            sm.append(clk)
             for name, flag in zip(names, r[3:7]):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples_under_load": len(sm), "samples": len(self.rows)}
 
 
 def measured_traffic():
@@ -224,7 +232,7 @@ def run_gpu_arm(args):
 
     lib = nat.load()  # raises if the CUDA library is missing: no fallback
     H, R, Q, P = (np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
-    ukf = BatchedUKF(H, Q, R, P)
+    ukf = BatchedUKF(H, Q, R, P, packed_cov=not args.full_cov)
     T = args.tracks
 
     # two resident input tiles (different seeds per rank and per tile) and one set of output buffers
@@ -280,20 +288,27 @@ def run_gpu_arm(args):
     value = world * tile_steps * args.steps / (total_ms * 1e-3)
     summary = reduce_summary(local_summary(res, tile_steps * args.steps), device=dev)  # outside the timed region
 
-    # ---- end-to-end through the public API with host buffers (rank-local tile) ---- #
+    # ---- end-to-end through the public API with HOST buffers ---- #
+    # BatchedUKF.run_host_pipelined: pinned host inputs -> device, forward + backward, all four result
+    # arrays -> pinned host, tile after tile with the copy engines overlapped with the kernels.
     Te = args.e2e_tracks
-    syn = make_tracks(Te, N_STEPS + 1, seed=5000 + rank, device=str(dev))
-    host_batch = TrackBatch.from_synthetic(syn, substeps=1).pin_memory()
-    del syn
-    dev_res = ukf.allocate(host_batch.to(dev), smoother=True)
-    host_out = dev_res.host_like(pinned=True)
-    e2e_steps = max(2, min(args.steps, 3))
-    moved = ukf.run_host(host_batch, host_out, dev_res, device=dev)  # warm-up
+    host_tiles = []
+    for j in range(2):
+        syn = make_tracks(Te, N_STEPS + 1, seed=5000 + 31 * rank + j, device=str(dev))
+        host_tiles.append(TrackBatch.from_synthetic(syn, substeps=1).pin_memory())
+        del syn
+    proto = ukf.allocate(host_tiles[0].to(dev), smoother=True)
+    host_outs = [proto.host_like(pinned=True) for _ in range(2)]
+    del proto
+    torch.cuda.empty_cache()
+    e2e_steps = max(4, min(args.steps, 6))
+    seq_in = [host_tiles[i % 2] for i in range(e2e_steps)]
+    seq_out = [host_outs[i % 2] for i in range(e2e_steps)]
+    moved = ukf.run_host_pipelined(seq_in[:2], seq_out[:2], device=dev)  # warm-up
     barrier()
     t0, t1 = ev(), ev()
     t0.record()
-    for _ in range(e2e_steps):
-        moved = ukf.run_host(host_batch, host_out, dev_res, device=dev)
+    moved = ukf.run_host_pipelined(seq_in, seq_out, device=dev)
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
@@ -302,7 +317,7 @@ def run_gpu_arm(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = float(tmax.item())
     e2e_value = world * Te * N_STEPS * e2e_steps / (e2e_ms * 1e-3)
-    assert float(host_out.mean_s[0, 0, 0]) == float(dev_res.mean_s[0, 0, 0].item())
+    assert bool(torch.isfinite(host_outs[0].mean_s).all()) and float(host_outs[0].mean_s.abs().sum()) > 0.0
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -345,7 +360,10 @@ def run_gpu_arm(args):
                 },
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"], "d2h_bytes_per_step": moved["d2h_bytes"],
-                    "tile_tracks": Te, "steps": e2e_steps, "outputs": "filtered+smoothed means and full 4x4 covariances to pinned host"},
+                    "tile_tracks": Te, "steps": e2e_steps,
+                    "outputs": ("filtered + smoothed means and covariances ("
+                                + ("full 4x4" if args.full_cov else "10 unique entries each, TrackResults.track() expands to 4x4")
+                                + ") to pinned host; H2D, kernels and D2H of successive tiles overlap (run_host_pipelined)")},
             "gpu_launches": 2 * args.steps,
             "clocks": clocks.summary(),
             "summary": summary,
@@ -374,6 +392,7 @@ def main():
     ap.add_argument("--tracks", type=int, default=148 * 128 * 8, help="tracks per resident tile per GPU")
     ap.add_argument("--e2e-tracks", type=int, default=148 * 128, help="tracks of the host-buffer end-to-end tile")
     ap.add_argument("--in-place", action="store_true", help="smooth in place (halves the state memory)")
+    ap.add_argument("--full-cov", action="store_true", help="store full 4x4 covariances (default: the 10 unique entries)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tracks-per-core", type=int, default=16)
     args = ap.parse_args()

@@ -45,6 +45,8 @@ extern "C" {
 /* SteProblem.flags */
 #define STE_FLAG_GATING 0x1u      /* Mahalanobis robustification before every update            */
 #define STE_FLAG_FORCE_GENERIC 0x2u /* never take the position-only (H = diag(1,1,0,0)) fast path */
+#define STE_FLAG_PACKED_COV 0x4u  /* cov_f / cov_s hold the 10 unique entries per state, planes in  */
+                                  /* the order 00 01 02 03 11 12 13 22 23 33, instead of 16         */
 
 /* per-track status bits (SteOutputs.status) */
 #define STE_STATUS_NONFINITE 0x1     /* a state or covariance entry became NaN/Inf                  */
@@ -104,7 +106,7 @@ typedef struct SteInputs {
 
 typedef struct SteOutputs {
     double *mean_f;      /* [max_steps+1][4][ld]  filtered means; row 0 = prior (kalman_filter.py:76) */
-    double *cov_f;       /* [max_steps+1][16][ld] filtered covariances                                */
+    double *cov_f;       /* [max_steps+1][16][ld] filtered covariances ([..][10][ld] if PACKED_COV)   */
     double *mean_s;      /* smoothed, same shapes (may alias mean_f / cov_f for in-place smoothing)  */
     double *cov_s;
     int32_t *status;     /* [T] OR-ed STE_STATUS_* (the forward pass overwrites, the backward ORs)    */

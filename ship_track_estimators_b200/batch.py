@@ -282,6 +282,18 @@ class TrackResults:
     smooth_stats: Optional[torch.Tensor] = None  # [N][30][T] device-side tape between the two passes (not a result)
     n_steps_host: Optional[np.ndarray] = None
 
+    @property
+    def packed_cov(self) -> bool:
+        """True when the covariance tensors hold the 10 unique entries per state (``[N+1][10][T]``,
+        order 00 01 02 03 11 12 13 22 23 33) instead of the full row-major 4x4."""
+        return self.cov_f.shape[1] == 10
+
+    @staticmethod
+    def expand_cov(c: np.ndarray) -> np.ndarray:
+        """``(..., 10)`` packed symmetric entries -> ``(..., 4, 4)``."""
+        idx = np.array([[0, 1, 2, 3], [1, 4, 5, 6], [2, 5, 7, 8], [3, 6, 8, 9]])
+        return c[..., idx]
+
     _TENSORS = ("mean_f", "cov_f", "mean_s", "cov_s", "status", "n_updates", "gate_iters", "gate_lambda", "gate_scale")
 
     def host_like(self, pinned: bool = True) -> "TrackResults":
@@ -308,18 +320,22 @@ class TrackResults:
             moved += src.numel() * src.element_size()
         return moved
 
+    def _cov_np(self, cov: torch.Tensor, n: int, i: int) -> np.ndarray:
+        c = cov[: n + 1, :, i].cpu().numpy()
+        return self.expand_cov(c) if cov.shape[1] == 10 else c.reshape(n + 1, 4, 4)
+
     def track(self, i: int) -> Dict[str, np.ndarray]:
         """Host copies for one track in the reference's shapes: means (N+1, 4), covs (N+1, 4, 4)."""
         n = int(self.n_steps_host[i]) if self.n_steps_host is not None else self.mean_f.shape[0] - 1
         out = {
             "means": self.mean_f[: n + 1, :, i].cpu().numpy(),
-            "covs": self.cov_f[: n + 1, :, i].cpu().numpy().reshape(n + 1, 4, 4),
+            "covs": self._cov_np(self.cov_f, n, i),
             "status": int(self.status[i].item()),
             "n_updates": int(self.n_updates[i].item()),
         }
         if self.mean_s is not None:
             out["means_s"] = self.mean_s[: n + 1, :, i].cpu().numpy()
-            out["covs_s"] = self.cov_s[: n + 1, :, i].cpu().numpy().reshape(n + 1, 4, 4)
+            out["covs_s"] = self._cov_np(self.cov_s, n, i)
         if self.gate_iters is not None:
             m = out["n_updates"]
             out["gate_iters"] = self.gate_iters[:m, i].cpu().numpy().astype(np.int32)
@@ -336,7 +352,8 @@ class BatchedUKF:
     zero or replayed from the batch's noise tapes.
     """
 
-    def __init__(self, H, Q=None, R=None, P=None, *, gating=False, gate_chi=50.0, gate_max_iter=100, force_generic=False):
+    def __init__(self, H, Q=None, R=None, P=None, *, gating=False, gate_chi=50.0, gate_max_iter=100, force_generic=False,
+                 packed_cov=False):
         if H is None:
             raise ValueError("Set proper system dynamics.")  # reference unscented.py:52-53
         eye = np.eye(4)
@@ -345,6 +362,9 @@ class BatchedUKF:
             gating=gating, gate_chi=gate_chi, gate_max_iter=gate_max_iter, force_generic=force_generic,
         )
         self._lib = nat.load()
+        # store the 10 unique covariance entries per state instead of the full 4x4 (30 % less state
+        # traffic, memory and PCIe volume; TrackResults.track() expands them back)
+        self.packed_cov = bool(packed_cov)
 
     # ------------------------------------------------------------------ #
     def _problem(self, b: TrackBatch) -> nat.SteProblem:
@@ -352,7 +372,8 @@ class BatchedUKF:
         p = nat.SteProblem()
         p.n_tracks, p.max_steps, p.max_obs = b.n_tracks, b.max_steps, b.max_obs
         p.substeps, p.rate_repeat = int(b.substeps), int(b.rate_repeat_all)
-        p.flags = (nat.STE_FLAG_GATING if m.gating else 0) | (nat.STE_FLAG_FORCE_GENERIC if m.force_generic else 0)
+        p.flags = ((nat.STE_FLAG_GATING if m.gating else 0) | (nat.STE_FLAG_FORCE_GENERIC if m.force_generic else 0)
+                   | (nat.STE_FLAG_PACKED_COV if self.packed_cov else 0))
         p.gate_max_iter, p.gate_chi = int(m.gate_max_iter), float(m.gate_chi)
         p.ld = b.n_tracks
         for name, M in (("H", m.H), ("Q", m.Q), ("R", m.R), ("P0", m.P0)):
@@ -378,11 +399,12 @@ class BatchedUKF:
         reference does).  ``False`` trades that memory for ~2x the smoother's arithmetic."""
         dev, T, S = b.device, b.n_tracks, b.max_steps + 1
         f64 = dict(dtype=torch.float64, device=dev)
+        C = 10 if self.packed_cov else 16
         mean_f = torch.empty(S, 4, T, **f64)
-        cov_f = torch.empty(S, 16, T, **f64)
+        cov_f = torch.empty(S, C, T, **f64)
         mean_s = cov_s = None
         if smoother:
-            mean_s, cov_s = (mean_f, cov_f) if in_place else (torch.empty(S, 4, T, **f64), torch.empty(S, 16, T, **f64))
+            mean_s, cov_s = (mean_f, cov_f) if in_place else (torch.empty(S, 4, T, **f64), torch.empty(S, C, T, **f64))
         res = TrackResults(
             mean_f=mean_f, cov_f=cov_f, mean_s=mean_s, cov_s=cov_s,
             status=torch.zeros(T, dtype=torch.int32, device=dev), n_updates=torch.zeros(T, dtype=torch.int32, device=dev),
@@ -411,9 +433,14 @@ class BatchedUKF:
             if need and b.z[r] is None:
                 raise ValueError(f"observation row {r} is referenced by H/R but absent from the batch")
 
+    def _check_layout(self, res: TrackResults):
+        if res.packed_cov != self.packed_cov:
+            raise ValueError("result buffers were allocated with a different covariance layout (packed_cov)")
+
     def forward(self, b: TrackBatch, res: TrackResults) -> None:
         """Launch the forward filter (asynchronous on the current stream)."""
         self._check_rows(b)
+        self._check_layout(res)
         if self.model.gating and b.noise_upd is not None:
             raise NotImplementedError("gating with measurement noise tapes (data-dependent draw count)")
         p, i, o = self._problem(b), self._inputs(b), self._outputs(res)
@@ -424,6 +451,7 @@ class BatchedUKF:
         """Launch the URTSS backward pass over the filtered states in ``res``."""
         if res.mean_s is None:
             raise ValueError("results were allocated without smoother buffers")
+        self._check_layout(res)
         p, i, o = self._problem(b), self._inputs(b), self._outputs(res)
         with torch.cuda.device(b.device):
             nat.check(self._lib.ste_urtss_backward_f64(C.byref(p), C.byref(i), C.byref(o), nat.current_stream()))
@@ -437,6 +465,50 @@ class BatchedUKF:
         self.run(dev_batch, smoother=smoother, res=dev_res)
         d2h = dev_res.copy_to(host_out, non_blocking=True)
         return {"h2d_bytes": host_batch.input_bytes(), "d2h_bytes": d2h}
+
+    def run_host_pipelined(self, host_batches: Sequence[TrackBatch], host_outs: Sequence[TrackResults], smoother: bool = True,
+                           device="cuda") -> Dict[str, int]:
+        """End-to-end over a sequence of HOST tiles with the three engines overlapped: while tile i
+        is filtered and smoothed, tile i+1's inputs travel host->device and tile i-1's results
+        device->host (PCIe is full duplex and the copy engines run beside the SMs).  Two device
+        buffer sets alternate.  ``host_batches`` / ``host_outs`` live in pinned memory; all tiles
+        share one shape.  Returns the bytes copied per tile in each direction; synchronise (or call
+        ``torch.cuda.synchronize``) before reading ``host_outs``."""
+        dev = torch.device(device)
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        for s_ in (s_in, s_run, s_out):
+            s_.wait_stream(cur)
+        n = len(host_batches)
+        dev_in: List[Optional[TrackBatch]] = [None, None]
+        dev_res = [None, None]
+        in_done = [torch.cuda.Event() for _ in range(n)]
+        run_done = [torch.cuda.Event() for _ in range(n)]
+        out_done = [torch.cuda.Event() for _ in range(n)]
+        moved = {"h2d_bytes": 0, "d2h_bytes": 0}
+        for i in range(n):
+            k = i % 2
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(run_done[i - 2])        # the kernels that read this input slot are done
+                dev_in[k] = host_batches[i].to(dev, non_blocking=True)
+                in_done[i].record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(in_done[i])
+                if i >= 2:
+                    s_run.wait_event(out_done[i - 2])       # this result slot has been copied out
+                if dev_res[k] is None:
+                    dev_res[k] = self.allocate(dev_in[k], smoother=smoother)
+                self.run(dev_in[k], smoother=smoother, res=dev_res[k])
+                run_done[i].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(run_done[i])
+                moved["d2h_bytes"] = dev_res[k].copy_to(host_outs[i], non_blocking=True)
+                out_done[i].record(s_out)
+            moved["h2d_bytes"] = host_batches[i].input_bytes()
+        for s_ in (s_in, s_run, s_out):
+            cur.wait_stream(s_)
+        return moved
 
     def run(self, b: TrackBatch, smoother: bool = True, res: Optional[TrackResults] = None, in_place: bool = False) -> TrackResults:
         res = res if res is not None else self.allocate(b, smoother=smoother, in_place=in_place)

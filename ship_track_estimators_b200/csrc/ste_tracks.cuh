@@ -33,28 +33,38 @@ struct KernelArgs {
     SteOutputs out;
 };
 
-STE_DEV void store_state(double *mean, double *cov, int64_t ld, int64_t s, int t,
-                                            const double (&x)[4], const double (&P)[10]) {
+// Covariance storage: 16 planes per state (the full row-major 4x4 the reference returns) or, with
+// STE_FLAG_PACKED_COV, only the 10 unique entries in SYM() order.  Both passes keep covariances
+// exactly symmetric, so the packed form loses nothing; it cuts the state traffic by 30 %.
+STE_DEV int cov_planes(bool packed) { return packed ? 10 : 16; }
+STE_DEV int cov_plane(bool packed, int i, int j) { return packed ? SYM(i, j) : i * 4 + j; }
+
+STE_DEV void store_state(double *mean, double *cov, int64_t ld, int64_t s, int t, bool packed,
+                         const double (&x)[4], const double (&P)[10]) {
     double *m = mean + (s * 4) * ld + t;
-    double *c = cov + (s * 16) * ld + t;
+    double *c = cov + (s * cov_planes(packed)) * ld + t;
 #pragma unroll
     for (int r = 0; r < 4; ++r) STE_STORE_STREAM(m + r * ld, x[r]);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) STE_STORE_STREAM(c + (i * 4 + j) * ld, P[SYM(i, j)]);
+        for (int j = 0; j < 4; ++j)
+            if (i <= j || !packed) STE_STORE_STREAM(c + cov_plane(packed, i, j) * ld, P[SYM(i, j)]);
 }
 
-STE_DEV void load_state(const double *mean, const double *cov, int64_t ld, int64_t s, int t,
-                                           double (&x)[4], double (&P)[10]) {
-    const double *m = mean + (s * 4) * ld + t;
-    const double *c = cov + (s * 16) * ld + t;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) x[r] = STE_LOAD_STREAM(m + r * ld);
+STE_DEV void load_cov(const double *cov_state, int64_t ld, bool packed, double (&P)[10]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = i; j < 4; ++j) P[SYM(i, j)] = STE_LOAD_STREAM(c + (i * 4 + j) * ld);
+        for (int j = i; j < 4; ++j) P[SYM(i, j)] = cov_state[cov_plane(packed, i, j) * ld];
+}
+
+STE_DEV void load_state(const double *mean, const double *cov, int64_t ld, int64_t s, int t, bool packed,
+                        double (&x)[4], double (&P)[10]) {
+    const double *m = mean + (s * 4) * ld + t;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = STE_LOAD_STREAM(m + r * ld);
+    load_cov(cov + (s * cov_planes(packed)) * ld + t, ld, packed, P);
 }
 
 STE_DEV bool any_nonfinite(const double (&x)[4], const double (&P)[10]) {
@@ -85,7 +95,8 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
         for (int j = i; j < 4; ++j)
             P[SYM(i, j)] = a.in.P0 ? a.in.P0[(i * 4 + j) * ld + t] : a.prob.P0[i * 4 + j];
     int status = 0;
-    store_state(a.out.mean_f, a.out.cov_f, ld, 0, t, x, P);  // the prior (kalman_filter.py:76-77)
+    const bool packed = (a.prob.flags & STE_FLAG_PACKED_COV) != 0;
+    store_state(a.out.mean_f, a.out.cov_f, ld, 0, t, packed, x, P);  // the prior (kalman_filter.py:76-77)
 
     // observation rows are staged into scratch by stage_obs() a whole predict ahead of their use
     auto stage_obs = [&](int ui) {
@@ -181,7 +192,7 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
         if (advance) ++ui;
         if (upd) assimilate(ui);
         else stage_wait();   // the next step's inputs must have landed before they are read
-        store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, x, P);
+        store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, packed, x, P);
     }
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
     if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;
@@ -206,12 +217,13 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
     int rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
     rep = rep > 0 ? rep : 1;
     int status = 0;
+    const bool packed = (a.prob.flags & STE_FLAG_PACKED_COV) != 0;
 
     {   // the last state is untouched by the smoother (:297); it seeds the carried (xs, Ps)
         double xs[4], Ps[10];
-        load_state(a.out.mean_f, a.out.cov_f, ld, nt, t, xs, Ps);
+        load_state(a.out.mean_f, a.out.cov_f, ld, nt, t, packed, xs, Ps);
         if (a.out.mean_s != a.out.mean_f || a.out.cov_s != a.out.cov_f)
-            store_state(a.out.mean_s, a.out.cov_s, ld, nt, t, xs, Ps);
+            store_state(a.out.mean_s, a.out.cov_s, ld, nt, t, packed, xs, Ps);
 #pragma unroll
         for (int r = 0; r < 4; ++r) sc.at(kScratchXs + r) = xs[r];
 #pragma unroll
@@ -225,7 +237,7 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
 #pragma unroll 1
     for (int step = nt - 1; step >= 0; --step) {
         const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
-        const double *cf = a.out.cov_f + ((int64_t)step * 16) * ld + t;
+        const double *cf = a.out.cov_f + ((int64_t)step * cov_planes(packed)) * ld + t;
         double xf[4], xs[4], Ps[10];
 #pragma unroll
         for (int r = 0; r < 4; ++r) xf[r] = mf[r * ld];
@@ -237,10 +249,7 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
         }
         if (use_stats && step > 0) {
             double Pf[10];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+            load_cov(cf, ld, packed, Pf);
             urtss_step_from_stats(xf, Pf, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, e, xs, Ps,
                                   status, sc);
         } else {
@@ -251,29 +260,23 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
             const double cr = a.in.cog_rate[(int64_t)ri * ld + t];
             {
                 double Pf[10];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+                load_cov(cf, ld, packed, Pf);
                 if (step > 0) {   // pull the next (earlier) state towards L2 while this step computes
 #pragma unroll
                     for (int r = 0; r < 4; ++r) prefetch_l2(mf + (r - 4) * ld);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = i; j < 4; ++j) prefetch_l2(cf + (i * 4 + j - 16) * ld);
+                        for (int j = i; j < 4; ++j) prefetch_l2(cf + (cov_plane(packed, i, j) - cov_planes(packed)) * ld);
                     prefetch_l2(a.in.dt + (int64_t)(step - 1) * ld + t);
                 }
                 urtss_moments(xf, Pf, a.prob.Q, dt, sr, cr, s1, Pb, status, sc);
             }
             double Pf[10];   // again (L2-resident) rather than held across the sigma-point loop
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = cf[(i * 4 + j) * ld];
+            load_cov(cf, ld, packed, Pf);
             urtss_gain(xf, Pf, s1, Pb, e, xs, Ps, status, sc);
         }
-        store_state(a.out.mean_s, a.out.cov_s, ld, step, t, xs, Ps);
+        store_state(a.out.mean_s, a.out.cov_s, ld, step, t, packed, xs, Ps);
         bad |= any_nonfinite(xs, Ps);
     }
     if (bad) status |= STE_STATUS_NONFINITE;

@@ -203,6 +203,14 @@ def test_full_size_properties(cuda, native_lib):
     assert float((dm.abs() / a.mean_s.abs().clamp(min=1.0)).max()) <= 1e-10
     assert float(((nr.cov_s - a.cov_s).abs() / a.cov_s.abs().amax(dim=1, keepdim=True)).max()) <= 1e-10
     assert torch.equal(nr.mean_f, a.mean_f) and torch.equal(nr.cov_f, a.cov_f)
+    # packed covariance storage (10 unique entries): bit-identical numbers, 30 % less state traffic
+    pk = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF, packed_cov=True).run(batch)
+    assert pk.cov_s.shape[1] == 10 and pk.packed_cov
+    sym = torch.tensor([0, 1, 2, 3, 5, 6, 7, 10, 11, 15], device=cuda)
+    assert torch.equal(pk.mean_s, a.mean_s) and torch.equal(pk.cov_s, a.cov_s.index_select(1, sym))
+    assert torch.equal(pk.cov_f, a.cov_f.index_select(1, sym))
+    one_p, one_f = pk.track(17), a.track(17)
+    assert np.array_equal(one_p["covs_s"], one_f["covs_s"]) and np.array_equal(one_p["covs"], one_f["covs"])
     # in place
     c = ukf.run(batch, in_place=True)
     assert c.mean_s is c.mean_f
@@ -393,3 +401,23 @@ def test_derived_inputs_on_device(width, cuda, native_lib):
         b = ukf.run(TrackBatch.from_synthetic(syn, substeps=2).to(cuda))
         for t in range(0, T, 6):
             assert_track_close(a.track(t), b.track(t), tol=1e-9, label=f"derived inputs track {t}", unc=np.zeros(4))
+
+
+def test_pipelined_host_api(cuda, native_lib):
+    """run_host_pipelined: three tiles through H2D / kernels / D2H on separate streams give the
+    same bytes as the one-tile-at-a-time calls."""
+    import torch
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF, packed_cov=True)
+    tiles = [TrackBatch.from_synthetic(make_tracks(512, 65, seed=40 + i, device="cpu"), substeps=1).pin_memory() for i in range(3)]
+    ref = [ukf.run(t.to(cuda)) for t in tiles]
+    outs = [ref[0].host_like(pinned=True) for _ in tiles]
+    moved = ukf.run_host_pipelined(tiles, outs, device=cuda)
+    torch.cuda.synchronize()
+    assert moved["h2d_bytes"] == tiles[0].input_bytes() and moved["d2h_bytes"] > 0
+    for r, o in zip(ref, outs):
+        assert torch.equal(r.mean_s.cpu(), o.mean_s) and torch.equal(r.cov_s.cpu(), o.cov_s)
+        assert torch.equal(r.mean_f.cpu(), o.mean_f) and torch.equal(r.status.cpu(), o.status)
