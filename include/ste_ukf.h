@@ -173,9 +173,11 @@ int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t
 int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b, double *out0,
                        double *out1, void *stream);
 
-/* Measurement helper: one block of `warps` warps runs `iters` rounds of `chains` (1..8) independent
- * dependent-DFMA chains per thread; cycles[0] (device int64) receives the clock64 span.  Gives the
- * DFMA latency (warps = chains = 1) and the issue interval of the FP64 pipe. */
+/* Measurement helper: one block of `warps` warps runs `iters` rounds of n independent dependent
+ * chains per thread, chains = 100 * mode + n with n in {1, 2, 4, 8}: mode 0 DFMA on registers,
+ * 1 DFMA with constant-bank operands, 2 DMUL/DADD alternating, 3 DFMA followed by a compare +
+ * select.  cycles[0] (device int64) receives the clock64 span.  Gives the latency (warps = n = 1)
+ * and the issue interval of the FP64 pipe for the instruction mixes the filter kernels issue. */
 int ste_probe_fp64_latency(int32_t warps, int32_t iters, int32_t chains, double *sink,
                            long long *cycles, void *stream);
 

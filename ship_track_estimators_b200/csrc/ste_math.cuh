@@ -301,7 +301,7 @@ STE_DEV int pinv_spd4(const double (&A)[10], double (&Ainv)[10]) {
 // Pseudo-inverse of a symmetric 2x2 [a b; b c] with the same cutoff rule (one Jacobi rotation
 // diagonalises a 2x2 exactly).  `floor_sv` is an extra singular value taking part in the
 // max (0 when the 2x2 is the only non-zero block of the full matrix).
-STE_DEV int pinv_sym2(double a, double b, double c, double (&inv)[3]) {
+STE_COLD int pinv_sym2_eig(double a, double b, double c, double *inv) {
     const double d = c - a;
     const double bb = b + b;
     const double h = fast_sqrt(fma(d, d, bb * bb));
@@ -318,6 +318,30 @@ STE_DEV int pinv_sym2(double a, double b, double c, double (&inv)[3]) {
     inv[1] = fma(-cs * f0, sn, sn * f1 * cs);
     inv[2] = fma(sn * f0, sn, cs * f1 * cs);
     return (k0 ? 0 : 1) + (k1 ? 0 : 1);
+}
+
+// Hot path: S22 = P22 + R22 of a running filter is positive definite and well conditioned (R adds
+// to its diagonal), so the pseudo-inverse is the inverse, adj(S) / det(S): one reciprocal on the
+// critical path instead of two dependent square roots.  det = a c - b^2 is formed with an exact
+// product error term; anything that is not clearly positive definite (det <= 1e-8 a c, i.e. the
+// two rows closer than ~1e-4 rad to parallel, or a non-positive diagonal) takes the
+// eigen-decomposition with numpy's cutoff semantics.
+STE_DEV int pinv_sym2(double a, double b, double c, double (&inv)[3]) {
+    const double ac = a * c;
+    const double det = fma(-b, b, ac) + fma(a, c, -ac);
+    if (!(a > 0.0 && c > 0.0 && det > 1e-8 * ac)) {
+        double t[3];
+        const int dropped = pinv_sym2_eig(a, b, c, t);
+        inv[0] = t[0];
+        inv[1] = t[1];
+        inv[2] = t[2];
+        return dropped;
+    }
+    const double r = fast_rcp(det);
+    inv[0] = c * r;
+    inv[1] = -b * r;
+    inv[2] = a * r;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------ //

@@ -304,8 +304,11 @@ __global__ void fastmath_probe_kernel(int kind, int n, const double *a, const do
     out1[i] = r1;
 }
 
-// dependent-chain DFMA latency: `CHAINS` independent chains per thread, clock64 timed
-template <int CHAINS>
+// FP64 pipe microbenchmark: CHAINS independent dependent chains per thread, clock64 timed.
+// MODE 0: DFMA, register operands.  1: DFMA with a __constant__ (uniform-register) multiplicand.
+// 2: DMUL + DADD alternating.  3: DFMA followed by a select on its result (DSETP + FSEL pair).
+__constant__ double kProbeC[2] = {1.0000000001, 1e-12};
+template <int CHAINS, int MODE>
 __global__ void fp64_latency_probe_kernel(int iters, double *sink, long long *cycles) {
     double acc[CHAINS];
     const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-12;
@@ -315,7 +318,15 @@ __global__ void fp64_latency_probe_kernel(int iters, double *sink, long long *cy
 #pragma unroll 4
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int k = 0; k < CHAINS; ++k) acc[k] = fma(acc[k], a, b);
+        for (int k = 0; k < CHAINS; ++k) {
+            if (MODE == 0) acc[k] = fma(acc[k], a, b);
+            if (MODE == 1) acc[k] = fma(acc[k], kProbeC[0], kProbeC[1]);
+            if (MODE == 2) acc[k] = (i & 1) ? acc[k] * a : acc[k] + b;
+            if (MODE == 3) {
+                const double v = fma(acc[k], a, b);
+                acc[k] = (v > 1e300) ? b : v;
+            }
+        }
     }
     const long long t1 = clock64();
     double s = 0.0;
@@ -534,16 +545,18 @@ int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b
 }
 
 int ste_probe_fp64_latency(int32_t warps, int32_t iters, int32_t chains, double *sink, long long *cycles, void *stream) {
-    if (warps < 1 || warps > 32 || iters < 1 || chains < 1 || chains > 8 || !sink || !cycles)
+    if (warps < 1 || warps > 32 || iters < 1 || chains < 1 || !sink || !cycles)
         return fail(STE_ERR_INVALID_ARG, "bad latency probe arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    switch (chains) {
-        case 1: fp64_latency_probe_kernel<1><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
-        case 2: fp64_latency_probe_kernel<2><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
-        case 4: fp64_latency_probe_kernel<4><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
-        case 8: fp64_latency_probe_kernel<8><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); break;
-        default: return fail(STE_ERR_INVALID_ARG, "chains must be 1, 2, 4 or 8");
-    }
+    const int mode = chains / 100;   // chains = 100 * mode + {1, 2, 4, 8}
+    const int ch = chains % 100;
+#define STE_PROBE_CASE(C_, M_) if (ch == C_ && mode == M_) { fp64_latency_probe_kernel<C_, M_><<<1, 32 * warps, 0, s>>>(iters, sink, cycles); return check_launch("fp64_latency_probe_kernel"); }
+    STE_PROBE_CASE(1, 0) STE_PROBE_CASE(2, 0) STE_PROBE_CASE(4, 0) STE_PROBE_CASE(8, 0)
+    STE_PROBE_CASE(1, 1) STE_PROBE_CASE(4, 1) STE_PROBE_CASE(8, 1)
+    STE_PROBE_CASE(1, 2) STE_PROBE_CASE(4, 2) STE_PROBE_CASE(8, 2)
+    STE_PROBE_CASE(1, 3) STE_PROBE_CASE(4, 3) STE_PROBE_CASE(8, 3)
+#undef STE_PROBE_CASE
+    return fail(STE_ERR_INVALID_ARG, "chains must be 100 * mode + {1, 2, 4, 8}");
     return check_launch("fp64_latency_probe_kernel");
 }
 

@@ -1,4 +1,5 @@
-"""DFMA latency / issue-interval microbenchmark on the FP64 pipe (dev tool)."""
+"""FP64-pipe microbenchmark: latency / issue interval for DFMA and for the instruction mixes the
+filter kernels actually issue (dev tool; numbers quoted in DESIGN.md)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,10 +7,13 @@ from ship_track_estimators_b200 import _native as nat
 lib = nat.load(); dev = torch.device("cuda:0")
 sink = torch.zeros(1024, dtype=torch.float64, device=dev); cyc = torch.zeros(1, dtype=torch.int64, device=dev)
 iters = 20000
-for warps in (1, 4, 8, 12, 16, 24, 32):
-    row = []
-    for chains in (1, 2, 4, 8):
-        nat.check(lib.ste_probe_fp64_latency(warps, iters, chains, nat.ptr(sink), nat.ptr(cyc), nat.current_stream()))
-        torch.cuda.synchronize()
-        row.append(cyc.item() / iters)
-    print(f"warps/block {warps:2d} (per SMSP {warps/4:4.2f}): cycles/iter for 1/2/4/8 chains:", [round(r, 2) for r in row], " -> SMSP cycles per warp-DFMA:", [round(r / (ch * max(warps / 4, 1)), 2) for r, ch in zip(row, (1, 2, 4, 8))])
+names = {0: "DFMA reg operands", 1: "DFMA constant-bank operands", 2: "DMUL/DADD alternating", 3: "DFMA + compare/select"}
+for mode in (0, 1, 2, 3):
+    print(names[mode])
+    for warps in (1, 4, 12, 16, 32):
+        row = []
+        for chains in ((1, 2, 4, 8) if mode == 0 else (1, 4, 8)):
+            nat.check(lib.ste_probe_fp64_latency(warps, iters, 100 * mode + chains, nat.ptr(sink), nat.ptr(cyc), nat.current_stream()))
+            torch.cuda.synchronize()
+            row.append((chains, cyc.item() / iters))
+        print(f"  warps/block {warps:2d} (per SMSP {warps/4:4.2f}): SMSP cycles per FP64 op:", [(c, round(r / (c * max(warps / 4, 1)), 2)) for c, r in row])
