@@ -63,7 +63,7 @@ STE_DEV void jacobi_params(const double (&app)[N], const double (&aqq)[N], const
     STE_LANES cc[l] = fma(0.5, fabs(d[l]) * rh[l], 0.5);
     fast_rsqrt_v<N>(cc, rc);
     STE_LANES {
-        const bool skip = (apq[l] == 0.0);                 // also covers d == b == 0 (NaN from 0 * inf)
+        const bool skip = (apq[l] == 0.0) || !(v[l] > 1e-290);   // zero or underflowed pivot: identity (also d == b == 0)
         const double s2t = (d[l] >= 0.0 ? b[l] : -b[l]) * rh[l];
         c[l] = skip ? 1.0 : cc[l] * rc[l];
         s[l] = skip ? 0.0 : (0.5 * s2t) * rc[l];

@@ -421,3 +421,23 @@ def test_pipelined_host_api(cuda, native_lib):
     for r, o in zip(ref, outs):
         assert torch.equal(r.mean_s.cpu(), o.mean_s) and torch.equal(r.cov_s.cpu(), o.cov_s)
         assert torch.equal(r.mean_f.cpu(), o.mean_f) and torch.equal(r.status.cpu(), o.status)
+
+
+def test_long_tracks_against_oracle(cuda, native_lib):
+    """Track lengths of the modern-ship data (thousands of fixes, BASELINE config 2): a 3000-step
+    track against the oracle, and 64 tracks of 10 000 steps for finiteness / determinism."""
+    import torch
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    syn = make_tracks(4, 1501, seed=8, device="cpu", dts_choices=(1.0,))
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+    res = ukf.run(TrackBatch.from_synthetic(syn, substeps=2).to(cuda))
+    ref = _oracle_track(syn, 1, 2, H_POS, Q_DEF, R_POS, P_DEF)
+    assert_track_close(res.track(1), ref, tol=TOL, label="3000-step track", unc=np.zeros(4))
+    big = make_tracks(64, 10001, seed=9, device=str(cuda))
+    b = TrackBatch.from_synthetic(big, substeps=1)
+    r1, r2 = ukf.run(b), ukf.run(b)
+    assert torch.isfinite(r1.mean_s).all() and torch.isfinite(r1.cov_s).all() and int(r1.status.sum()) == 0
+    assert torch.equal(r1.mean_s, r2.mean_s) and torch.equal(r1.cov_s[10000], r1.cov_f[10000])
