@@ -67,6 +67,23 @@ def _cpu_worker(job):
     return done, time.perf_counter() - t0
 
 
+def _cpu_worker_c(job):
+    """Same sample through the plain-C oracle (oracle/ukf_oracle.c), one process per core."""
+    seed, n_tracks, n_steps = job
+    import numpy as np
+
+    from oracle import ukf_c as OC
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    syn = make_tracks(n_tracks, n_steps + 1, seed=seed, device="cpu")
+    H, R, Q, P = (np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
+    args = (syn.x0().numpy(), syn.dts.numpy(), syn.lon.numpy(), syn.lat.numpy(), syn.sog_rate.numpy(), syn.cog_rate.numpy(), H, Q, R, P)
+    OC.load()
+    t0 = time.perf_counter()
+    OC.run_batch(*args, substeps=1, smoother=True)
+    return n_tracks * n_steps, time.perf_counter() - t0
+
+
 def host_cores() -> int:
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -84,9 +101,9 @@ class CpuPool:
         self.pool = mp.get_context("spawn").Pool(cores)
         self.pool.map(_cpu_worker, [(0, 1, 2)] * cores)  # import numpy/scipy/torch once per worker
 
-    def run(self, tracks_per_core: int, n_steps: int, seed: int):
+    def run(self, tracks_per_core: int, n_steps: int, seed: int, worker=None):
         """-> (aggregate track-steps/s, track-steps done, slowest worker's busy seconds)."""
-        out = self.pool.map(_cpu_worker, [(seed + c, tracks_per_core, n_steps) for c in range(self.cores)], chunksize=1)
+        out = self.pool.map(worker or _cpu_worker, [(seed + c, tracks_per_core, n_steps) for c in range(self.cores)], chunksize=1)
         steps, busy = sum(o[0] for o in out), max(o[1] for o in out)
         return steps / busy, steps, busy
 
@@ -372,11 +389,15 @@ def run_gpu_arm(args):
             cores = host_cores()
             pool = CpuPool(cores)
             v, steps, busy = pool.run(args.cpu_tracks_per_core, N_STEPS, seed=4321)
+            vc, steps_c, busy_c = pool.run(64 * args.cpu_tracks_per_core, N_STEPS, seed=8765, worker=_cpu_worker_c)
             pool.close()
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": (f"{cores} processes x {args.cpu_tracks_per_core} tracks x {N_STEPS} steps of the same synthetic workload (UKF then URTSS, "
                            f"zero noise), numpy oracle port calling the reference's scipy/numpy routines: {steps} track-steps, slowest worker {busy:.1f} s"),
+                "compiled_port": {"value": vc, "unit": UNIT, "cores": cores,
+                                  "sample": (f"plain-C restatement (oracle/ukf_oracle.c, gcc -O2, one process per core): "
+                                             f"{steps_c} track-steps, slowest worker {busy_c:.1f} s")},
             }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -441,3 +441,24 @@ def test_long_tracks_against_oracle(cuda, native_lib):
     r1, r2 = ukf.run(b), ukf.run(b)
     assert torch.isfinite(r1.mean_s).all() and torch.isfinite(r1.cov_s).all() and int(r1.status.sum()) == 0
     assert torch.equal(r1.mean_s, r2.mean_s) and torch.equal(r1.cov_s[10000], r1.cov_f[10000])
+
+
+def test_large_tile_against_c_oracle(cuda, native_lib):
+    """Every track of a 2048 x 256-step tile (UKF + URTSS) against the plain-C oracle."""
+    from oracle import ukf_c as OC
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T, N = 2048, 256
+    syn = make_tracks(T, N + 1, seed=31, device="cpu")
+    res = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF).run(TrackBatch.from_synthetic(syn, substeps=1).to(cuda))
+    ref = OC.run_batch(syn.x0().numpy(), syn.dts.numpy(), syn.lon.numpy(), syn.lat.numpy(), syn.sog_rate.numpy(), syn.cog_rate.numpy(),
+                       H_POS, Q_DEF, R_POS, P_DEF, substeps=1)
+    for key, got in (("mean_f", res.mean_f), ("mean_s", res.mean_s)):
+        g, r = got.cpu().numpy(), ref[key]
+        d = g - r
+        d[:, 3] = (d[:, 3] + 180.0) % 360.0 - 180.0
+        assert float(np.max(np.abs(d) / np.maximum(1.0, np.abs(r)))) <= TOL, key
+    for key, got in (("cov_f", res.cov_f), ("cov_s", res.cov_s)):
+        g, r = got.cpu().numpy(), ref[key]
+        assert float(np.max(np.max(np.abs(g - r), axis=1) / np.max(np.abs(r), axis=1))) <= TOL, key

@@ -106,3 +106,47 @@ def test_update_mask_exact_equality():
         m = O.update_mask(O.generate_dts(dts, k), dts)
         hits = m.reshape(-1, k)[:, -1]
         assert (hits.all() and m.sum() == len(dts)) == expect_all
+
+
+# --------------------------------------------------------------------------------------------- #
+# the plain-C oracle (oracle/ukf_oracle.c): same fixtures, same bound as the CUDA path             #
+# --------------------------------------------------------------------------------------------- #
+ALL_FIXTURES = FIXTURES + ["c2_historical_batch"]
+
+
+@pytest.mark.parametrize("name", ALL_FIXTURES)
+def test_c_oracle_matches_reference_fixture(name):
+    from _helpers import assert_track_close
+    from oracle import ukf_c as OC
+
+    tracks, _ = load_golden(name)
+    for i, tr in enumerate(tracks):
+        noise = dict(pred=tr["noise_pred"], upd=tr["noise_upd"], bwd=tr.get("noise_bwd")) if "noise_pred" in tr else None
+        out = OC.run_track(tr["x0"], tr["P0"], tr["H"], tr["Q"], tr["R"], tr["dt_array"], tr["dts"], tr["z"], tr["sog_rate"],
+                           tr["cog_rate"], smoother="means_s" in tr, noise=noise, gating="gate_iters" in tr)
+        assert np.array_equal(out["mask"], tr["mask"])
+        if "gate_iters" in tr:
+            assert np.array_equal(out["gate_iters"], tr["gate_iters"]), f"{name}[{i}]"
+            np.testing.assert_allclose(out["gate_lambda"], tr["gate_lambda"], rtol=1e-9)
+        assert_track_close(out, tr, smoother="means_s" in tr, label=f"C oracle {name}[{i}]")
+
+
+def test_c_oracle_batch_layout_matches_per_track_calls():
+    """oracle_batch (the [plane][T] driver used for large parity runs and the CPU baseline) against
+    run_track on the same synthetic tile."""
+    from oracle import ukf_c as OC
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T, nobs, k = 5, 33, 2
+    syn = make_tracks(T, nobs, seed=12, device="cpu", dts_choices=(1.0, 2.0))
+    H, R = np.diag([1.0, 1.0, 0.0, 0.0]), np.diag([1e-3, 1e-3, 0.0, 0.0])
+    Q, P = np.diag([1e-2, 1e-2, 1e-4, 1e-4]), np.eye(4)
+    dt = np.repeat(syn.dts.numpy() / k, k, axis=0)
+    out = OC.run_batch(syn.x0().numpy(), dt, syn.lon.numpy(), syn.lat.numpy(), syn.sog_rate.numpy(), syn.cog_rate.numpy(), H, Q, R, P,
+                       substeps=k, z_sog=syn.sog.numpy(), z_cog=syn.cog.numpy())
+    for t in range(T):
+        z = np.stack([syn.lon[:, t].numpy(), syn.lat[:, t].numpy(), syn.sog[:, t].numpy(), syn.cog[:, t].numpy()])
+        one = OC.run_track(z[:, 0], P, H, Q, R, dt[:, t], syn.dts[:, t].numpy(), z, syn.sog_rate[:, t].numpy(), syn.cog_rate[:, t].numpy())
+        assert np.array_equal(out["mean_s"][:, :, t], one["means_s"]) and np.array_equal(out["cov_f"][:, :, t].reshape(-1, 4, 4), one["covs"])
+        ref = O.run_track(z[:, 0], P, H, Q, R, dt[:, t], syn.dts[:, t].numpy(), z, syn.sog_rate[:, t].numpy(), syn.cog_rate[:, t].numpy())
+        assert mean_err(one["means_s"], ref["means_s"]) <= 1e-10 and cov_err(one["covs_s"], ref["covs_s"]) <= 1e-10
