@@ -133,6 +133,16 @@ int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs 
  * written by the forward pass, writes mean_s/cov_s. */
 int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream);
 
+/* The loop of examples/example_ukf_rts_smoother_batch.py:19-71 over successive tiles of tracks,
+ * software-pipelined: ONE launch runs KalmanFilterBase.run for the tracks of tile `fwd_*` and
+ * UnscentedKalmanFilter.rts_step (all steps) for the tracks of tile `bwd_*`, which an earlier
+ * call has already filtered (forward pass or fused pass, with smooth_stats).  Results are
+ * bit-identical to ste_ukf_forward_f64(fwd) followed by ste_urtss_backward_f64(bwd); the
+ * smoother's memory latency hides behind the filter's arithmetic.  The two tiles must use
+ * different output arrays; either may be empty (n_tracks == 0). */
+int ste_ukf_fused_f64(const SteProblem *fwd_prob, const SteInputs *fwd_in, SteOutputs *fwd_out,
+                      const SteProblem *bwd_prob, const SteInputs *bwd_in, SteOutputs *bwd_out, void *stream);
+
 /* One UnscentedKalmanFilter.predict (unscented.py:144-207) for T independent filters, in place.
  * x [4][ld], P [16][ld], dt/sog_rate/cog_rate [T]; noise [4][ld] unit normals or NULL;
  * sigma_prior / sigma_post [36][ld] (plane = row*9 + point) or NULL; status [T] or NULL. */

@@ -456,6 +456,42 @@ class BatchedUKF:
         with torch.cuda.device(b.device):
             nat.check(self._lib.ste_urtss_backward_f64(C.byref(p), C.byref(i), C.byref(o), nat.current_stream()))
 
+    def fused(self, fwd_batch: TrackBatch, fwd_res: TrackResults, bwd_batch: TrackBatch, bwd_res: TrackResults) -> None:
+        """ONE launch: the forward filter of ``fwd_batch`` and the backward smoother of ``bwd_batch``
+        (filtered by an earlier ``forward``/``fused`` call into ``bwd_res``).  Bit-identical to
+        ``forward(fwd_batch, fwd_res); backward(bwd_batch, bwd_res)``; the smoother's memory
+        latency hides behind the filter's arithmetic.  The two result sets must be distinct."""
+        self._check_rows(fwd_batch)
+        self._check_layout(fwd_res)
+        self._check_layout(bwd_res)
+        if bwd_res.mean_s is None:
+            raise ValueError("results were allocated without smoother buffers")
+        if self.model.gating and fwd_batch.noise_upd is not None:
+            raise NotImplementedError("gating with measurement noise tapes (data-dependent draw count)")
+        if fwd_batch.device != bwd_batch.device:
+            raise ValueError("both tiles of a fused pass must live on one device")
+        pf, i_f, of = self._problem(fwd_batch), self._inputs(fwd_batch), self._outputs(fwd_res)
+        pb, ib, ob = self._problem(bwd_batch), self._inputs(bwd_batch), self._outputs(bwd_res)
+        with torch.cuda.device(fwd_batch.device):
+            nat.check(self._lib.ste_ukf_fused_f64(C.byref(pf), C.byref(i_f), C.byref(of), C.byref(pb), C.byref(ib), C.byref(ob),
+                                                  nat.current_stream()))
+
+    def run_many(self, batches: Sequence[TrackBatch], results: Sequence[TrackResults]) -> None:
+        """Filter and smooth a sequence of resident tiles, software-pipelined: tile i+1 is filtered
+        by the same launch that smooths tile i (``len(batches) + 1`` launches).  Consecutive tiles
+        must use different result sets (two alternating sets are enough when each tile's results
+        are consumed, in stream order, before its set comes round again)."""
+        n = len(batches)
+        if n != len(results):
+            raise ValueError("one result set per tile")
+        for i in range(n + 1):
+            if i == 0:
+                self.forward(batches[0], results[0])
+            elif i == n:
+                self.backward(batches[n - 1], results[n - 1])
+            else:
+                self.fused(batches[i], results[i], batches[i - 1], results[i - 1])
+
     def run_host(self, host_batch: TrackBatch, host_out: TrackResults, dev_res: TrackResults, smoother: bool = True,
                  device="cuda") -> Dict[str, int]:
         """End-to-end call on HOST buffers: pinned inputs -> device, forward (+ backward), results ->

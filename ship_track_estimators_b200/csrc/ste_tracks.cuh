@@ -78,38 +78,53 @@ STE_DEV bool any_nonfinite(const double (&x)[4], const double (&P)[10]) {
 
 // ------------------------------------------------------------------------------------------ //
 // Forward filter: KalmanFilterBase.run (kalman_filter.py:36-117).
+//
+// The time loop is written as begin() / step(s) / end() on a small state object so that the
+// fused kernel can interleave it, step by step, with the backward pass of another tile.
 // ------------------------------------------------------------------------------------------ //
-template <bool POS_ONLY, bool GATING>
-STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) {
-    const int64_t ld = a.prob.ld;
-    const int nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
-    const Model model{a.prob.H, a.prob.Q, a.prob.R};
-    const int k_sub = a.prob.substeps > 0 ? a.prob.substeps : 1;
-
+// PARK: between steps the state (x, P) rests in the (then dead) root slots of the scratch instead
+// of in registers, so that whatever the caller runs between two steps does not compete with it.
+template <bool POS_ONLY, bool GATING, bool PARK = false>
+struct ForwardTrack {
+    const KernelArgs &a;
+    const int t;
+    const Scratch sc;
+    const int64_t ld;
+    const bool packed;
+    int nt = 0, k_sub = 1;
     double x[4], P[10];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) x[r] = a.in.x0[r * ld + t];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = i; j < 4; ++j)
-            P[SYM(i, j)] = a.in.P0 ? a.in.P0[(i * 4 + j) * ld + t] : a.prob.P0[i * 4 + j];
-    int status = 0;
-    const bool packed = (a.prob.flags & STE_FLAG_PACKED_COV) != 0;
-    store_state(a.out.mean_f, a.out.cov_f, ld, 0, t, packed, x, P);  // the prior (kalman_filter.py:76-77)
+    int status = 0, ui = 0;
+    // The smoother statistics are valid for the backward pass only if it would read the same
+    // rates: it indexes them by step / rate_repeat (unscented.py:287-311), the filter by the
+    // update index.  They agree on every regular step grid; a track where they do not is flagged
+    // and smoothed by recomputation.
+    int rep = 1, ri = 0, rc = 0;
+    bool consistent = true, upd_next = false;
 
-    // observation rows are staged into scratch by stage_obs() a whole predict ahead of their use
-    auto stage_obs = [&](int ui) {
+    STE_DEV ForwardTrack(const KernelArgs &args, int track, const Scratch &scratch)
+        : a(args), t(track), sc(scratch), ld(args.prob.ld), packed((args.prob.flags & STE_FLAG_PACKED_COV) != 0) {}
+
+    // observation rows are staged into scratch a whole predict ahead of their use
+    STE_DEV void stage_obs(int u) const {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            if ((!POS_ONLY || r < 2) && a.in.z[r]) stage_async(&sc.at(kScratchObs + r), a.in.z[r] + (int64_t)ui * ld + t);
+            if ((!POS_ONLY || r < 2) && a.in.z[r]) stage_async(&sc.at(kScratchObs + r), a.in.z[r] + (int64_t)u * ld + t);
         }
-    };
-#pragma unroll
-    for (int r = 0; r < 4; ++r) sc.at(kScratchObs + r) = 0.0;   // absent rows read as 0
-    stage_obs(0);
+    }
+    // Inputs of step s (dt, the two rates, the observation of its update) are staged into shared
+    // scratch with cp.async one whole step ahead: no register is held across the sigma-point loop
+    // and the DRAM latency hides behind ~4000 instructions of the previous step.
+    STE_DEV void stage_step(int s, int rate_index) const {
+        stage_async(&sc.at(kScratchIn + 0), a.in.dt + (int64_t)s * ld + t);
+        stage_async(&sc.at(kScratchIn + 1), a.in.sog_rate + (int64_t)rate_index * ld + t);
+        stage_async(&sc.at(kScratchIn + 2), a.in.cog_rate + (int64_t)rate_index * ld + t);
+    }
+    STE_DEV bool step_updates(int s) const {
+        return a.in.upd_mask ? (a.in.upd_mask[(int64_t)s * ld + t] != 0) : ((s + 1) % k_sub == 0);
+    }
 
-    auto assimilate = [&](int ui) {
+    STE_DEV void assimilate(int u) {
+        const Model model{a.prob.H, a.prob.Q, a.prob.R};
         double z[4], un[4];
         stage_wait();
 #pragma unroll
@@ -117,7 +132,7 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
         const double *noise = nullptr;
         if (a.in.noise_upd) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) un[r] = a.in.noise_upd[((int64_t)ui * 4 + r) * ld + t];
+            for (int r = 0; r < 4; ++r) un[r] = a.in.noise_upd[((int64_t)u * 4 + r) * ld + t];
             noise = un;
         }
         int it;
@@ -127,45 +142,53 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
         else
             ukf_update_generic<GATING>(x, P, model, z, noise, a.prob.gate_chi, a.prob.gate_max_iter, status, it, lam, rs);
         if (GATING) {
-            if (a.out.gate_iters) a.out.gate_iters[(int64_t)ui * ld + t] = (uint8_t)min_(it, 255);
-            if (a.out.gate_lambda) a.out.gate_lambda[(int64_t)ui * ld + t] = lam;
-            if (a.out.gate_scale) a.out.gate_scale[(int64_t)ui * ld + t] = rs;
+            if (a.out.gate_iters) a.out.gate_iters[(int64_t)u * ld + t] = (uint8_t)min_(it, 255);
+            if (a.out.gate_lambda) a.out.gate_lambda[(int64_t)u * ld + t] = lam;
+            if (a.out.gate_scale) a.out.gate_scale[(int64_t)u * ld + t] = rs;
         }
-    };
-
-    int ui = 0;
-    // The smoother statistics are valid for the backward pass only if it would read the same
-    // rates: it indexes them by step / rate_repeat (unscented.py:287-311), the filter by the
-    // update index.  They agree on every regular step grid; a track where they do not is flagged
-    // and smoothed by recomputation.
-    int rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
-    rep = rep > 0 ? rep : 1;
-    int ri = 0, rc = 0;
-    bool consistent = true;
-
-    // Inputs of step s (dt, the two rates, the observation of its update) are staged into shared
-    // scratch with cp.async one whole step ahead: no register is held across the sigma-point loop
-    // and the DRAM latency hides behind ~4000 instructions of the previous step.
-    auto stage_step = [&](int s, int rate_index) {
-        stage_async(&sc.at(kScratchIn + 0), a.in.dt + (int64_t)s * ld + t);
-        stage_async(&sc.at(kScratchIn + 1), a.in.sog_rate + (int64_t)rate_index * ld + t);
-        stage_async(&sc.at(kScratchIn + 2), a.in.cog_rate + (int64_t)rate_index * ld + t);
-    };
-    auto step_updates = [&](int s) -> bool {
-        return a.in.upd_mask ? (a.in.upd_mask[(int64_t)s * ld + t] != 0) : ((s + 1) % k_sub == 0);
-    };
-    bool upd_next = false;
-    if (nt > 0) {
-        stage_step(0, 0);
-        upd_next = step_updates(0);
     }
-    assimilate(0);   // kalman_filter.py:81 (waits for the staged copies, including step 0's inputs)
 
-#pragma unroll 1
-    for (int s = 0; s < nt; ++s) {
-#if defined(STE_STEP_SYNC) && defined(__CUDA_ARCH__)
-        __syncthreads();   // experiment: keep the warps of a block in phase (uniform track lengths only)
-#endif
+    STE_DEV void begin() {
+        nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
+        k_sub = a.prob.substeps > 0 ? a.prob.substeps : 1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[r] = a.in.x0[r * ld + t];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = i; j < 4; ++j)
+                P[SYM(i, j)] = a.in.P0 ? a.in.P0[(i * 4 + j) * ld + t] : a.prob.P0[i * 4 + j];
+        store_state(a.out.mean_f, a.out.cov_f, ld, 0, t, packed, x, P);  // the prior (kalman_filter.py:76-77)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sc.at(kScratchObs + r) = 0.0;   // absent rows read as 0
+        stage_obs(0);
+        rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
+        rep = rep > 0 ? rep : 1;
+        if (nt > 0) {
+            stage_step(0, 0);
+            upd_next = step_updates(0);
+        }
+        assimilate(0);   // kalman_filter.py:81 (waits for the staged copies, including step 0's inputs)
+        park();
+    }
+
+    STE_DEV void park() const {
+        if (!PARK) return;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sc.at(kScratchRoot + r) = x[r];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sc.at(kScratchRoot + 4 + k) = P[k];
+    }
+    STE_DEV void unpark() {
+        if (!PARK) return;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[r] = sc.at(kScratchRoot + r);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) P[k] = sc.at(kScratchRoot + 4 + k);
+    }
+
+    STE_DEV void step(int s) {
+        unpark();
         const bool upd = upd_next;
         const double dt = sc.at(kScratchIn + 0), sr = sc.at(kScratchIn + 1), cr = sc.at(kScratchIn + 2);
         consistent &= (min_(ri, a.prob.max_obs - 1) == ui);
@@ -193,11 +216,30 @@ STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) 
         if (upd) assimilate(ui);
         else stage_wait();   // the next step's inputs must have landed before they are read
         store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, packed, x, P);
+        park();
     }
-    if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
-    if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;
-    a.out.status[t] = status;
-    if (a.out.n_updates) a.out.n_updates[t] = ui + 1;
+
+    STE_DEV void end() {
+        unpark();
+        if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
+        if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;
+        a.out.status[t] = status;
+        if (a.out.n_updates) a.out.n_updates[t] = ui + 1;
+    }
+};
+
+template <bool POS_ONLY, bool GATING>
+STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) {
+    ForwardTrack<POS_ONLY, GATING> f(a, t, sc);
+    f.begin();
+#pragma unroll 1
+    for (int s = 0; s < f.nt; ++s) {
+#if defined(STE_STEP_SYNC) && defined(__CUDA_ARCH__)
+        __syncthreads();   // experiment: keep the warps of a block in phase (uniform track lengths only)
+#endif
+        f.step(s);
+    }
+    f.end();
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -211,15 +253,26 @@ STE_DEV void prefetch_l2(const void *p) {
 #endif
 }
 
-STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc) {
-    const int64_t ld = a.prob.ld;
-    const int nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
-    int rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
-    rep = rep > 0 ? rep : 1;
-    int status = 0;
-    const bool packed = (a.prob.flags & STE_FLAG_PACKED_COV) != 0;
+struct BackwardTrack {
+    const KernelArgs &a;
+    const int t;
+    Scratch sc;
+    const int64_t ld;
+    const bool packed;
+    int nt = 0, rep = 1, status = 0;
+    // Statistics stored by the forward pass replace the sigma-point recomputation for every step
+    // but step 0: state 0 is the PRIOR (kalman_filter.py:76-81), which the filter never predicted
+    // from (it predicted from the prior's update), so its statistics do not exist.
+    bool use_stats = false, bad = false;
 
-    {   // the last state is untouched by the smoother (:297); it seeds the carried (xs, Ps)
+    STE_DEV BackwardTrack(const KernelArgs &args, int track, const Scratch &scratch)
+        : a(args), t(track), sc(scratch), ld(args.prob.ld), packed((args.prob.flags & STE_FLAG_PACKED_COV) != 0) {}
+
+    STE_DEV void begin() {
+        nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
+        rep = a.in.rate_repeat ? a.in.rate_repeat[t] : a.prob.rate_repeat;
+        rep = rep > 0 ? rep : 1;
+        // the last state is untouched by the smoother (:297); it seeds the carried (xs, Ps)
         double xs[4], Ps[10];
         load_state(a.out.mean_f, a.out.cov_f, ld, nt, t, packed, xs, Ps);
         if (a.out.mean_s != a.out.mean_f || a.out.cov_s != a.out.cov_f)
@@ -228,14 +281,28 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
         for (int r = 0; r < 4; ++r) sc.at(kScratchXs + r) = xs[r];
 #pragma unroll
         for (int k = 0; k < 10; ++k) sc.at(kScratchPs + k) = Ps[k];
+        use_stats = a.out.smooth_stats && !(a.out.status[t] & STE_STATUS_SMOOTH_RECOMPUTE);
     }
-    // Statistics stored by the forward pass replace the sigma-point recomputation for every step
-    // but step 0: state 0 is the PRIOR (kalman_filter.py:76-81), which the filter never predicted
-    // from (it predicted from the prior's update), so its statistics do not exist.
-    const bool use_stats = a.out.smooth_stats && !(a.out.status[t] & STE_STATUS_SMOOTH_RECOMPUTE);
-    bool bad = false;
-#pragma unroll 1
-    for (int step = nt - 1; step >= 0; --step) {
+
+    // Pull what step(step) will read from the statistics path towards L2 (no register, no
+    // scratch): issued a whole forward step ahead by the fused kernel.
+    STE_DEV void prefetch_stats_step(int step) const {
+        const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
+        const double *cf = a.out.cov_f + ((int64_t)step * cov_planes(packed)) * ld + t;
+        const double *st = a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) prefetch_l2(mf + r * ld);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = i; j < 4; ++j) prefetch_l2(cf + cov_plane(packed, i, j) * ld);
+#pragma unroll
+        for (int k = 0; k < kStatsPlanes; ++k) prefetch_l2(st + k * ld);
+    }
+
+    // STATS_ONLY: the caller guarantees use_stats && step > 0 (no recomputation code is generated)
+    template <bool STATS_ONLY = false>
+    STE_DEV void step(int step) {
         const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
         const double *cf = a.out.cov_f + ((int64_t)step * cov_planes(packed)) * ld + t;
         double xf[4], xs[4], Ps[10];
@@ -247,7 +314,7 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
             for (int r = 0; r < 4; ++r)
                 e[r] = a.in.noise_bwd[((int64_t)step * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
-        if (use_stats && step > 0) {
+        if (STATS_ONLY || (use_stats && step > 0)) {
             double Pf[10];
             load_cov(cf, ld, packed, Pf);
             urtss_step_from_stats(xf, Pf, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, e, xs, Ps,
@@ -279,8 +346,88 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
         store_state(a.out.mean_s, a.out.cov_s, ld, step, t, packed, xs, Ps);
         bad |= any_nonfinite(xs, Ps);
     }
-    if (bad) status |= STE_STATUS_NONFINITE;
-    a.out.status[t] |= status;
+
+    STE_DEV void end() {
+        if (bad) status |= STE_STATUS_NONFINITE;
+        a.out.status[t] |= status;
+    }
+};
+
+STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc) {
+    BackwardTrack g(a, t, sc);
+    g.begin();
+#pragma unroll 1
+    for (int step = g.nt - 1; step >= 0; --step) g.step(step);
+    g.end();
+}
+
+// ------------------------------------------------------------------------------------------ //
+// Fused pass: the forward filter of tile A and the backward smoother of tile B (already
+// filtered, statistics on its tape) in ONE time loop per thread.  The smoother step is ~13 % of
+// the filter step's arithmetic but, run as its own kernel, it is bound by HBM latency/bandwidth
+// and takes ~30 % of the time.  Here its 44 input values are pulled towards L2 at the top of the
+// iteration, the forward step (several microseconds of FP64 work) runs, and the smoother step
+// then reads L2 hits and spends its few hundred instructions in the FP64 pipe's idle slots.
+// Results are bit-identical to the two separate passes: the same step functions run in the
+// same order per track.
+//
+// Scratch layout of the fused kernel (slots per thread):
+//   [0, 46)   the forward pass's slots (40 used); after the loop, the backward recomputation
+//             (step 0, or every step of a track whose statistics are unusable) reuses them in
+//             the stand-alone backward layout (root 0..15, xs/Ps 16..29, Delta 30..45)
+//   [46, 60)  (xs, Ps) of the backward pass while the loop runs
+// ------------------------------------------------------------------------------------------ //
+constexpr int kScratchFusedCarry = 46;
+constexpr int kScratchSlotsFused = 60;
+
+template <bool POS_ONLY, bool GATING>
+STE_DEV void fused_track(const KernelArgs &a, const KernelArgs &b, const int t, const Scratch &sc) {
+    const bool has_f = t < a.prob.n_tracks, has_b = t < b.prob.n_tracks;
+    ForwardTrack<POS_ONLY, GATING, true> f(a, t, sc);
+    // the carried (xs, Ps) sit at kScratchXs/kScratchPs relative to a shifted base
+    BackwardTrack g(b, t, Scratch{sc.base + (long)(kScratchFusedCarry - kScratchXs) * sc.stride, sc.stride});
+    if (has_b) g.begin();
+    if (has_f) f.begin();
+    // tracks without usable statistics are smoothed entirely after the loop
+    const int nb_loop = (has_b && g.use_stats && g.nt > 0) ? g.nt - 1 : 0;
+    int n_iter = f.nt > nb_loop ? f.nt : nb_loop;
+#if defined(STE_FUSED_SYNC) && defined(__CUDA_ARCH__)
+    {
+        __shared__ int block_iters;
+        if (threadIdx.x == 0) block_iters = 0;
+        __syncthreads();
+        atomicMax(&block_iters, n_iter);
+        __syncthreads();
+        n_iter = block_iters;
+    }
+#endif
+#pragma unroll 1
+    for (int i = 0; i < n_iter; ++i) {
+#if defined(STE_FUSED_SYNC) && defined(__CUDA_ARCH__)
+        __syncthreads();   // keep the warps of a block on the same instructions (shared fetch)
+#endif
+        const int sb = g.nt - 1 - i;
+        const bool do_b = i < nb_loop;
+        if (do_b) g.prefetch_stats_step(sb);
+        if (i < f.nt) f.step(i);
+        if (do_b) g.step<true>(sb);
+    }
+    if (has_f) f.end();
+    if (has_b) {
+        double xs[4], Ps[10];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xs[r] = g.sc.at(kScratchXs + r);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) Ps[k] = g.sc.at(kScratchPs + k);
+        g.sc = sc;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g.sc.at(kScratchXs + r) = xs[r];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) g.sc.at(kScratchPs + k) = Ps[k];
+#pragma unroll 1
+        for (int step = g.nt - 1 - nb_loop; step >= 0; --step) g.step(step);
+        g.end();
+    }
 }
 
 }  // namespace ste

@@ -17,13 +17,20 @@ namespace ste {
 #define STE_THREADS 128
 #endif
 constexpr int kThreads = STE_THREADS;
-// Minimum resident blocks per SM the register allocator must make room for (occupancy is bounded by
-// registers only: these kernels use 16 KB of shared memory per block and almost no bandwidth).
+// Minimum resident blocks per SM the register allocator must make room for (measured optima):
+//  - forward: 3 blocks = 12 warps at 159 registers, no spills (2 blocks: -5 %, 4 blocks: spills);
+//  - backward over the statistics tape: HBM-bound, and what hurts it is local-memory traffic, so
+//    it gets the registers it asks for (227, no spills) at 2 blocks = 8 warps: 13.7e9 track-steps/s
+//    against 10.2e9 at 4 blocks / 128 registers / 208 B of spills;
+//  - backward by recomputation (no tape): compute-bound like the forward pass, 4 blocks.
 #ifndef STE_FWD_MIN_BLOCKS
 #define STE_FWD_MIN_BLOCKS 3
 #endif
 #ifndef STE_BWD_MIN_BLOCKS
-#define STE_BWD_MIN_BLOCKS 4
+#define STE_BWD_MIN_BLOCKS 2
+#endif
+#ifndef STE_BWD_RECOMPUTE_MIN_BLOCKS
+#define STE_BWD_RECOMPUTE_MIN_BLOCKS 4
 #endif
 
 template <bool POS_ONLY, bool GATING>
@@ -33,10 +40,30 @@ __global__ void __launch_bounds__(kThreads, STE_FWD_MIN_BLOCKS) ukf_forward_kern
     if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
 
-__global__ void __launch_bounds__(kThreads, STE_BWD_MIN_BLOCKS) urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
+// TAPE: the launch has a statistics tape (same code either way; only the register budget differs)
+template <bool TAPE>
+__global__ void __launch_bounds__(kThreads, TAPE ? STE_BWD_MIN_BLOCKS : STE_BWD_RECOMPUTE_MIN_BLOCKS)
+urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
     extern __shared__ double scratch[];   // kScratchSlotsBwd * kThreads doubles (46 KB: opt-in size)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.prob.n_tracks) backward_track(a, t, Scratch{scratch + threadIdx.x, kThreads});
+}
+
+#ifndef STE_FUSED_MIN_BLOCKS
+#define STE_FUSED_MIN_BLOCKS 2   // 242 registers, no spills; at 3 blocks the 4000-instruction loop starves on instruction fetch
+#endif
+// forward pass of tile a + backward pass of tile b, one thread per (track of a, track of b)
+template <bool POS_ONLY, bool GATING>
+__global__ void __launch_bounds__(kThreads, STE_FUSED_MIN_BLOCKS)
+ukf_fused_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ KernelArgs b) {
+    extern __shared__ double scratch[];   // kScratchSlotsFused * kThreads doubles
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+#if defined(STE_FUSED_SYNC)
+    fused_track<POS_ONLY, GATING>(a, b, t, Scratch{scratch + threadIdx.x, kThreads});   // block-wide barriers inside
+#else
+    if (t < a.prob.n_tracks || t < b.prob.n_tracks)
+        fused_track<POS_ONLY, GATING>(a, b, t, Scratch{scratch + threadIdx.x, kThreads});
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -408,7 +435,7 @@ int ste_version(void) { return STE_ABI_VERSION; }
 
 const char *ste_last_error(void) { return g_err; }
 
-int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream) {
+static int validate_forward(const SteProblem *prob, const SteInputs *in, const SteOutputs *out) {
     if (int rc = validate_problem(prob)) return rc;
     if (!in || !out) return fail(STE_ERR_INVALID_ARG, "null SteInputs/SteOutputs");
     if (!in->x0 || !in->dt || !in->sog_rate || !in->cog_rate) return fail(STE_ERR_INVALID_ARG, "missing input array");
@@ -424,11 +451,33 @@ int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs 
         if (pos) used = r < 2;  // rows 2, 3 only ever multiply exact zeros of pinv(S)
         if (used && !in->z[r]) return fail(STE_ERR_INVALID_ARG, "observation row referenced by H/R is NULL");
     }
-    if (prob->n_tracks == 0) return STE_OK;
+    return STE_OK;
+}
+
+static int validate_backward(const SteProblem *prob, const SteInputs *in, const SteOutputs *out) {
+    if (int rc = validate_problem(prob)) return rc;
+    if (!in || !out) return fail(STE_ERR_INVALID_ARG, "null SteInputs/SteOutputs");
+    if (!in->dt || !in->sog_rate || !in->cog_rate) return fail(STE_ERR_INVALID_ARG, "missing input array");
+    if (!out->mean_f || !out->cov_f || !out->mean_s || !out->cov_s || !out->status)
+        return fail(STE_ERR_INVALID_ARG, "missing output array");
+    if ((out->mean_s == out->mean_f) != (out->cov_s == out->cov_f))
+        return fail(STE_ERR_INVALID_ARG, "in-place smoothing must alias both mean and cov");
+    return STE_OK;
+}
+
+static KernelArgs kernel_args(const SteProblem *prob, const SteInputs *in, const SteOutputs *out) {
     KernelArgs a;
     a.prob = *prob;
     a.in = *in;
     a.out = *out;
+    return a;
+}
+
+int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream) {
+    if (int rc = validate_forward(prob, in, out)) return rc;
+    if (prob->n_tracks == 0) return STE_OK;
+    const bool gating = (prob->flags & STE_FLAG_GATING) != 0, pos = position_only(*prob);
+    const KernelArgs a = kernel_args(prob, in, out);
     const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
     cudaStream_t s = (cudaStream_t)stream;
     if (pos) {
@@ -442,24 +491,44 @@ int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs 
 }
 
 int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream) {
-    if (int rc = validate_problem(prob)) return rc;
-    if (!in || !out) return fail(STE_ERR_INVALID_ARG, "null SteInputs/SteOutputs");
-    if (!in->dt || !in->sog_rate || !in->cog_rate) return fail(STE_ERR_INVALID_ARG, "missing input array");
-    if (!out->mean_f || !out->cov_f || !out->mean_s || !out->cov_s || !out->status)
-        return fail(STE_ERR_INVALID_ARG, "missing output array");
-    if ((out->mean_s == out->mean_f) != (out->cov_s == out->cov_f))
-        return fail(STE_ERR_INVALID_ARG, "in-place smoothing must alias both mean and cov");
+    if (int rc = validate_backward(prob, in, out)) return rc;
     if (prob->n_tracks == 0) return STE_OK;
-    KernelArgs a;
-    a.prob = *prob;
-    a.in = *in;
-    a.out = *out;
+    const KernelArgs a = kernel_args(prob, in, out);
     const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
     const size_t smem = sizeof(double) * kScratchSlotsBwd * kThreads;
-    if (cudaFuncSetAttribute(urtss_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    auto kernel = out->smooth_stats ? urtss_backward_kernel<true> : urtss_backward_kernel<false>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return check_launch("cudaFuncSetAttribute(urtss_backward_kernel)");
-    urtss_backward_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(a);
+    kernel<<<grid, block, smem, (cudaStream_t)stream>>>(a);
     return check_launch("urtss_backward_kernel");
+}
+
+extern "C++" {
+template <bool POS_ONLY, bool GATING>
+static int launch_fused(const KernelArgs &a, const KernelArgs &b, cudaStream_t s) {
+    const int n = a.prob.n_tracks > b.prob.n_tracks ? a.prob.n_tracks : b.prob.n_tracks;
+    const dim3 grid((n + kThreads - 1) / kThreads), block(kThreads);
+    const size_t smem = sizeof(double) * kScratchSlotsFused * kThreads;
+    if (cudaFuncSetAttribute(ukf_fused_kernel<POS_ONLY, GATING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(ukf_fused_kernel)");
+    ukf_fused_kernel<POS_ONLY, GATING><<<grid, block, smem, s>>>(a, b);
+    return check_launch("ukf_fused_kernel");
+}
+}  // extern "C++"
+
+int ste_ukf_fused_f64(const SteProblem *fwd_prob, const SteInputs *fwd_in, SteOutputs *fwd_out,
+                      const SteProblem *bwd_prob, const SteInputs *bwd_in, SteOutputs *bwd_out, void *stream) {
+    if (int rc = validate_forward(fwd_prob, fwd_in, fwd_out)) return rc;
+    if (int rc = validate_backward(bwd_prob, bwd_in, bwd_out)) return rc;
+    if (fwd_out->mean_f == bwd_out->mean_f || fwd_out->mean_f == bwd_out->mean_s || fwd_out->status == bwd_out->status)
+        return fail(STE_ERR_INVALID_ARG, "the two tiles of a fused pass must not share output arrays");
+    if (fwd_prob->n_tracks == 0) return ste_urtss_backward_f64(bwd_prob, bwd_in, bwd_out, stream);
+    if (bwd_prob->n_tracks == 0) return ste_ukf_forward_f64(fwd_prob, fwd_in, fwd_out, stream);
+    const bool gating = (fwd_prob->flags & STE_FLAG_GATING) != 0, pos = position_only(*fwd_prob);
+    const KernelArgs a = kernel_args(fwd_prob, fwd_in, fwd_out), b = kernel_args(bwd_prob, bwd_in, bwd_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pos) return gating ? launch_fused<true, true>(a, b, s) : launch_fused<true, false>(a, b, s);
+    return gating ? launch_fused<false, true>(a, b, s) : launch_fused<false, false>(a, b, s);
 }
 
 int ste_ukf_predict_f64(const SteProblem *prob, double *x, double *P, const double *dt, const double *sog_rate,

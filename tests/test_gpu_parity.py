@@ -423,6 +423,81 @@ def test_pipelined_host_api(cuda, native_lib):
         assert torch.equal(r.mean_f.cpu(), o.mean_f) and torch.equal(r.status.cpu(), o.status)
 
 
+@pytest.mark.parametrize("gating,packed", [(False, False), (False, True), (True, True)])
+def test_fused_pass_is_bit_identical_to_separate_passes(gating, packed, cuda, native_lib):
+    """ste_ukf_fused_f64 (forward of one tile + backward of another in one launch) and run_many
+    against forward() + backward(): ragged tiles of different sizes, a tile of irregular sub-step
+    grids (statistics unusable: smoothed by recomputation inside the fused kernel), and an empty
+    tile on either side."""
+    import ctypes as C
+
+    import torch
+
+    from ship_track_estimators_b200 import _native as nat
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    R = np.diag([0.05, 0.05, 0.0, 0.0]) if gating else R_POS
+    ukf = BatchedUKF(H_POS, Q_DEF, R, P_DEF, gating=gating, packed_cov=packed)
+    kw = dict(outlier_frac=0.05) if gating else {}
+    shapes = [(700, 90, 1, dict(nobs_min=10)), (300, 140, 2, dict(dts_choices=(1, 2, 3), nobs_min=30)), (1000, 40, 1, dict())]
+    tiles = [TrackBatch.from_synthetic(make_tracks(T, n, seed=60 + i, device="cpu", **kw, **extra), substeps=k,
+                                       need_rows=ukf.model.rows_needed()).to(cuda)
+             for i, (T, n, k, extra) in enumerate(shapes)]
+    # irregular sub-step grids (1, 2 or 4 predicts per gap, binary-exact times): the smoother indexes
+    # the rates by step // rate_repeat, the filter by update, so most of these tracks are flagged
+    rng = np.random.default_rng(5)
+    sts, dt_arrays = [], []
+    while len(sts) < 150:
+        nobs = int(rng.integers(6, 30))
+        dts = rng.choice([1.0, 2.0], nobs - 1)
+        sub = rng.choice([1, 2, 4], nobs - 1)
+        n, rep = int(sub.sum()), int((sub.sum() + 1) / (nobs - 1))
+        if rep < 1 or (n - 1) // rep >= nobs:
+            continue        # the reference's smoother would index past its rates (IndexError there and here)
+        dt_arrays.append(np.concatenate([np.full(n, d / n) for d, n in zip(dts, sub)]))
+        lon, lat = np.cumsum(rng.normal(0, 0.05, nobs)) + 10, np.cumsum(rng.normal(0, 0.05, nobs)) + 50
+        sts.append(SimpleNamespace(dts=dts, z=np.stack([lon, lat, rng.uniform(5, 25, nobs), rng.uniform(0, 360, nobs)]),
+                                   sog_rate=rng.normal(0, 0.3, nobs), cog_rate=rng.normal(0, 2.0, nobs)))
+    tiles.insert(1, TrackBatch.from_tracks(sts, dt_arrays, device=cuda))
+    ref = [ukf.run(b) for b in tiles]
+    assert int(((ref[1].status & nat.STE_STATUS_SMOOTH_RECOMPUTE) != 0).sum()) > 50
+    got = [ukf.allocate(b) for b in tiles]
+    ukf.run_many(tiles, got)
+    torch.cuda.synchronize()
+
+    def owned_equal(b, r, g, names=("mean_f", "cov_f", "mean_s", "cov_s")):
+        T = b.n_tracks
+        steps = b.n_steps.cpu() if b.n_steps is not None else None
+        for name in names:
+            x, y = getattr(r, name), getattr(g, name)
+            for t in range(0, T, 7):            # what each track owns: states 0..n_steps
+                n = int(steps[t]) + 1 if steps is not None else x.shape[0]
+                assert torch.equal(x[:n, :, t], y[:n, :, t]), (name, t)
+        assert torch.equal(r.status[:T], g.status[:T]) and torch.equal(r.n_updates[:T], g.n_updates[:T])
+
+    for b, r, g in zip(tiles, ref, got):
+        owned_equal(b, r, g)
+
+    # an empty tile on either side degenerates to the plain pass (raw ABI)
+    p0, i0, o0 = nat.SteProblem(), nat.SteInputs(), nat.SteOutputs()
+    p0.n_tracks, p0.max_steps, p0.max_obs, p0.ld = 0, 0, 1, 0
+    p0.H[0] = p0.H[5] = 1.0
+    dummy = torch.zeros(16, dtype=torch.float64, device=cuda)
+    i0.x0 = i0.dt = i0.sog_rate = i0.cog_rate = i0.z[0] = i0.z[1] = dummy.data_ptr()
+    o0.mean_f = o0.cov_f = o0.mean_s = o0.cov_s = dummy.data_ptr()
+    o0.status = torch.zeros(1, dtype=torch.int32, device=cuda).data_ptr()
+    again = ukf.allocate(tiles[0])
+    p, i, o = ukf._problem(tiles[0]), ukf._inputs(tiles[0]), ukf._outputs(again)
+    stream = nat.current_stream()
+    assert native_lib.ste_ukf_fused_f64(C.byref(p), C.byref(i), C.byref(o), C.byref(p0), C.byref(i0), C.byref(o0), stream) == 0
+    assert native_lib.ste_ukf_fused_f64(C.byref(p0), C.byref(i0), C.byref(o0), C.byref(p), C.byref(i), C.byref(o), stream) == 0
+    torch.cuda.synchronize()
+    owned_equal(tiles[0], ref[0], again)
+    with pytest.raises(RuntimeError, match="must not share"):
+        ukf.fused(tiles[0], again, tiles[0], again)
+
+
 def test_long_tracks_against_oracle(cuda, native_lib):
     """Track lengths of the modern-ship data (thousands of fixes, BASELINE config 2): a 3000-step
     track against the oracle, and 64 tracks of 10 000 steps for finiteness / determinism."""
