@@ -286,6 +286,48 @@ STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&o
     }
 }
 
+// ---- small-argument inverse trigonometry: Maclaurin series, no reduction, no selects ----------- //
+// Used by the small-displacement tier of the geodetic step (a ship moves a few km per predict):
+//   atan q       for |q| <= 2^-4   (first neglected term q^14/15  < 1e-18 relative)
+//   asin s       for |s| <= 2^-7   (first neglected term 0.03 s^8 < 1e-18 relative)
+//   sqrt(1 + e)  for 0 <= e <= 2^-8 (first neglected term 0.016 e^7 < 1e-18)
+// The callers establish the ranges once per filter step (step_is_small).
+STE_CONST double kAtanS[6] = {-1.0 / 3.0, 1.0 / 5.0, -1.0 / 7.0, 1.0 / 9.0, -1.0 / 11.0, 1.0 / 13.0};
+STE_CONST double kAsinS[3] = {1.0 / 6.0, 3.0 / 40.0, 15.0 / 336.0};
+STE_CONST double kSqrt1pS[6] = {0.5, -0.125, 0.0625, -5.0 / 128.0, 7.0 / 256.0, -21.0 / 1024.0};
+constexpr double kSmallAtanMax = 0.0625;        // 2^-4
+constexpr double kSmallAsinMax = 0.0078125;     // 2^-7
+
+template <int N>
+STE_DEV void small_atan_v(const double (&q)[N], const double (&z)[N], double (&out)[N]) {   // z = q*q
+    double p[N];
+    STE_LANES p[l] = fma(z[l], kAtanS[5], kAtanS[4]);
+    STE_LANES p[l] = fma(z[l], p[l], kAtanS[3]);
+    STE_LANES p[l] = fma(z[l], p[l], kAtanS[2]);
+    STE_LANES p[l] = fma(z[l], p[l], kAtanS[1]);
+    STE_LANES p[l] = fma(z[l], p[l], kAtanS[0]);
+    STE_LANES out[l] = fma(q[l], z[l] * p[l], q[l]);
+}
+template <int N>
+STE_DEV void small_asin_v(const double (&s)[N], double (&out)[N]) {
+    double z[N], p[N];
+    STE_LANES z[l] = s[l] * s[l];
+    STE_LANES p[l] = fma(z[l], kAsinS[2], kAsinS[1]);
+    STE_LANES p[l] = fma(z[l], p[l], kAsinS[0]);
+    STE_LANES out[l] = fma(s[l], z[l] * p[l], s[l]);
+}
+// a * sqrt(1 + e)
+template <int N>
+STE_DEV void small_hypot_scale_v(const double (&a)[N], const double (&e)[N], double (&out)[N]) {
+    double p[N];
+    STE_LANES p[l] = fma(e[l], kSqrt1pS[5], kSqrt1pS[4]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[3]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[2]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[1]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[0]);
+    STE_LANES out[l] = fma(a[l], e[l] * p[l], a[l]);
+}
+
 template <bool X_NONNEG>
 STE_DEV double fast_atan2(double y, double x) {
     const double yv[1] = {y}, xv[1] = {x};

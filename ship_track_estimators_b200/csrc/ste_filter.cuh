@@ -64,6 +64,17 @@ STE_DEV bool step_in_fast_range(const double (&x)[4], const double (&P)[10], dou
            (oa < lim * lim) && (od < lim * lim);   // false on NaN
 }
 
+// Small-displacement tier (geodetic_finish_n<.., SMALL>): every sigma point moves at most 2^-7 rad
+// (|u_i| <= |u| + sqrt(tr3), times |dt|/R) and starts within 80 degrees of latitude
+// (|lat_i| <= |lat| + sqrt(tr3)); squares are compared so that no root is taken.  Then
+// |tan(dlon)| <= sin(2^-7) / cos(80.45 deg) / cos(dlon) = 0.0472 < 2^-4 as the series assume.
+STE_DEV bool step_is_small(const double (&x)[4], const double (&P)[10], double dtR) {
+    const double tr3 = 3.0 * (P[SYM(0, 0)] + P[SYM(1, 1)] + P[SYM(2, 2)] + P[SYM(3, 3)]);
+    const double a = kSmallAsinMax - fabs(x[2] * dtR);     // room left for the speed offset, in radians
+    const double b = 80.0 - fabs(x[1]);                    // room left for the latitude offset, in degrees
+    return (a > 0.0) && (b > 0.0) && (tr3 * (dtR * dtR) <= a * a) && (tr3 <= b * b);   // false on NaN
+}
+
 // ------------------------------------------------------------------------------------------ //
 // predict (:144-207).  Unscented transform of (x, P) through the geodetic model.
 //
@@ -76,10 +87,11 @@ STE_DEV bool step_in_fast_range(const double (&x)[4], const double (&P)[10], dou
 template <bool LIB>
 STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, double dt, double dtR,
                              double sog_rate, double cog_rate, const double (&e)[4], const Scratch &sc,
-                             double *sig_prior, double *sig_post, double *stats, int64_t ld) {
+                             double *sig_prior, double *sig_post, double *stats, int64_t ld, const bool small = false) {
     const AngleTrig base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
     double c[4];
-    geodetic_finish<LIB>(x, base, dt, sog_rate, cog_rate, c);
+    if (!LIB && small) geodetic_finish<LIB, true>(x, base, dt, sog_rate, cog_rate, c);
+    else geodetic_finish<LIB>(x, base, dt, sog_rate, cog_rate, c);
     if (sig_prior) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -111,7 +123,8 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
             const AngleTrig off = offset_trig<LIB>(m[1], m[3], m[2], dtR);
             AngleTrig tt[2];
             angle_add_pair(base, off, tt[0], tt[1]);
-            geodetic_finish_n<LIB, 2>(xx, tt, dt, sog_rate, cog_rate, yy);
+            if (!LIB && small) geodetic_finish_n<LIB, 2, true>(xx, tt, dt, sog_rate, cog_rate, yy);
+            else geodetic_finish_n<LIB, 2>(xx, tt, dt, sog_rate, cog_rate, yy);
         }
         if (sig_prior) {
 #pragma unroll
@@ -205,7 +218,8 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
         stash_root(sc, M);
     }
     if (fast) {
-        predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld);
+        predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld,
+                               step_is_small(x, P, dtR));
     } else {
         double xt[4], Pt[10], et[4];
 #pragma unroll

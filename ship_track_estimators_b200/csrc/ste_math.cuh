@@ -410,9 +410,42 @@ STE_DEV void angle_add_pair(const AngleTrig &b, const AngleTrig &o, AngleTrig &p
 
 // Propagate NP sigma points at once: x[i] = [lon, lat, u, cog], t[i] = trig of its (lat, cog, u dt/R).
 // All 2*NP angles (longitude increments, latitudes) go through one lock-step atan2.
-template <bool LIB, int NP>
+//
+// SMALL (the caller has checked step_is_small): every point moves by an angular distance
+// <= 2^-7 rad (50 km) and stays below 81 degrees of latitude.  Then the longitude increment is
+// atan(east/north) with |east/north| <= 2^-4, cos(lat2) = north sqrt(1 + (east/north)^2), and the
+// latitude INCREMENT is asin(up cos(lat1) - cos(lat2) sin(lat1)) with |.| <= 2^-7: three short
+// Maclaurin series replace the square root and the two full-range atan2 (no selects, 40 % fewer
+// FP64 operations per point).
+template <bool LIB, int NP, bool SMALL = false>
 STE_DEV void geodetic_finish_n(const double (&x)[NP][4], const AngleTrig (&t)[NP], double dt, double sog_rate,
                                double cog_rate, double (&y)[NP][4]) {
+    if (!LIB && SMALL) {
+        double east[NP], north[NP], up[NP], q[NP], e[NP], h[NP], dlon[NP], sdel[NP], dlat[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const double sdca = t[i].sd * t[i].ca;
+            east[i] = t[i].sd * t[i].sa;
+            north[i] = fma(t[i].cp, t[i].cd, -t[i].sp * sdca);
+            up[i] = fma(t[i].sp, t[i].cd, t[i].cp * sdca);
+        }
+        fast_div_v<NP>(east, north, q);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) e[i] = q[i] * q[i];
+        small_hypot_scale_v<NP>(north, e, h);      // cos(lat2)
+        small_atan_v<NP>(q, e, dlon);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) sdel[i] = fma(up[i], t[i].cp, -h[i] * t[i].sp);   // sin(lat2 - lat1)
+        small_asin_v<NP>(sdel, dlat);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            y[i][0] = fma(x[i][0], kDegToRad, dlon[i]) * kRadToDeg;
+            y[i][1] = fma(dlat[i], kRadToDeg, x[i][1]);
+            y[i][2] = fma(sog_rate, dt, x[i][2]);
+            y[i][3] = fma(cog_rate, dt, (x[i][3] * kDegToRad) * kRadToDeg);
+        }
+        return;
+    }
     double ay[2 * NP], ax[2 * NP], ang[2 * NP], h2[NP], h[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -444,14 +477,14 @@ STE_DEV void geodetic_finish_n(const double (&x)[NP][4], const AngleTrig (&t)[NP
     }
 }
 
-template <bool LIB>
+template <bool LIB, bool SMALL = false>
 STE_DEV void geodetic_finish(const double (&x)[4], const AngleTrig &t, double dt, double sog_rate,
                              double cog_rate, double (&y)[4]) {
     double xs[1][4], ys[1][4];
     AngleTrig ts[1] = {t};
 #pragma unroll
     for (int r = 0; r < 4; ++r) xs[0][r] = x[r];
-    geodetic_finish_n<LIB, 1>(xs, ts, dt, sog_rate, cog_rate, ys);
+    geodetic_finish_n<LIB, 1, SMALL>(xs, ts, dt, sog_rate, cog_rate, ys);
 #pragma unroll
     for (int r = 0; r < 4; ++r) y[r] = ys[0][r];
 }

@@ -58,3 +58,17 @@ extern "C" int emul_fused(const SteProblem *pa, const SteInputs *ia, SteOutputs 
     }
     return 0;
 }
+
+// geodetic step of n states through the generic branch-free tier and the small-displacement tier
+extern "C" void emul_geodetic_tiers(int n, const double *x, const double *dt, const double *sr, const double *cr,
+                                    double *y_generic, double *y_small) {
+    for (int i = 0; i < n; ++i) {
+        double xi[4], a[4], b[4];
+        for (int r = 0; r < 4; ++r) xi[r] = x[i * 4 + r];
+        const double dtR = dt[i] / kEarthRadiusKm;
+        const AngleTrig t = angle_trig<false>(xi[1], xi[3], xi[2], dtR);
+        geodetic_finish<false, false>(xi, t, dt[i], sr[i], cr[i], a);
+        geodetic_finish<false, true>(xi, t, dt[i], sr[i], cr[i], b);
+        for (int r = 0; r < 4; ++r) { y_generic[i * 4 + r] = a[r]; y_small[i * 4 + r] = b[r]; }
+    }
+}
