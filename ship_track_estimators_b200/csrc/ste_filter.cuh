@@ -84,25 +84,12 @@ STE_DEV bool step_is_small(const double (&x)[4], const double (&P)[10], double d
 // with e the additive noise the reference adds to the mean BEFORE forming deviations (:198-205).
 // This needs no storage for the 9 propagated points.  The root M must already be in scratch.
 // ------------------------------------------------------------------------------------------ //
-template <bool LIB>
-STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, double dt, double dtR,
-                             double sog_rate, double cog_rate, const double (&e)[4], const Scratch &sc,
-                             double *sig_prior, double *sig_post, double *stats, int64_t ld, const bool small = false) {
-    const AngleTrig base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
-    double c[4];
-    if (!LIB && small) geodetic_finish<LIB, true>(x, base, dt, sog_rate, cog_rate, c);
-    else geodetic_finish<LIB>(x, base, dt, sog_rate, cog_rate, c);
-    if (sig_prior) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            sig_prior[(r * 9) * ld] = x[r];
-            sig_post[(r * 9) * ld] = c[r];
-        }
-    }
-    double s1[4] = {0.0, 0.0, 0.0, 0.0};
-    double s2[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) s2[k] = 0.0;
+// The rolled loop over the four root columns, one instance per tier of the geodetic step (SMALL:
+// see step_is_small) so that the hot tier is straight-line code in the instruction stream.
+template <bool LIB, bool SMALL>
+STE_DEV void sigma_pair_loop(const double (&x)[4], const AngleTrig &base, const double (&c)[4], double dt, double dtR,
+                             double sog_rate, double cog_rate, const Scratch &sc, double *sig_prior, double *sig_post,
+                             const bool keep_delta, int64_t ld, double (&s1)[4], double (&s2)[10]) {
 #ifndef STE_PAIR_UNROLL
 #define STE_PAIR_UNROLL 1
 #endif
@@ -123,8 +110,7 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
             const AngleTrig off = offset_trig<LIB>(m[1], m[3], m[2], dtR);
             AngleTrig tt[2];
             angle_add_pair(base, off, tt[0], tt[1]);
-            if (!LIB && small) geodetic_finish_n<LIB, 2, true>(xx, tt, dt, sog_rate, cog_rate, yy);
-            else geodetic_finish_n<LIB, 2>(xx, tt, dt, sog_rate, cog_rate, yy);
+            geodetic_finish_n<LIB, 2, SMALL>(xx, tt, dt, sog_rate, cog_rate, yy);
         }
         if (sig_prior) {
 #pragma unroll
@@ -135,7 +121,7 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
                 sig_post[(r * 9 + 5 + col) * ld] = ym[r];
             }
         }
-        if (stats) {
+        if (keep_delta) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) sc.at(kScratchDeltaFwd + col * 4 + r) = yp[r] - ym[r];
         }
@@ -149,6 +135,39 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int q = r; q < 4; ++q) s2[SYM(r, q)] = fma(yp[r], yp[q], fma(ym[r], ym[q], s2[SYM(r, q)]));
+    }
+}
+
+template <bool LIB>
+STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, double dt, double dtR,
+                             double sog_rate, double cog_rate, const double (&e)[4], const Scratch &sc,
+                             double *sig_prior, double *sig_post, double *stats, int64_t ld, const bool small = false) {
+    const AngleTrig base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
+    double c[4];
+    double s1[4] = {0.0, 0.0, 0.0, 0.0};
+    double s2[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) s2[k] = 0.0;
+    if (!LIB && small) {
+        geodetic_finish<LIB, true>(x, base, dt, sog_rate, cog_rate, c);
+        if (sig_prior) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                sig_prior[(r * 9) * ld] = x[r];
+                sig_post[(r * 9) * ld] = c[r];
+            }
+        }
+        sigma_pair_loop<LIB, true>(x, base, c, dt, dtR, sog_rate, cog_rate, sc, sig_prior, sig_post, stats != nullptr, ld, s1, s2);
+    } else {
+        geodetic_finish<LIB, false>(x, base, dt, sog_rate, cog_rate, c);
+        if (sig_prior) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                sig_prior[(r * 9) * ld] = x[r];
+                sig_post[(r * 9) * ld] = c[r];
+            }
+        }
+        sigma_pair_loop<LIB, false>(x, base, c, dt, dtR, sog_rate, cog_rate, sc, sig_prior, sig_post, stats != nullptr, ld, s1, s2);
     }
     double mu[4], delta[4];
 #pragma unroll
