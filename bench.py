@@ -35,8 +35,8 @@ N_STEPS = 1024
 BYTES_FWD, BYTES_BWD = 200.0, 344.0  # algorithmic bytes per track-step at k = 1
 # FP64 operations the kernels issue per track-step, counted from SASS with ncu (profiles/r01_*):
 # 2 * DFMA + DMUL + DADD, forward (with smoother statistics) and backward (from statistics).
-FLOPS_FWD, FLOPS_BWD = 3545.0, 570.0
-FP64_INSTR_FWD, FP64_INSTR_BWD = 2366.0, 320.0  # DFMA + DMUL + DADD + DSETP warp-instructions per track-step
+FLOPS_FWD, FLOPS_BWD = 2984.0, 570.0
+FP64_INSTR_FWD, FP64_INSTR_BWD = 1961.0, 328.0  # DFMA + DMUL + DADD + DSETP warp-instructions per track-step
 MODEL = dict(H=[1.0, 1.0, 0.0, 0.0], R=[1e-3, 1e-3, 0.0, 0.0], Q=[1e-2, 1e-2, 1e-4, 1e-4], P=[1.0, 1.0, 1.0, 1.0])
 METRIC = "track-steps/sec (UKF+URTSS fp64)"
 UNIT = "track-steps/s"
@@ -344,8 +344,18 @@ def run_gpu_arm(args):
         achieved = dom_bytes * tile_steps / (dom_ms * 1e-3) / 1e9
         step_gbs = (BYTES_FWD + BYTES_BWD) * tile_steps / ((f_ms + b_ms) * 1e-3) / 1e9
         traffic = measured_traffic()
+        if traffic and args.full_cov:
+            traffic = dict(traffic["full_cov"], source=traffic["source"])
         dom_key = "backward" if b_ms >= f_ms else "forward"
         traffic_launch = traffic[dom_key]["dram_bytes_per_track_step"] * tile_steps if traffic else None
+        # both kernels: algorithmic GB/s and, from the committed ncu traffic per track-step, DRAM GB/s
+        per_kernel = {}
+        for key, alg, ms in (("forward", BYTES_FWD, f_ms), ("backward", BYTES_BWD, b_ms)):
+            per_kernel[key] = {"ms": ms, "algorithmic_gbs": alg * tile_steps / (ms * 1e-3) / 1e9,
+                               "frac": alg * tile_steps / (ms * 1e-3) / 1e9 / peak}
+            if traffic:
+                gbs = traffic[key]["dram_bytes_per_track_step"] * tile_steps / (ms * 1e-3) / 1e9
+                per_kernel[key].update(dram_gbs=gbs, dram_frac=gbs / peak)
         # FP64 pipe: probe the DFMA peak on this GPU, compare with the counted instructions
         blocks, threads, iters = 148 * 16, 256, 20000
         sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
@@ -364,7 +374,7 @@ def run_gpu_arm(args):
                 "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_launch, "traffic_source": (traffic or {}).get("source"),
                 "peak_source": peak_src, "algorithmic_bytes_per_track_step": dom_bytes,
-                "kernel_ms": dom_ms, "forward_ms": f_ms, "backward_ms": b_ms,
+                "kernel_ms": dom_ms, "forward_ms": f_ms, "backward_ms": b_ms, "kernels": per_kernel,
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_track_step": BYTES_FWD + BYTES_BWD},
                 "fp64_pipe": {
                     "peak_tflops_measured": fp64_peak,
