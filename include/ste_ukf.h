@@ -177,6 +177,18 @@ int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t
                           const double *lon, const double *lat, const double *dts, const int32_t *n_obs,
                           double *sog, double *cog, double *sog_rate, double *cog_rate, void *stream);
 
+/* performance_metrics.rmse / abs_diff / cum_abs_diff (performance_metrics.py:4-58) of a state
+ * estimate against the observations it assimilated, for T tracks in one launch.  For track t and
+ * observation row r (rows with in->z[r] == NULL are skipped and left untouched), the pairs are
+ * (x, xref) = (mean[s][r][t], z[r][u][t]) for u = 0 with s = 0 (the prior and the first fix) and,
+ * for every later assimilated observation u, the state s that follows its update - the cadence is
+ * the forward pass's (upd_mask / substeps, n_steps, max_obs).  No angle wrapping, as in the reference.
+ * mean [max_steps+1][4][ld] (mean_f or mean_s); outputs, each [4][ld] or NULL: rmse = sqrt(mean of
+ * squares), cum_abs = last element of cum_abs_diff (the sum of |x - xref|), max_abs = max of abs_diff;
+ * abs_diff [max_obs][4][ld] or NULL receives every |x - xref|; n_pairs [T] or NULL the pair count. */
+int ste_track_metrics_f64(const SteProblem *prob, const SteInputs *in, const double *mean, double *rmse,
+                          double *cum_abs, double *max_abs, double *abs_diff, int32_t *n_pairs, void *stream);
+
 /* Test hook: evaluates the library's own fp64 elementary functions (csrc/ste_fastmath.cuh) on n
  * arguments.  kind 0 sincos(a), |a| <= 105615 -> (out0, out1); 1 atan2(a, b); 2 sqrt(a); 3 rsqrt(a); 4 1/a; 5 a/b;
  * 6 atan2(a, b) for b >= 0. */

@@ -300,3 +300,34 @@ def run_track(x0, P0, H, Q, R, dt_array, dts, z, sog_rate, cog_rate, smoother=Tr
             xs, Ps = run_smoother(out["means"], out["covs"], Q, dt_array, len(dts), sog_rate, cog_rate, noise=noise)
             out["means_s"], out["covs_s"] = xs, Ps
     return out
+
+
+# --------------------------------------------------------------------------- #
+# fit metrics (performance_metrics.py:4-58) and their per-track form          #
+# --------------------------------------------------------------------------- #
+def rmse(x, xref):
+    """performance_metrics.py:4-20."""
+    return np.sqrt(np.mean((np.asarray(x) - np.asarray(xref)) ** 2))
+
+
+def cum_abs_diff(x, xref):
+    """performance_metrics.py:23-39."""
+    return np.cumsum(np.abs(np.asarray(x) - np.asarray(xref)))
+
+
+def abs_diff(x, xref):
+    """performance_metrics.py:42-58."""
+    return np.abs(np.asarray(x) - np.asarray(xref))
+
+
+def track_metrics(means, mask, z, rows=(0, 1)):
+    """The three metrics of one track's estimate against its assimilated observations: state 0
+    with fix 0, then the state after each update (kalman_filter.py:76-116 appends the state after
+    the update of a step; ``mask`` is that step's update flag) with the fix it used."""
+    states = [0] + [s + 1 for s in range(len(mask)) if mask[s]]
+    states = states[: z.shape[1]]
+    out = {}
+    for r in rows:
+        x, xref = np.asarray(means)[states, r], z[r, : len(states)]
+        out[r] = dict(rmse=rmse(x, xref), cum_abs=cum_abs_diff(x, xref)[-1], max_abs=abs_diff(x, xref).max(), abs_diff=abs_diff(x, xref))
+    return out

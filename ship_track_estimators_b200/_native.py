@@ -97,6 +97,7 @@ _PROTOTYPES = {
     "ste_sigma_points_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_double, _dptr, _dptr, _dptr, _dptr, C.c_void_p]),
     "ste_geodetic_f64": (C.c_int, [C.c_int32, C.c_int64, _dptr, _dptr, _dptr, _dptr, _dptr, C.c_void_p]),
     "ste_derive_inputs_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [_dptr] * 8 + [C.c_void_p]),
+    "ste_track_metrics_f64": (C.c_int, [C.POINTER(SteProblem), C.POINTER(SteInputs)] + [_dptr] * 6 + [C.c_void_p]),
     "ste_probe_fastmath": (C.c_int, [C.c_int32, C.c_int32, _dptr, _dptr, _dptr, _dptr, C.c_void_p]),
     "ste_probe_fp64_latency": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _dptr, _dptr, C.c_void_p]),
     "ste_probe_fp64_fma": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _dptr, C.c_void_p]),

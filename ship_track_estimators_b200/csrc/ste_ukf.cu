@@ -232,6 +232,56 @@ __global__ void __launch_bounds__(kThreads) geodetic_kernel(int T, int64_t ld, c
 }
 
 // ------------------------------------------------------------------------------------------ //
+// performance_metrics.py:4-58 over whole tiles: residuals between a state estimate and the
+// observations it assimilated, one thread per track walking the forward pass's update cadence.
+// Streaming reads of [step][row][track] planes; HBM-bound (two to four doubles per update).
+// ------------------------------------------------------------------------------------------ //
+struct MetricsArgs {
+    SteProblem prob;
+    SteInputs in;
+    const double *mean;
+    double *rmse, *cum_abs, *max_abs, *abs_diff;
+    int32_t *n_pairs;
+};
+
+__global__ void __launch_bounds__(kThreads) track_metrics_kernel(const __grid_constant__ MetricsArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.prob.n_tracks) return;
+    const int64_t ld = a.prob.ld;
+    const int nt = a.in.n_steps ? min(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
+    const int k_sub = a.prob.substeps > 0 ? a.prob.substeps : 1;
+    double sq[4] = {0.0, 0.0, 0.0, 0.0}, sa[4] = {0.0, 0.0, 0.0, 0.0}, mx[4] = {0.0, 0.0, 0.0, 0.0};
+    int pairs = 0, ui = 0;
+    auto pair = [&](int state, int obs) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (!a.in.z[r]) continue;
+            const double d = fabs(STE_LOAD_STREAM(a.mean + ((int64_t)state * 4 + r) * ld + t) - a.in.z[r][(int64_t)obs * ld + t]);
+            sq[r] = fma(d, d, sq[r]);
+            sa[r] += d;
+            mx[r] = fmax(mx[r], d);   // NaN residuals propagate through sq / sa
+            if (a.abs_diff) STE_STORE_STREAM(a.abs_diff + ((int64_t)obs * 4 + r) * ld + t, d);
+        }
+        ++pairs;
+    };
+    pair(0, 0);
+    // (unrolling this loop so that several steps' loads are in flight was measured slower: 1.19 ms
+    // against 0.71 ms for 113 664 x 512 - consecutive steps are megabytes apart)
+    for (int s = 0; s < nt; ++s) {
+        const bool upd = a.in.upd_mask ? (a.in.upd_mask[(int64_t)s * ld + t] != 0) : ((s + 1) % k_sub == 0);
+        if (upd && ui + 1 < a.prob.max_obs) pair(s + 1, ++ui);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (!a.in.z[r]) continue;
+        if (a.rmse) a.rmse[r * ld + t] = sqrt(sq[r] / (double)pairs);
+        if (a.cum_abs) a.cum_abs[r * ld + t] = sa[r];
+        if (a.max_abs) a.max_abs[r * ld + t] = mx[r];
+    }
+    if (a.n_pairs) a.n_pairs[t] = pairs;
+}
+
+// ------------------------------------------------------------------------------------------ //
 // Derived filter inputs from raw fixes: what ShipTrack computes per
 // ship on the host (ship_track.py:197-304) with the spherical pair haversine_formula / heading
 // (utils.py:75-147), plus the CLI's optional box smoothing of SOG and COG (utils.py:150-172,
@@ -604,6 +654,20 @@ int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t
     derive_inputs_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_tracks, max_obs, ld, smooth_width, lon, lat, dts, n_obs, sog,
                                                                   cog, sog_rate, cog_rate);
     return check_launch("derive_inputs_kernel");
+}
+
+int ste_track_metrics_f64(const SteProblem *prob, const SteInputs *in, const double *mean, double *rmse, double *cum_abs,
+                          double *max_abs, double *abs_diff, int32_t *n_pairs, void *stream) {
+    if (int rc = validate_problem(prob)) return rc;
+    if (!in || !mean) return fail(STE_ERR_INVALID_ARG, "null SteInputs / state array");
+    if (prob->n_tracks == 0) return STE_OK;
+    MetricsArgs a{};
+    a.prob = *prob;
+    a.in = *in;
+    a.mean = mean; a.rmse = rmse; a.cum_abs = cum_abs; a.max_abs = max_abs; a.abs_diff = abs_diff; a.n_pairs = n_pairs;
+    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    track_metrics_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("track_metrics_kernel");
 }
 
 int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b, double *out0, double *out1, void *stream) {

@@ -305,7 +305,24 @@ def synthetic_tracks(n, nobs, **kw):
     return out
 
 
+def metrics_kat():
+    """Known answers of performance_metrics.rmse / cum_abs_diff / abs_diff (reference import)."""
+    from track_estimators.performance_metrics import abs_diff, cum_abs_diff, rmse
+
+    rng = np.random.default_rng(77)
+    out = {}
+    for i, shape in enumerate([(50,), (7, 3), (1,), (1025,)]):
+        x, xref = rng.normal(0, 10, shape), rng.normal(0, 10, shape)
+        out.update({f"x{i}": x, f"xref{i}": xref, f"rmse{i}": np.asarray(rmse(x, xref)),
+                    f"cum{i}": cum_abs_diff(x, xref), f"abs{i}": abs_diff(x, xref)})
+    np.savez_compressed(os.path.join(HERE, "kat_metrics.npz"), n=np.asarray(4), **out)
+    print("kat_metrics done")
+
+
 def main():
+    if sys.argv[1:] == ["metrics"]:
+        return metrics_kat()
+    metrics_kat()
     hist = os.path.join(REF, "data/historical_ships/historical_ship_data.csv")
     modern = os.path.join(REF, "data/modern_ships/WCE5063_subset.csv")
 

@@ -537,3 +537,42 @@ def test_large_tile_against_c_oracle(cuda, native_lib):
     for key, got in (("cov_f", res.cov_f), ("cov_s", res.cov_s)):
         g, r = got.cpu().numpy(), ref[key]
         assert float(np.max(np.max(np.abs(g - r), axis=1) / np.max(np.abs(r), axis=1))) <= TOL, key
+
+
+@pytest.mark.parametrize("k,gating", [(1, False), (2, True)])
+def test_track_metrics_against_oracle(k, gating, cuda, native_lib):
+    """ste_track_metrics_f64: per-track rmse / cum_abs_diff / abs_diff of the filtered and smoothed
+    estimates against the assimilated fixes, on ragged tiles, versus the oracle's restatement of
+    performance_metrics.py applied to the same states."""
+    import torch
+
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.performance_metrics import rmse, track_metrics
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T, nobs = 300, 70
+    syn = make_tracks(T, nobs, seed=91 + k, device="cpu", dts_choices=(1, 2, 3), nobs_min=5, outlier_frac=0.05 if gating else 0.0)
+    R = np.diag([0.05, 0.05, 0.0, 0.0]) if gating else R_POS
+    ukf = BatchedUKF(H_POS, Q_DEF, R, P_DEF, gating=gating)
+    need = ukf.model.rows_needed()
+    batch = TrackBatch.from_synthetic(syn, substeps=k, need_rows=need).to(cuda)
+    res = ukf.run(batch)
+    for which, key in (("filtered", "means"), ("smoothed", "means_s")):
+        got = track_metrics(ukf, batch, res, which=which, keep_abs_diff=True)
+        rows = [r for r in range(4) if need[r]]
+        assert all(bool(torch.isnan(got["rmse"][r]).all()) for r in range(4) if r not in rows)
+        for t in range(0, T, 13):
+            m = int(syn.nobs[t])
+            z = np.stack([syn.lon[:m, t].numpy(), syn.lat[:m, t].numpy(), syn.sog[:m, t].numpy(), syn.cog[:m, t].numpy()])
+            mask = np.tile(np.arange(1, k + 1) == k, m - 1)
+            ref = O.track_metrics(res.track(t)[key], mask, z, rows=rows)
+            assert int(got["n_pairs"][t]) == m
+            for r in rows:
+                assert np.array_equal(got["abs_diff"][:m, r, t].cpu().numpy(), ref[r]["abs_diff"]), (which, t, r)
+                assert float(got["max_abs"][r, t]) == ref[r]["max_abs"]
+                np.testing.assert_allclose(float(got["cum_abs"][r, t]), ref[r]["cum_abs"], rtol=1e-13)
+                np.testing.assert_allclose(float(got["rmse"][r, t]), ref[r]["rmse"], rtol=1e-13)
+    # the array helpers work on device tensors too
+    a, b = res.mean_s[:, 0, 0], res.mean_f[:, 0, 0]
+    np.testing.assert_allclose(float(rmse(a, b)), O.rmse(a.cpu().numpy(), b.cpu().numpy()), rtol=1e-13)

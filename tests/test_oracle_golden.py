@@ -150,3 +150,20 @@ def test_c_oracle_batch_layout_matches_per_track_calls():
         assert np.array_equal(out["mean_s"][:, :, t], one["means_s"]) and np.array_equal(out["cov_f"][:, :, t].reshape(-1, 4, 4), one["covs"])
         ref = O.run_track(z[:, 0], P, H, Q, R, dt[:, t], syn.dts[:, t].numpy(), z, syn.sog_rate[:, t].numpy(), syn.cog_rate[:, t].numpy())
         assert mean_err(one["means_s"], ref["means_s"]) <= 1e-10 and cov_err(one["covs_s"], ref["covs_s"]) <= 1e-10
+
+
+def test_metrics_against_reference_known_answers():
+    """oracle rmse / cum_abs_diff / abs_diff and the package's own array helpers against values the
+    reference's performance_metrics produced (tests/golden/make_golden.py metrics_kat)."""
+    import os
+
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200 import performance_metrics as PM
+
+    kat = np.load(os.path.join(os.path.dirname(__file__), "golden", "kat_metrics.npz"))
+    for i in range(int(kat["n"])):
+        x, xref = kat[f"x{i}"], kat[f"xref{i}"]
+        for mod in (O, PM):
+            assert np.array_equal(mod.abs_diff(x, xref), kat[f"abs{i}"])
+            assert np.array_equal(mod.cum_abs_diff(x, xref), kat[f"cum{i}"])
+            assert float(mod.rmse(x, xref)) == float(kat[f"rmse{i}"])

@@ -50,6 +50,10 @@ print(json.dumps({"tracks": a.tracks, "steps": a.steps, "fwd_ms": f_ms, "bwd_ms"
                   "status_nonzero": int((res.status != 0).sum().item()), "all": [f_all, b_all]}))
 print("sample smoothed", res.mean_s[0, :, 0].tolist(), res.mean_s[-1, :, 0].tolist())
 
+from ship_track_estimators_b200.performance_metrics import track_metrics
+m_ms, _ = timed(lambda: track_metrics(ukf, batch, res, which="smoothed"), a.reps)
+print(json.dumps({"track_metrics_ms": m_ms, "GBs_algorithmic": ts * 32 / m_ms / 1e6}))
+
 if a.fused:
     syn2 = make_tracks(a.tracks, a.steps + 1, seed=2, device="cuda:0")
     batch2 = TrackBatch.from_synthetic(syn2, substeps=1)
