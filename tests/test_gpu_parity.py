@@ -576,3 +576,32 @@ def test_track_metrics_against_oracle(k, gating, cuda, native_lib):
     # the array helpers work on device tensors too
     a, b = res.mean_s[:, 0, 0], res.mean_f[:, 0, 0]
     np.testing.assert_allclose(float(rmse(a, b)), O.rmse(a.cpu().numpy(), b.cpu().numpy()), rtol=1e-13)
+
+
+def test_fleet_ingest_to_smoothed_tracks(cuda, native_lib, tmp_path):
+    """CSV -> ingest.read_csv_fleet -> device-derived inputs -> UKF + URTSS, against the per-ship
+    host route (ShipTrack.read_csv + calculate_*_rate with the spherical pair, TrackBatch.from_tracks)."""
+    from test_host_dropin import _fleet_csv
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.ingest import read_csv_fleet
+    from ship_track_estimators_b200.ship_track import ShipTrack
+    from ship_track_estimators_b200.utils import generate_dts, haversine_formula, heading
+
+    csv = str(tmp_path / "fleet.csv")
+    _fleet_csv(csv, seed=11, n_ships=12, time_ordered=True)
+    kw = dict(id_col="primary.id", lat_col="lat", lon_col="lon")
+    fleet = read_csv_fleet(csv, on_bad_rows="skip", **kw)
+    fleet = fleet.select([i for i in range(fleet.n_tracks) if fleet.n_obs[i] >= 3])
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+    res = ukf.run(fleet.to_batch(device=cuda, substeps=2))
+    sts = []
+    for sid in fleet.ids:
+        st = ShipTrack(calc_distance_func=haversine_formula, calc_heading_func=heading)
+        st.read_csv(csv, ship_id=sid, **kw)
+        st.calculate_sog_rate(); st.calculate_cog_rate()
+        st.get_measurements(include_sog=True, include_cog=True)
+        sts.append(st)
+    ref = ukf.run(TrackBatch.from_tracks(sts, [generate_dts(st.dts, 2) for st in sts], device=cuda))
+    for i in range(fleet.n_tracks):
+        assert_track_close(res.track(i), ref.track(i), tol=1e-9, label=f"ship {fleet.ids[i]}", unc=np.zeros(4))

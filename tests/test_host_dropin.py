@@ -89,3 +89,81 @@ def test_cli_flags_and_settings(tmp_path):
     from ship_track_estimators_b200.cli.json_loader import load_input_json
 
     assert load_input_json(str(p)) == cfg
+
+
+def _fleet_csv(path, seed=3, n_ships=9, string_labels=True, time_ordered=False):
+    """A file shaped like the historical data: ships interleaved, a leading label column that pandas
+    turns into the index, and (optionally) a stray repeated-header row that makes the labels strings."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for s in range(n_ships):
+        n = 1 if s == 0 else int(rng.integers(2, 40))     # one ship with a single fix
+        t = pd.Timestamp("1901-03-01") + pd.to_timedelta(np.cumsum(rng.choice([6, 12, 24, 30], n)), unit="h")
+        lat = rng.uniform(-50, 50) + np.cumsum(rng.normal(0, 0.3, n))      # a slow random walk: a plausible ship
+        lon = rng.uniform(-170, 170) + np.cumsum(rng.normal(0, 0.3, n))
+        for j in range(n):
+            rows.append({"primary.id": f"0{120000 + s * 7}", "yr": t[j].year, "mo": t[j].month, "dy": t[j].day, "hr": t[j].hour,
+                         "lat": round(float(lat[j]), 2), "lon": round(float(lon[j]), 2)})
+    order = rng.permutation(len(rows))
+    labels = rng.permutation(np.arange(90, 90 + len(rows)))        # labels cross a digit boundary: '100' < '99' as strings
+    if time_ordered:    # ships still interleaved, but label order inside a ship follows time (usable tracks)
+        order = np.asarray(sorted(range(len(rows)), key=lambda k: (pd.Timestamp(year=rows[k]["yr"], month=rows[k]["mo"],
+                                                                                  day=rows[k]["dy"], hour=rows[k]["hr"]), k)))
+        labels = np.asarray([f"{k:05d}" for k in range(len(rows))])
+    lines = ["primary.id,yr,mo,dy,hr,lat,lon"]                      # header has one column fewer than the rows -> index
+    for lab, k in zip(labels, order):
+        r = rows[k]
+        lines.append(f"{lab},{r['primary.id']},{r['yr']},{r['mo']},{r['dy']},{r['hr']},{r['lat']},{r['lon']}")
+        if string_labels and lab == labels[5]:
+            lines.append("row,id.tidy,yr,mo,dy,hr,lat,lon")
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return sorted({r["primary.id"] for r in rows})
+
+
+@pytest.mark.parametrize("string_labels", [True, False])
+def test_bulk_csv_ingest_matches_per_ship_reader(tmp_path, string_labels):
+    """ingest.read_csv_fleet (one parse, SoA layout) == ShipTrack.read_csv ship by ship: row selection,
+    sort_index order inside a ship (lexicographic when the labels are strings), gaps in hours,
+    reverse, explicit id lists, stray rows."""
+    from ship_track_estimators_b200.ingest import read_csv_fleet
+
+    csv = str(tmp_path / "fleet.csv")
+    ids = _fleet_csv(csv, string_labels=string_labels)
+    if not string_labels:
+        ids = sorted(str(int(i)) for i in ids)      # an all-numeric id column is parsed as integers (both readers)
+    kw = dict(id_col="primary.id", lat_col="lat", lon_col="lon")
+    if string_labels:
+        with pytest.raises(ValueError, match="unparsable"):
+            read_csv_fleet(csv, **kw)
+    fleet = read_csv_fleet(csv, on_bad_rows="skip", **kw)
+    assert sorted(fleet.ids) == ids and fleet.lon.shape == (int(fleet.n_obs.max()), len(ids))
+    for reverse in (False, True):
+        fl = read_csv_fleet(csv, ship_ids=ids[::-1], reverse=reverse, **kw)
+        assert fl.ids == ids[::-1]
+        for i, sid in enumerate(fl.ids):
+            lat, lon, dts = ShipTrack().read_csv(csv, ship_id=sid, reverse=reverse, **kw)
+            a, b, c = fl.track(i)
+            assert np.array_equal(a, lat) and np.array_equal(b, lon) and np.array_equal(c, dts), (sid, reverse)
+            assert not fl.lon[len(lat):, i].any() and not fl.dts[max(len(lat) - 1, 0):, i].any()   # zero padding
+    with pytest.raises(ValueError, match="No data found"):
+        read_csv_fleet(csv, ship_ids=["nobody"], **kw)
+    two_plus = [i for i in range(fleet.n_tracks) if fleet.n_obs[i] >= 2]
+    assert len(two_plus) == fleet.n_tracks - 1 and fleet.select(two_plus).n_tracks == len(two_plus)
+    with pytest.raises(ValueError, match="at least two fixes"):
+        fleet.to_batch(device="cpu")
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/historical_ships/historical_ship_data.csv"),
+                    reason="reference data only exists in the build container")
+def test_bulk_csv_ingest_on_the_historical_file():
+    from ship_track_estimators_b200.ingest import read_csv_fleet
+
+    csv = "/root/reference/data/historical_ships/historical_ship_data.csv"
+    kw = dict(id_col="primary.id", lat_col="lat", lon_col="lon2")
+    fleet = read_csv_fleet(csv, on_bad_rows="skip", **kw)
+    assert fleet.n_tracks == 116
+    for i in range(0, fleet.n_tracks, 5):
+        lat, lon, dts = ShipTrack().read_csv(csv, ship_id=fleet.ids[i], **kw)
+        a, b, c = fleet.track(i)
+        assert np.array_equal(a, lat) and np.array_equal(b, lon) and np.array_equal(c, dts)
