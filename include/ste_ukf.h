@@ -171,9 +171,18 @@ int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const dou
  * calculate_sog_rate / calculate_cog_rate (ship_track.py:197-304) with the spherical pair
  * haversine_formula / heading (utils.py:75-147) and, when smooth_width > 1, the CLI's box smoothing
  * of SOG and COG (utils.py:150-172, main_cli.py:99-104: np.convolve(y, ones(w)/w, "same")).
+ * geodesy STE_GEODESY_SPHERE: that spherical pair.  STE_GEODESY_WGS84: the reference's DEFAULT pair
+ * geographiclib_distance / geographiclib_heading (utils.py:9-72), i.e. the WGS84 inverse geodesic of
+ * the third-party geographiclib (>= 2.0, not vendored by the reference): restated here with
+ * Vincenty's inverse formulae (same ellipsoid; agrees with the reference's one exact vector,
+ * examples/cli_example/output_01203823_predictions.txt:1, to 8e-13 relative), including the
+ * reference's "same point within 1e-8 degrees -> 0" guard; nearly antipodal legs, which Vincenty's
+ * iteration does not resolve, give NaN.
  * lon, lat [max_obs][ld] degrees; dts [max_obs-1][ld] hours; n_obs [T] fixes per track or NULL;
  * outputs sog (km/h), cog (deg), sog_rate, cog_rate [max_obs][ld] (rows >= n_obs[t] are zeroed). */
-int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t smooth_width,
+#define STE_GEODESY_SPHERE 0
+#define STE_GEODESY_WGS84 1
+int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t smooth_width, int32_t geodesy,
                           const double *lon, const double *lat, const double *dts, const int32_t *n_obs,
                           double *sog, double *cog, double *sog_rate, double *cog_rate, void *stream);
 

@@ -331,3 +331,59 @@ def track_metrics(means, mask, z, rows=(0, 1)):
         x, xref = np.asarray(means)[states, r], z[r, : len(states)]
         out[r] = dict(rmse=rmse(x, xref), cum_abs=cum_abs_diff(x, xref)[-1], max_abs=abs_diff(x, xref).max(), abs_diff=abs_diff(x, xref))
     return out
+
+
+# --------------------------------------------------------------------------- #
+# WGS84 leg (utils.py:9-72).  The reference takes s12 / azi1 from the third-    #
+# party geographiclib (>= 2.0, requirements.txt:4; NOT present in              #
+# /root/reference nor installed here).  Restated with Vincenty's published      #
+# inverse formulae on the same ellipsoid; PINNED ONLY by the reference's one    #
+# exact vector (examples/cli_example/output_01203823_predictions.txt:1) and its #
+# loose unit tests (tests/test_utils.py:36-60, 87-100): parity otherwise        #
+# unpinned.                                                                     #
+# --------------------------------------------------------------------------- #
+def wgs84_inverse(lat1, lon1, lat2, lon2):
+    """(s12 metres, azi1 degrees) of the WGS84 geodesic from point 1 to point 2."""
+    import math
+
+    a, f = 6378137.0, 1.0 / 298.257223563
+    b = (1.0 - f) * a
+    U1, U2 = math.atan((1 - f) * math.tan(math.radians(lat1))), math.atan((1 - f) * math.tan(math.radians(lat2)))
+    L = math.radians(lon2 - lon1)
+    su1, cu1, su2, cu2 = math.sin(U1), math.cos(U1), math.sin(U2), math.cos(U2)
+    lam = L
+    for _ in range(200):
+        sl, cl = math.sin(lam), math.cos(lam)
+        ss = math.hypot(cu2 * sl, cu1 * su2 - su1 * cu2 * cl)
+        cs = su1 * su2 + cu1 * cu2 * cl
+        sig = math.atan2(ss, cs)
+        sa = cu1 * cu2 * sl / ss
+        c2a = 1 - sa * sa
+        c2m = cs - 2 * su1 * su2 / c2a if c2a != 0 else 0.0
+        C = f / 16 * c2a * (4 + f * (4 - 3 * c2a))
+        new = L + (1 - C) * f * sa * (sig + C * ss * (c2m + C * cs * (-1 + 2 * c2m * c2m)))
+        conv = abs(new - lam) < 1e-15
+        lam = new
+        if conv:
+            break
+    sl, cl = math.sin(lam), math.cos(lam)
+    ty, tx = cu2 * sl, cu1 * su2 - su1 * cu2 * cl
+    ss, cs = math.hypot(ty, tx), su1 * su2 + cu1 * cu2 * cl
+    sig = math.atan2(ss, cs)
+    sa = cu1 * cu2 * sl / ss
+    c2a = 1 - sa * sa
+    c2m = cs - 2 * su1 * su2 / c2a if c2a != 0 else 0.0
+    u2 = c2a * (a * a - b * b) / (b * b)
+    A = 1 + u2 / 16384 * (4096 + u2 * (-768 + u2 * (320 - 175 * u2)))
+    B = u2 / 1024 * (256 + u2 * (-128 + u2 * (74 - 47 * u2)))
+    ds = B * ss * (c2m + B / 4 * (cs * (-1 + 2 * c2m * c2m) - B / 6 * c2m * (-3 + 4 * ss * ss) * (-3 + 4 * c2m * c2m)))
+    return b * A * (sig - ds), math.degrees(math.atan2(ty, tx))
+
+
+def wgs84_leg(lon1, lat1, lon2, lat2):
+    """(distance km, heading deg in [0, 360)) as geographiclib_distance / geographiclib_heading
+    return them, with their same-point guard (utils.py:32-38, 64-70)."""
+    if abs(lat1 - lat2) < 1e-8 and abs(lon1 - lon2) < 1e-8:
+        return 0.0, 0.0
+    s12, azi1 = wgs84_inverse(lat1, lon1, lat2, lon2)
+    return s12 * 1e-3, (azi1 + 360) % 360

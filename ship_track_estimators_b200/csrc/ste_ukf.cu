@@ -302,7 +302,55 @@ __device__ __forceinline__ void leg_speed_course(double lon1, double lat1, doubl
     cog = py_mod360(atan2(east, north) * kRadToDeg + 360.0);                       // utils.py:139-145
 }
 
-__global__ void __launch_bounds__(kThreads) derive_inputs_kernel(int T, int max_obs, int64_t ld, int width,
+// WGS84 leg: Vincenty's inverse formulae (Survey Review 23 (176), 1975) for the distance s12 and the
+// initial azimuth the reference takes from geographiclib (utils.py:36-37, 68-70).
+__device__ __forceinline__ void leg_speed_course_wgs84(double lon1, double lat1, double lon2, double lat2, double dt,
+                                                       double &sog, double &cog) {
+    if (fabs(lat1 - lat2) < 1e-8 && fabs(lon1 - lon2) < 1e-8) {   // utils.py:32-33, 64-65
+        sog = 0.0 / dt;
+        cog = 0.0;
+        return;
+    }
+    constexpr double a = 6378137.0, f = 1.0 / 298.257223563, b = (1.0 - f) * a;
+    const double U1 = atan((1.0 - f) * tan(lat1 * kDegToRad)), U2 = atan((1.0 - f) * tan(lat2 * kDegToRad));
+    const double L = (lon2 - lon1) * kDegToRad;
+    const double sU1 = sin(U1), cU1 = cos(U1), sU2 = sin(U2), cU2 = cos(U2);
+    double lam = L, sl, cl, ss, cs, sig, sa, c2a, c2sm;
+    bool converged = false;
+    for (int it = 0; it < 200; ++it) {
+        sl = sin(lam); cl = cos(lam);
+        ss = hypot(cU2 * sl, cU1 * sU2 - sU1 * cU2 * cl);
+        cs = sU1 * sU2 + cU1 * cU2 * cl;
+        sig = atan2(ss, cs);
+        sa = cU1 * cU2 * sl / ss;
+        c2a = 1.0 - sa * sa;
+        c2sm = c2a != 0.0 ? cs - 2.0 * sU1 * sU2 / c2a : 0.0;
+        const double C = f / 16.0 * c2a * (4.0 + f * (4.0 - 3.0 * c2a));
+        const double next = L + (1.0 - C) * f * sa * (sig + C * ss * (c2sm + C * cs * (-1.0 + 2.0 * c2sm * c2sm)));
+        const double d = fabs(next - lam);
+        lam = next;
+        if (d < 1e-15) { converged = true; break; }
+    }
+    sl = sin(lam); cl = cos(lam);
+    const double ty = cU2 * sl, tx = cU1 * sU2 - sU1 * cU2 * cl;
+    ss = hypot(ty, tx);
+    cs = sU1 * sU2 + cU1 * cU2 * cl;
+    sig = atan2(ss, cs);
+    sa = cU1 * cU2 * sl / ss;
+    c2a = 1.0 - sa * sa;
+    c2sm = c2a != 0.0 ? cs - 2.0 * sU1 * sU2 / c2a : 0.0;
+    const double u2 = c2a * (a * a - b * b) / (b * b);
+    const double A = 1.0 + u2 / 16384.0 * (4096.0 + u2 * (-768.0 + u2 * (320.0 - 175.0 * u2)));
+    const double B = u2 / 1024.0 * (256.0 + u2 * (-128.0 + u2 * (74.0 - 47.0 * u2)));
+    const double dsig = B * ss * (c2sm + B / 4.0 * (cs * (-1.0 + 2.0 * c2sm * c2sm)
+                                                   - B / 6.0 * c2sm * (-3.0 + 4.0 * ss * ss) * (-3.0 + 4.0 * c2sm * c2sm)));
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const double s12 = converged ? b * A * (sig - dsig) : nan;
+    sog = (s12 * 1e-3) / dt;                                                   // utils.py:37, ship_track.py:213-217
+    cog = converged ? py_mod360(atan2(ty, tx) * kRadToDeg + 360.0) : nan;       // utils.py:69-70
+}
+
+__global__ void __launch_bounds__(kThreads) derive_inputs_kernel(int T, int max_obs, int64_t ld, int width, int geodesy,
                                                                  const double *lon, const double *lat, const double *dts,
                                                                  const int32_t *n_obs, double *sog, double *cog,
                                                                  double *sog_rate, double *cog_rate) {
@@ -316,7 +364,8 @@ __global__ void __launch_bounds__(kThreads) derive_inputs_kernel(int T, int max_
     // pass 1: one value per leg, the last one repeated ("stationary from the end point onwards")
     double s = 0.0, c = 0.0;
     for (int i = 0; i + 1 < n; ++i) {
-        leg_speed_course(at(lon, i), at(lat, i), at(lon, i + 1), at(lat, i + 1), at(dts, i), s, c);
+        if (geodesy == STE_GEODESY_WGS84) leg_speed_course_wgs84(at(lon, i), at(lat, i), at(lon, i + 1), at(lat, i + 1), at(dts, i), s, c);
+        else leg_speed_course(at(lon, i), at(lat, i), at(lon, i + 1), at(lat, i + 1), at(dts, i), s, c);
         put(raw_s, i, s);
         put(raw_c, i, c);
     }
@@ -643,15 +692,16 @@ int ste_geodetic_f64(int32_t n_tracks, int64_t ld, const double *x_in, const dou
     return check_launch("geodetic_kernel");
 }
 
-int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t smooth_width, const double *lon,
+int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t smooth_width, int32_t geodesy, const double *lon,
                           const double *lat, const double *dts, const int32_t *n_obs, double *sog, double *cog,
                           double *sog_rate, double *cog_rate, void *stream) {
     if (n_tracks < 0 || max_obs < 2 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / max_obs / ld");
     if (smooth_width < 0 || smooth_width > 64) return fail(STE_ERR_INVALID_ARG, "smooth_width outside [0, 64]");
+    if (geodesy != STE_GEODESY_SPHERE && geodesy != STE_GEODESY_WGS84) return fail(STE_ERR_INVALID_ARG, "unknown geodesy");
     if (!lon || !lat || !dts || !sog || !cog || !sog_rate || !cog_rate) return fail(STE_ERR_INVALID_ARG, "missing array");
     if (n_tracks == 0) return STE_OK;
     const dim3 grid((n_tracks + kThreads - 1) / kThreads), block(kThreads);
-    derive_inputs_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_tracks, max_obs, ld, smooth_width, lon, lat, dts, n_obs, sog,
+    derive_inputs_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_tracks, max_obs, ld, smooth_width, geodesy, lon, lat, dts, n_obs, sog,
                                                                   cog, sog_rate, cog_rate);
     return check_launch("derive_inputs_kernel");
 }

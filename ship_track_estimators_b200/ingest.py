@@ -43,7 +43,8 @@ class FleetFixes:
         return FleetFixes([self.ids[i] for i in keep], self.lon[:n, keep].copy(), self.lat[:n, keep].copy(),
                           self.dts[: max(n - 1, 0), keep].copy(), self.n_obs[keep].copy())
 
-    def to_batch(self, device="cuda", substeps: int = 1, smooth_width: int = 0, need_rows=(True, True, False, False)):
+    def to_batch(self, device="cuda", substeps: int = 1, smooth_width: int = 0, need_rows=(True, True, False, False),
+                 geodesy: str = "sphere"):
         """Upload the fixes and build the filter inputs on the device (ships need >= 2 fixes)."""
         from .derive import batch_from_fixes
 
@@ -51,7 +52,7 @@ class FleetFixes:
             raise ValueError("every ship needs at least two fixes; drop the others with select()")
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)   # noqa: E731
         return batch_from_fixes(up(self.lon), up(self.lat), up(self.dts), up(self.n_obs), substeps=substeps,
-                                smooth_width=smooth_width, need_rows=need_rows)
+                                smooth_width=smooth_width, need_rows=need_rows, geodesy=geodesy)
 
 
 def read_csv_fleet(csv_file: str, id_col: str = "id", lat_col: str = "lat", lon_col: str = "lon",

