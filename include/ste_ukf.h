@@ -47,6 +47,10 @@ extern "C" {
 #define STE_FLAG_FORCE_GENERIC 0x2u /* never take the position-only (H = diag(1,1,0,0)) fast path */
 #define STE_FLAG_PACKED_COV 0x4u  /* cov_f / cov_s hold the 10 unique entries per state, planes in  */
                                   /* the order 00 01 02 03 11 12 13 22 23 33, instead of 16         */
+#define STE_FLAG_LONG_STEPS 0x8u  /* never take the small-displacement tier of the geodetic step     */
+                                  /* (<= 50 km per predict below 80 deg latitude, decided per step   */
+                                  /* and track): for tiles mixing short and long steps, where the    */
+                                  /* lanes of a warp would otherwise split between the two tiers     */
 
 /* per-track status bits (SteOutputs.status) */
 #define STE_STATUS_NONFINITE 0x1     /* a state or covariance entry became NaN/Inf                  */

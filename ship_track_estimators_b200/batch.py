@@ -353,7 +353,7 @@ class BatchedUKF:
     """
 
     def __init__(self, H, Q=None, R=None, P=None, *, gating=False, gate_chi=50.0, gate_max_iter=100, force_generic=False,
-                 packed_cov=False):
+                 packed_cov=False, long_steps=False):
         if H is None:
             raise ValueError("Set proper system dynamics.")  # reference unscented.py:52-53
         eye = np.eye(4)
@@ -365,6 +365,11 @@ class BatchedUKF:
         # store the 10 unique covariance entries per state instead of the full 4x4 (30 % less state
         # traffic, memory and PCIe volume; TrackResults.track() expands them back)
         self.packed_cov = bool(packed_cov)
+        # The geodetic step has a cheaper tier for displacements <= 50 km per predict, chosen per
+        # step and track.  A tile that MIXES such steps with longer ones (sparse historical fixes
+        # beside dense ones) makes the lanes of a warp run both tiers; long_steps=True keeps every
+        # step on the full-range tier instead.  Results agree to 1 ulp either way.
+        self.long_steps = bool(long_steps)
 
     # ------------------------------------------------------------------ #
     def _problem(self, b: TrackBatch) -> nat.SteProblem:
@@ -373,7 +378,7 @@ class BatchedUKF:
         p.n_tracks, p.max_steps, p.max_obs = b.n_tracks, b.max_steps, b.max_obs
         p.substeps, p.rate_repeat = int(b.substeps), int(b.rate_repeat_all)
         p.flags = ((nat.STE_FLAG_GATING if m.gating else 0) | (nat.STE_FLAG_FORCE_GENERIC if m.force_generic else 0)
-                   | (nat.STE_FLAG_PACKED_COV if self.packed_cov else 0))
+                   | (nat.STE_FLAG_PACKED_COV if self.packed_cov else 0) | (nat.STE_FLAG_LONG_STEPS if self.long_steps else 0))
         p.gate_max_iter, p.gate_chi = int(m.gate_max_iter), float(m.gate_chi)
         p.ld = b.n_tracks
         for name, M in (("H", m.H), ("Q", m.Q), ("R", m.R), ("P0", m.P0)):

@@ -228,17 +228,17 @@ STE_COLD void predict_moments_cold(double *x_io, double *P_out, const double *Q,
 STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, double dt,
                          double sog_rate, double cog_rate, const double (&e)[4],
                          int &status, const Scratch &sc, double *sig_prior, double *sig_post, double *stats,
-                         int64_t ld) {
+                         int64_t ld, const bool every_step_updates = false, const bool allow_small = true) {
     const double dtR = dt * (1.0 / kEarthRadiusKm);
     const bool fast = step_in_fast_range(x, P, dtR);
     {
         double M[10];
-        if (sqrt_psd4(P, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
+        if (sqrt_psd4(P, kSigmaScale, M, every_step_updates)) status |= STE_STATUS_INDEFINITE;
         stash_root(sc, M);
     }
     if (fast) {
         predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld,
-                               step_is_small(x, P, dtR));
+                               allow_small && step_is_small(x, P, dtR));
     } else {
         double xt[4], Pt[10], et[4];
 #pragma unroll

@@ -179,33 +179,63 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 // (scipy returns a complex root there and numpy's float assignment drops the imaginary part,
 // unscented.py:104-105).  Returns true if a negative eigenvalue was clamped.
 //
-// Hot path: covariances of a running filter are strongly graded and nearly diagonal; measured on
-// the benchmark tracks the relative off-diagonals fall from ~2e-2 to ~2e-6 after one cyclic sweep
-// and to rounding level (5e-17) after two.  So two sweeps run unconditionally (no convergence
-// tests in between) and one test afterwards sends anything unusual - slow convergence, a singular
-// or an indefinite matrix - to the out-of-line finish.
-STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
+// Covariances of a running filter are strongly graded and nearly diagonal, and cyclic Jacobi
+// converges faster than quadratically on them.  Two finishes follow the sweeps:
+//  * diagonal: after two sweeps the off-diagonals are at rounding level (eps <= 1e-15, with
+//    eps = max |a_pq| / sqrt(a_pp a_qq)) and M = V sqrt(D) V^T;
+//  * series: the root of an ALMOST diagonal matrix D + E by its perturbation series, which has no
+//    small denominators (sums of root eigenvalues, never gaps):
+//        sqrt(D + E) = sqrt(D) + X1 + X2 + O(eps^3),   X1_ij = E_ij / (s_i + s_j),
+//        X2_ij = -(X1 X1)_ij / (s_i + s_j),             s = sqrt(diag D),
+//    and M = V (sqrt(D) + X1 + X2) V^T; used for eps <= 1e-4, where the neglected term is below
+//    1e-12 of the smaller root eigenvalue (measured on filter covariances: 4e-14).
+// `expect_diagonal` (uniform over a launch) picks the schedule.  When every predict follows an
+// update (no sub-steps) the filtered covariance is so close to diagonal that ONE sweep leaves
+// eps at a median of 2.5e-6, 99.95 % below 1e-4 (benchmark tracks): one sweep + series, a second
+// sweep only for the rare lane above the threshold (-150 FP64 operations per step).  With
+// sub-steps or irregular updates about half of the steps are above 1e-4 after one sweep, every
+// warp would run both sweeps AND the longer finish, so the schedule stays two unconditional sweeps
+// + diagonal finish.
+// Anything else - singular, indefinite, slowly converging - goes to the out-of-line finish.
+constexpr double kSqrtSeriesEps2 = 1e-8;     // eps^2 limit of the series finish
+constexpr double kSqrtDiagonalEps2 = 1e-30;  // eps^2 limit of the diagonal finish
+
+STE_DEV bool jacobi_off_within(const double (&a)[10], double eps2) {
+    const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
+    const double wmax = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
+    const double wmin = fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
+    bool ok = wmin > 1e-12 * wmax;   // false on NaN
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = p + 1; q < 4; ++q) ok &= (a[SYM(p, q)] * a[SYM(p, q)] <= eps2 * (w[p] * w[q]));
+    return ok;
+}
+
+STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], const bool expect_diagonal = false) {
     double a[10], V[16];
 #pragma unroll
     for (int i = 0; i < 10; ++i) a[i] = A[i] * scale;
 #pragma unroll
     for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-#ifndef STE_SWEEP_UNROLL
-#define STE_SWEEP_UNROLL 1
-#endif
-    STE_UNROLL(STE_SWEEP_UNROLL)
+    bool series_ok = false;
+#pragma unroll 1
     for (int sweep = 0; sweep < 2; ++sweep) {
         jacobi_sweep(a, V);
+        if (expect_diagonal && (series_ok = jacobi_off_within(a, kSqrtSeriesEps2))) break;
     }
-    const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
-    const double wmax = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
-    const double wmin = fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
-    bool done = wmin > 1e-12 * wmax;   // false on NaN
+    if (!expect_diagonal) {
+        if (jacobi_off_within(a, kSqrtDiagonalEps2)) {
+            double f[4];
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int q = p + 1; q < 4; ++q) done &= (a[SYM(p, q)] * a[SYM(p, q)] <= 1e-30 * (w[p] * w[q]));
-    if (!done) {
+            for (int k = 0; k < 4; ++k) f[k] = fast_sqrt(a[SYM(k, k)]);
+            sym_from_eig(V, f, M);
+            return false;
+        }
+        // (sending what two sweeps left between 1e-15 and 1e-4 through the series instead of the
+        // out-of-line finish was measured slower on ragged tiles: a third inline finish in mixed warps)
+    }
+    if (!series_ok) {
         double Mt[10];
         const bool clamped = sqrt_psd4_cold(A[0] * scale, A[1] * scale, A[2] * scale, A[3] * scale, A[4] * scale, A[5] * scale,
                                             A[6] * scale, A[7] * scale, A[8] * scale, A[9] * scale, Mt);
@@ -213,10 +243,77 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10]) {
         for (int i = 0; i < 10; ++i) M[i] = Mt[i];
         return clamped;
     }
-    double f[4];
+    // s_i = sqrt(d_i) and 1 / s_i from one reciprocal square root each
+    double w[4], rs[4], sd[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) f[k] = fast_sqrt(w[k]);
-    sym_from_eig(V, f, M);
+    for (int k = 0; k < 4; ++k) w[k] = a[SYM(k, k)];
+    fast_rsqrt_v<4>(w, rs);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double s0 = w[k] * rs[k];
+        sd[k] = fma(fma(-s0, s0, w[k]), 0.5 * rs[k], s0);   // one Newton correction: correctly rounded root (as fast_sqrt)
+    }
+    // pair sums and their reciprocals, pairs in SYM order: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    double ssum[6], rsum[6], X[10], G[10];
+    {
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) ssum[k++] = sd[p] + sd[q];
+    }
+    fast_rcp_v<6>(ssum, rsum);
+    {
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) X[SYM(p, q)] = a[SYM(p, q)] * rsum[k++];   // X1 (zero diagonal)
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) X[SYM(p, p)] = 0.0;
+    // G = X1 X1 (symmetric)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = p; q < 4; ++q) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k != p && k != q) acc = fma(X[SYM(p, k)], X[SYM(k, q)], acc);
+            G[SYM(p, q)] = acc;
+        }
+    // S = sqrt(D) + X1 + X2
+    double S[10];
+    {
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) S[SYM(p, q)] = fma(-G[SYM(p, q)], rsum[k++], X[SYM(p, q)]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) S[SYM(p, p)] = fma(-G[SYM(p, p)], 0.5 * rs[p], sd[p]);
+    // M = V S V^T
+    double T[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double acc = V[i * 4 + 0] * S[SYM(0, j)];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) acc = fma(V[i * 4 + k], S[SYM(k, j)], acc);
+            T[i * 4 + j] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) {
+            double acc = T[i * 4 + 0] * V[j * 4 + 0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) acc = fma(T[i * 4 + k], V[j * 4 + k], acc);
+            M[SYM(i, j)] = acc;
+        }
     return false;
 }
 
@@ -420,7 +517,7 @@ STE_DEV void angle_add_pair(const AngleTrig &b, const AngleTrig &o, AngleTrig &p
 template <bool LIB, int NP, bool SMALL = false>
 STE_DEV void geodetic_finish_n(const double (&x)[NP][4], const AngleTrig (&t)[NP], double dt, double sog_rate,
                                double cog_rate, double (&y)[NP][4]) {
-    if (!LIB && SMALL) {
+    if constexpr (!LIB && SMALL) {
         double east[NP], north[NP], up[NP], q[NP], e[NP], h[NP], dlon[NP], sdel[NP], dlat[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -444,36 +541,36 @@ STE_DEV void geodetic_finish_n(const double (&x)[NP][4], const AngleTrig (&t)[NP
             y[i][2] = fma(sog_rate, dt, x[i][2]);
             y[i][3] = fma(cog_rate, dt, (x[i][3] * kDegToRad) * kRadToDeg);
         }
-        return;
-    }
-    double ay[2 * NP], ax[2 * NP], ang[2 * NP], h2[NP], h[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const double east = t[i].sd * t[i].sa;
-        const double sdca = t[i].sd * t[i].ca;
-        const double north = fma(t[i].cp, t[i].cd, -t[i].sp * sdca);
-        ay[i] = east;
-        ax[i] = north;
-        ay[NP + i] = fma(t[i].sp, t[i].cd, t[i].cp * sdca);   // up
-        h2[i] = fma(east, east, north * north);
-    }
-    if (LIB) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) ax[NP + i] = sqrt(h2[i]);
-#pragma unroll
-        for (int i = 0; i < 2 * NP; ++i) ang[i] = atan2(ay[i], ax[i]);
     } else {
-        fast_sqrt_v<NP>(h2, h);
+        double ay[2 * NP], ax[2 * NP], ang[2 * NP], h2[NP], h[NP];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) ax[NP + i] = h[i];
-        fast_atan2_v<2 * NP>(ay, ax, ang);
-    }
+        for (int i = 0; i < NP; ++i) {
+            const double east = t[i].sd * t[i].sa;
+            const double sdca = t[i].sd * t[i].ca;
+            const double north = fma(t[i].cp, t[i].cd, -t[i].sp * sdca);
+            ay[i] = east;
+            ax[i] = north;
+            ay[NP + i] = fma(t[i].sp, t[i].cd, t[i].cp * sdca);   // up
+            h2[i] = fma(east, east, north * north);
+        }
+        if (LIB) {
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        y[i][0] = fma(x[i][0], kDegToRad, ang[i]) * kRadToDeg;
-        y[i][1] = ang[NP + i] * kRadToDeg;
-        y[i][2] = fma(sog_rate, dt, x[i][2]);
-        y[i][3] = fma(cog_rate, dt, (x[i][3] * kDegToRad) * kRadToDeg);
+            for (int i = 0; i < NP; ++i) ax[NP + i] = sqrt(h2[i]);
+#pragma unroll
+            for (int i = 0; i < 2 * NP; ++i) ang[i] = atan2(ay[i], ax[i]);
+        } else {
+            fast_sqrt_v<NP>(h2, h);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) ax[NP + i] = h[i];
+            fast_atan2_v<2 * NP>(ay, ax, ang);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            y[i][0] = fma(x[i][0], kDegToRad, ang[i]) * kRadToDeg;
+            y[i][1] = ang[NP + i] * kRadToDeg;
+            y[i][2] = fma(sog_rate, dt, x[i][2]);
+            y[i][3] = fma(cog_rate, dt, (x[i][3] * kDegToRad) * kRadToDeg);
+        }
     }
 }
 

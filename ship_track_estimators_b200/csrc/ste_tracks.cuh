@@ -173,18 +173,20 @@ struct ForwardTrack {
     }
 
     STE_DEV void park() const {
-        if (!PARK) return;
+        if constexpr (PARK) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) sc.at(kScratchRoot + r) = x[r];
+            for (int r = 0; r < 4; ++r) sc.at(kScratchRoot + r) = x[r];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) sc.at(kScratchRoot + 4 + k) = P[k];
+            for (int k = 0; k < 10; ++k) sc.at(kScratchRoot + 4 + k) = P[k];
+        }
     }
     STE_DEV void unpark() {
-        if (!PARK) return;
+        if constexpr (PARK) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) x[r] = sc.at(kScratchRoot + r);
+            for (int r = 0; r < 4; ++r) x[r] = sc.at(kScratchRoot + r);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) P[k] = sc.at(kScratchRoot + 4 + k);
+            for (int k = 0; k < 10; ++k) P[k] = sc.at(kScratchRoot + 4 + k);
+        }
     }
 
     STE_DEV void step(int s) {
@@ -211,7 +213,9 @@ struct ForwardTrack {
             for (int r = 0; r < 4; ++r)
                 e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
-        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld);
+        // launch-uniform: with an update after every predict the covariance is nearly diagonal (sqrt_psd4)
+        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld, !a.in.upd_mask && k_sub == 1,
+                    !(a.prob.flags & STE_FLAG_LONG_STEPS));
         if (advance) ++ui;
         if (upd) assimilate(ui);
         else stage_wait();   // the next step's inputs must have landed before they are read

@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(kThreads) ukf_predict_kernel(const __grid_cons
     int status = 0;
     __shared__ double scratch[kScratchSlots * kThreads];
     ukf_predict(x, P, a.prob.Q, a.dt[t], a.sog_rate[t], a.cog_rate[t], e, status, Scratch{scratch + threadIdx.x, kThreads},
-                a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, nullptr, ld);
+                a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, nullptr, ld, false,
+                !(a.prob.flags & STE_FLAG_LONG_STEPS));
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
     store_xP(a, t, x, P);
     if (a.status) a.status[t] = status;

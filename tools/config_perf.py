@@ -24,13 +24,14 @@ del b, res; torch.cuda.empty_cache()
 # C4: ragged, gated
 T, nmax, nmin = 148 * 128 * 2, 1200, 100
 syn = make_tracks(T, nmax, seed=2, device=dev, nobs_min=nmin, dts_choices=(1, 2, 3, 6, 12, 24), outlier_frac=0.01, smooth_width=2)
-for gating in (False, True):
-    ukf = BatchedUKF(H, Q, np.diag([0.05, 0.05, 0, 0]), P, gating=gating, packed_cov=True)
+for gating, long_steps in ((False, True), (True, True), (False, False)):
+    # gaps of 1-24 h at k = 2 mix <= 50 km and longer steps inside every warp: long_steps=True keeps one geodetic tier
+    ukf = BatchedUKF(H, Q, np.diag([0.05, 0.05, 0, 0]), P, gating=gating, packed_cov=True, long_steps=long_steps)
     b = TrackBatch.from_synthetic(syn, 2, need_rows=ukf.model.rows_needed())
     res = ukf.allocate(b, smoother=True)
     steps = b.track_steps()
     f = timed(lambda: ukf.forward(b, res)); bw = timed(lambda: ukf.backward(b, res))
-    out = {"config": f"C4 shape: ragged {nmin}-{nmax} fixes, k=2, smooth 2, 1% outliers, gating={gating}, URTSS", "tracks": T, "track_steps": steps,
+    out = {"config": f"C4 shape: ragged {nmin}-{nmax} fixes, k=2, smooth 2, 1% outliers, gating={gating}, long_steps={long_steps}, URTSS", "tracks": T, "track_steps": steps,
            "fwd_ms": f, "bwd_ms": bw, "track_steps_per_s": steps / (f + bw) * 1e3, "nonfinite": int((res.status & 1).ne(0).sum()),
            "recompute_flag": int((res.status & 0x100).ne(0).sum())}
     if gating:
