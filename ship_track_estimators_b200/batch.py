@@ -131,6 +131,27 @@ class TrackBatch:
             return int(self.n_steps.sum().item())
         return self.n_tracks * self.max_steps
 
+    def long_step_fraction(self, limit_km: float = 45.0) -> float:
+        """Fraction of the tile's legs (fix to next fix, divided over the sub-steps) longer than
+        ``limit_km`` - a little inside the 50 km range of the geodetic step's small-displacement tier.
+        A value well between 0 and 1 means the lanes of a warp would split between the two tiers:
+        build the filter with ``BatchedUKF(long_steps=True)`` then (see ``STE_FLAG_LONG_STEPS``)."""
+        lon, lat = self.z[0], self.z[1]
+        if lon is None or lat is None or lon.shape[0] < 2:
+            return 0.0
+        rad = torch.pi / 180.0
+        p1, p2, dl = lat[:-1] * rad, lat[1:] * rad, (lon[1:] - lon[:-1]) * rad
+        a = torch.sin((p2 - p1) / 2) ** 2 + torch.cos(p1) * torch.cos(p2) * torch.sin(dl / 2) ** 2
+        km = 2.0 * 6371.0 * torch.asin(torch.sqrt(a.clamp(0.0, 1.0))) / max(int(self.substeps), 1)
+        legs = torch.arange(lon.shape[0] - 1, device=lon.device)[:, None]
+        if self.n_steps is not None:     # legs a track really has: n_steps / substeps (from_tracks stores substeps = 1)
+            n_legs = (self.n_steps.to(torch.int64) // max(int(self.substeps), 1)).clamp(max=lon.shape[0] - 1)
+            valid = legs < n_legs[None, :]
+        else:
+            valid = torch.ones_like(km, dtype=torch.bool)
+        total = int(valid.sum())
+        return float(((km > limit_km) & valid).sum()) / total if total else 0.0
+
     _TENSORS = ("x0", "dt", "sog_rate", "cog_rate", "upd_mask", "n_steps", "rate_repeat", "P0",
                 "noise_pred", "noise_upd", "noise_bwd")
 

@@ -157,3 +157,15 @@ def test_synthetic_generator_definitions():
     # determinism
     again = make_tracks(5, 20, seed=11, nobs_min=8, dts_choices=(1, 2, 6))
     assert np.array_equal(again.lon.numpy(), syn.lon.numpy())
+
+
+def test_long_step_fraction_flags_mixed_tiles():
+    """TrackBatch.long_step_fraction: ~0 for hourly 20 km/h tracks, well inside (0, 1) for gaps of
+    1-24 h (the tiles BatchedUKF(long_steps=True) is meant for)."""
+    from ship_track_estimators_b200.batch import TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    dense = TrackBatch.from_synthetic(make_tracks(64, 60, seed=1, device="cpu"), 1)
+    mixed = TrackBatch.from_synthetic(make_tracks(64, 120, seed=2, device="cpu", nobs_min=30, dts_choices=(1, 2, 3, 6, 12, 24)), 2)
+    assert dense.long_step_fraction() < 0.02
+    assert 0.2 < mixed.long_step_fraction() < 0.8
