@@ -10,7 +10,7 @@ from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch, TrackResult
 
 def build():
     so = os.path.join(HERE, "libste_emul.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=fast", "-march=native", "-fPIC", "-shared", "-x", "c++",
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=fast", "-march=native", *os.environ.get("STE_EMUL_FLAGS", "").split(), "-fPIC", "-shared", "-x", "c++",
                            os.path.join(HERE, "emul.cpp"), "-o", so])
     return C.CDLL(so)
 
