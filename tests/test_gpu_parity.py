@@ -647,3 +647,60 @@ def test_fleet_ingest_to_smoothed_tracks(cuda, native_lib, tmp_path):
     ref = ukf.run(TrackBatch.from_tracks(sts, [generate_dts(st.dts, 2) for st in sts], device=cuda))
     for i in range(fleet.n_tracks):
         assert_track_close(res.track(i), ref.track(i), tol=1e-9, label=f"ship {fleet.ids[i]}", unc=np.zeros(4))
+
+
+def test_tape_noise_and_gating_on_4096_tracks_against_c_oracle(cuda, native_lib):
+    """parity in tape mode and gating decisions on >= 4 096 tracks per configuration.
+    (a) 4 096 tracks with process / measurement / smoother noise tapes (unit normals replayed in the
+    reference's draw order), every track against the plain-C oracle; (b) 4 096 ragged tracks with
+    displaced fixes and Mahalanobis gating: iteration counts identical for every update of every track."""
+    import dataclasses
+
+    import torch
+
+    from oracle import ukf_c as OC
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T = 4096
+    # (a) noise tapes
+    nobs = 33
+    syn = make_tracks(T, nobs, seed=101, device="cpu")
+    g = torch.Generator().manual_seed(7)
+    npred, nbwd = (torch.randn(nobs - 1, 4, T, dtype=torch.float64, generator=g) for _ in range(2))
+    nupd = torch.randn(nobs, 4, T, dtype=torch.float64, generator=g)
+    batch = dataclasses.replace(TrackBatch.from_synthetic(syn, substeps=1), noise_pred=npred, noise_upd=nupd, noise_bwd=nbwd).to(cuda)
+    res = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF).run(batch)
+    mf, ms, cs = res.mean_f.cpu().numpy(), res.mean_s.cpu().numpy(), res.cov_s.cpu().numpy()
+    worst = 0.0
+    for t in range(T):
+        z = np.stack([syn.lon[:, t].numpy(), syn.lat[:, t].numpy(), syn.sog[:, t].numpy(), syn.cog[:, t].numpy()])
+        dts = syn.dts[:, t].numpy()
+        ref = OC.run_track(z[:, 0], P_DEF, H_POS, Q_DEF, R_POS, dts, dts, z, syn.sog_rate[:, t].numpy(), syn.cog_rate[:, t].numpy(),
+                           noise=dict(pred=npred[:, :, t].numpy(), upd=nupd[:, :, t].numpy(), bwd=nbwd[:, :, t].numpy()),
+                           mask=np.ones(nobs - 1, dtype=bool))
+        for got, want in ((mf[:, :, t], ref["means"]), (ms[:, :, t], ref["means_s"])):
+            d = got - want
+            d[:, 3] = (d[:, 3] + 180.0) % 360.0 - 180.0
+            worst = max(worst, float(np.max(np.abs(d) / np.maximum(1.0, np.abs(want)))))
+        c = ref["covs_s"].reshape(nobs, 16)
+        worst = max(worst, float(np.max(np.max(np.abs(cs[:, :, t] - c), axis=1) / np.max(np.abs(c), axis=1))))
+    assert worst <= TOL, worst
+    # (b) gating decisions
+    nobs, k = 40, 2
+    syn = make_tracks(T, nobs, seed=102, device="cpu", dts_choices=(1, 2, 3), nobs_min=12, outlier_frac=0.05, smooth_width=2)
+    R = np.diag([0.05, 0.05, 0.0, 0.0])
+    ukf = BatchedUKF(H_POS, Q_DEF, R, P_DEF, gating=True)
+    res = ukf.run(TrackBatch.from_synthetic(syn, substeps=k, need_rows=ukf.model.rows_needed()).to(cuda))
+    gi = res.gate_iters.cpu().numpy()
+    gated = 0
+    for t in range(T):
+        m = int(syn.nobs[t])
+        z = np.stack([syn.lon[:m, t].numpy(), syn.lat[:m, t].numpy(), syn.sog[:m, t].numpy(), syn.cog[:m, t].numpy()])
+        dts = syn.dts[: m - 1, t].numpy()
+        ref = OC.run_track(z[:, 0], P_DEF, H_POS, Q_DEF, R, O.generate_dts(dts, k), dts, z, syn.sog_rate[:m, t].numpy(),
+                           syn.cog_rate[:m, t].numpy(), smoother=False, gating=True, mask=np.tile(np.arange(1, k + 1) == k, m - 1))
+        assert np.array_equal(gi[:m, t], ref["gate_iters"]), f"track {t}"
+        gated += int((ref["gate_iters"] > 0).sum())
+    assert gated > 1000
