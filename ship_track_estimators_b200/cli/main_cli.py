@@ -19,6 +19,7 @@ from ..kalman_filters.unscented import UnscentedKalmanFilter
 from ..ship_track import ShipTrack
 from ..utils import generate_dts, smooth
 from .argument_parser import create_parser
+from .writers import write_track_outputs
 from .json_loader import load_input_json
 
 logger = logging.getLogger(__name__)
@@ -115,12 +116,7 @@ def track_estimator(argv=None):
         predictions_smoothed, estimate_vars_smoothed = ukf.run_rts_smoother(ship_track=ship_track)
 
     logger.info(f"Writing outputs with prefix '{args.output_prefix}'.")
-    stem = f"{args.output_prefix}_{args.ship_id}"
-    np.savetxt(f"{stem}_predictions.txt", np.asarray(predictions))
-    np.savetxt(f"{stem}_variances.txt", np.diagonal(np.asarray(estimate_vars), axis1=1, axis2=2))
-    np.savetxt(f"{stem}_dts.txt", np.asarray(dt_array))
-    np.savetxt(f"original_{args.ship_id}_track.txt", np.array((ship_track.lon, ship_track.lat)).T)
-    if args.apply_rts_smoother:
-        np.savetxt(f"{stem}_predictions_smoothed.txt", np.asarray(predictions_smoothed))
-        np.savetxt(f"{stem}_variances_smoothed.txt", np.diagonal(np.asarray(estimate_vars_smoothed), axis1=1, axis2=2))
+    write_track_outputs(args.output_prefix, args.ship_id, predictions, estimate_vars, dt_array, ship_track.lon, ship_track.lat,
+                        predictions_smoothed if args.apply_rts_smoother else None,
+                        estimate_vars_smoothed if args.apply_rts_smoother else None)
     exit_banner()

@@ -704,3 +704,40 @@ def test_tape_noise_and_gating_on_4096_tracks_against_c_oracle(cuda, native_lib)
         assert np.array_equal(gi[:m, t], ref["gate_iters"]), f"track {t}"
         gated += int((ref["gate_iters"] > 0).sum())
     assert gated > 1000
+
+
+def test_fleet_estimator_writes_the_cli_files(cuda, native_lib, tmp_path, monkeypatch):
+    """cli.writers.estimate_fleet (one parse, device-derived inputs with the CLI's default WGS84 pair and
+    box smoothing, one filter + one smoother launch, the CLI's files per ship) against the per-ship
+    console script run on the same CSV with the noise pinned to zero."""
+    import json
+    import os
+
+    from test_host_dropin import _fleet_csv
+
+    from ship_track_estimators_b200.cli import main_cli
+    from ship_track_estimators_b200.cli.writers import estimate_fleet
+
+    csv = str(tmp_path / "fleet.csv")
+    _fleet_csv(csv, seed=21, n_ships=7, time_ordered=True)
+    settings = {"dim": 4, "H": [1, 1, 0, 0], "R": [0.001, 0.001, 0, 0], "Q": [1e-2, 1e-2, 1e-4, 1e-4], "P": [1.0, 1.0, 1.0, 1.0],
+                "dt": -1, "nsteps": 2, "smooth": 2}
+    (tmp_path / "input.json").write_text(json.dumps(settings))
+    os.makedirs(tmp_path / "fleet")
+    fleet, _ = estimate_fleet(csv, settings, id_col="primary.id", lat_col="lat", lon_col="lon", apply_rts_smoother=True,
+                              directory=str(tmp_path / "fleet"), device=cuda)
+    assert fleet.n_tracks >= 5
+    monkeypatch.setattr(np.random, "normal", lambda loc=0.0, scale=1.0, size=None: np.zeros(size))
+    monkeypatch.chdir(tmp_path)
+    for sid in fleet.ids[:3]:
+        main_cli.track_estimator(["-i", "input.json", "-o", "output", "-t", csv, "-s", sid, "-ic", "primary.id", "-lat", "lat", "-lon", "lon", "-rts"])
+        for name in ("predictions", "variances", "predictions_smoothed", "variances_smoothed", "dts"):
+            one, many = np.loadtxt(tmp_path / f"output_{sid}_{name}.txt"), np.loadtxt(tmp_path / "fleet" / f"output_{sid}_{name}.txt")
+            assert one.shape == many.shape, (sid, name)
+            if name == "dts":
+                assert np.array_equal(one, many)
+            elif name.startswith("predictions"):
+                assert mean_err(many, one) <= 1e-9, (sid, name)
+            else:
+                assert np.max(np.abs(many - one) / np.max(np.abs(one), axis=1, keepdims=True)) <= 1e-9, (sid, name)
+        assert np.array_equal(np.loadtxt(tmp_path / f"original_{sid}_track.txt"), np.loadtxt(tmp_path / "fleet" / f"original_{sid}_track.txt"))
