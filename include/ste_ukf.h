@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define STE_ABI_VERSION 1
+#define STE_ABI_VERSION 2   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
 #define STE_DIM 4
 #define STE_NSIGMA 9
 

@@ -13,7 +13,7 @@ from typing import Optional
 from . import build as _build
 
 # --- mirror of include/ste_ukf.h ------------------------------------------------------------ #
-STE_ABI_VERSION = 1
+STE_ABI_VERSION = 2
 STE_OK, STE_ERR_INVALID_ARG, STE_ERR_CUDA, STE_ERR_UNSUPPORTED = 0, -1, -2, -3
 STE_FLAG_GATING, STE_FLAG_FORCE_GENERIC, STE_FLAG_PACKED_COV, STE_FLAG_LONG_STEPS = 0x1, 0x2, 0x4, 0x8
 STE_STATUS_NONFINITE = 0x1
