@@ -48,7 +48,7 @@ extern "C" {
 #define STE_FLAG_PACKED_COV 0x4u  /* cov_f / cov_s hold the 10 unique entries per state, planes in  */
                                   /* the order 00 01 02 03 11 12 13 22 23 33, instead of 16         */
 #define STE_FLAG_LONG_STEPS 0x8u  /* never take the small-displacement tier of the geodetic step     */
-                                  /* (<= 50 km per predict below 80 deg latitude, decided per step   */
+                                  /* (<= 100 km per predict below 75 deg latitude, decided per step  */
                                   /* and track): for tiles mixing short and long steps, where the    */
                                   /* lanes of a warp would otherwise split between the two tiers     */
 

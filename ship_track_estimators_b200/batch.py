@@ -131,9 +131,9 @@ class TrackBatch:
             return int(self.n_steps.sum().item())
         return self.n_tracks * self.max_steps
 
-    def long_step_fraction(self, limit_km: float = 45.0) -> float:
+    def long_step_fraction(self, limit_km: float = 90.0) -> float:
         """Fraction of the tile's legs (fix to next fix, divided over the sub-steps) longer than
-        ``limit_km`` - a little inside the 50 km range of the geodetic step's small-displacement tier.
+        ``limit_km`` - a little inside the 100 km range of the geodetic step's small-displacement tier.
         A value well between 0 and 1 means the lanes of a warp would split between the two tiers:
         build the filter with ``BatchedUKF(long_steps=True)`` then (see ``STE_FLAG_LONG_STEPS``)."""
         lon, lat = self.z[0], self.z[1]
@@ -386,7 +386,7 @@ class BatchedUKF:
         # store the 10 unique covariance entries per state instead of the full 4x4 (30 % less state
         # traffic, memory and PCIe volume; TrackResults.track() expands them back)
         self.packed_cov = bool(packed_cov)
-        # The geodetic step has a cheaper tier for displacements <= 50 km per predict, chosen per
+        # The geodetic step has a cheaper tier for displacements <= 100 km per predict, chosen per
         # step and track.  A tile that MIXES such steps with longer ones (sparse historical fixes
         # beside dense ones) makes the lanes of a warp run both tiers; long_steps=True keeps every
         # step on the full-range tier instead.  Results agree to 1 ulp either way.

@@ -288,15 +288,15 @@ STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&o
 
 // ---- small-argument inverse trigonometry: Maclaurin series, no reduction, no selects ----------- //
 // Used by the small-displacement tier of the geodetic step (a ship moves a few km per predict):
-//   atan q       for |q| <= 2^-4   (first neglected term q^14/15  < 1e-18 relative)
-//   asin s       for |s| <= 2^-7   (first neglected term 0.03 s^8 < 1e-18 relative)
-//   sqrt(1 + e)  for 0 <= e <= 2^-8 (first neglected term 0.016 e^7 < 1e-18)
+//   atan q       for |q| <= 0.0645  (first neglected term q^14/15   < 2e-18 relative)
+//   asin s       for |s| <= 2^-6    (first neglected term 0.022 s^10 < 2e-20 relative)
+//   sqrt(1 + e)  for 0 <= e <= 0.0042 (first neglected term 0.016 e^7 < 1e-18)
 // The callers establish the ranges once per filter step (step_is_small).
 STE_CONST double kAtanS[6] = {-1.0 / 3.0, 1.0 / 5.0, -1.0 / 7.0, 1.0 / 9.0, -1.0 / 11.0, 1.0 / 13.0};
-STE_CONST double kAsinS[3] = {1.0 / 6.0, 3.0 / 40.0, 15.0 / 336.0};
+STE_CONST double kAsinS[4] = {1.0 / 6.0, 3.0 / 40.0, 15.0 / 336.0, 105.0 / 3456.0};
 STE_CONST double kSqrt1pS[6] = {0.5, -0.125, 0.0625, -5.0 / 128.0, 7.0 / 256.0, -21.0 / 1024.0};
-constexpr double kSmallAtanMax = 0.0625;        // 2^-4
-constexpr double kSmallAsinMax = 0.0078125;     // 2^-7
+constexpr double kSmallAsinMax = 0.015625;      // 2^-6 rad: 99.5 km on the sphere
+constexpr double kSmallLatMaxDeg = 75.0;        // with it |tan(dlon)| <= sin(2^-6) / cos(75.9 deg) / cos(dlon) = 0.0643
 
 template <int N>
 STE_DEV void small_atan_v(const double (&q)[N], const double (&z)[N], double (&out)[N]) {   // z = q*q
@@ -312,7 +312,8 @@ template <int N>
 STE_DEV void small_asin_v(const double (&s)[N], double (&out)[N]) {
     double z[N], p[N];
     STE_LANES z[l] = s[l] * s[l];
-    STE_LANES p[l] = fma(z[l], kAsinS[2], kAsinS[1]);
+    STE_LANES p[l] = fma(z[l], kAsinS[3], kAsinS[2]);
+    STE_LANES p[l] = fma(z[l], p[l], kAsinS[1]);
     STE_LANES p[l] = fma(z[l], p[l], kAsinS[0]);
     STE_LANES out[l] = fma(s[l], z[l] * p[l], s[l]);
 }

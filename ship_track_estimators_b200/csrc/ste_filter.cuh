@@ -64,16 +64,16 @@ STE_DEV bool step_in_fast_range(const double (&x)[4], const double (&P)[10], dou
            (oa < lim * lim) && (od < lim * lim);   // false on NaN
 }
 
-// Small-displacement tier (geodetic_finish_n<.., SMALL>): every sigma point moves at most 2^-7 rad
-// and starts within 80 degrees of latitude.  The root M of 3P is symmetric with M M = 3P, so row r
+// Small-displacement tier (geodetic_finish_n<.., SMALL>): every sigma point moves at most 2^-6 rad
+// and starts within 75 degrees of latitude.  The root M of 3P is symmetric with M M = 3P, so row r
 // of M has norm sqrt(3 P_rr) and every offset of component r is bounded by it: |u_i| <= |u| +
 // sqrt(3 P_22) (times |dt|/R for the distance), |lat_i| <= |lat| + sqrt(3 P_11); squares are
-// compared so that no root is taken.  Then |tan(dlon)| <= sin(2^-7) / cos(80.45 deg) / cos(dlon)
-// = 0.0472 < 2^-4 as the series assume.  (A negative diagonal entry - indefinite P - fails the test.)
+// compared so that no root is taken.  Then |tan(dlon)| <= sin(2^-6) / cos(75.9 deg) / cos(dlon)
+// = 0.0643 as the series assume.  (A negative diagonal entry - indefinite P - fails the test.)
 STE_DEV bool step_is_small(const double (&x)[4], const double (&P)[10], double dtR) {
     const double su2 = 3.0 * P[SYM(2, 2)], sl2 = 3.0 * P[SYM(1, 1)];
     const double a = kSmallAsinMax - fabs(x[2] * dtR);     // room left for the speed offset, in radians
-    const double b = 80.0 - fabs(x[1]);                    // room left for the latitude offset, in degrees
+    const double b = kSmallLatMaxDeg - fabs(x[1]);         // room left for the latitude offset, in degrees
     return (a > 0.0) && (b > 0.0) && (su2 >= 0.0) && (sl2 >= 0.0) && (su2 * (dtR * dtR) <= a * a) && (sl2 <= b * b);   // false on NaN
 }
 

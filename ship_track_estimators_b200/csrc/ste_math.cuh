@@ -509,9 +509,9 @@ STE_DEV void angle_add_pair(const AngleTrig &b, const AngleTrig &o, AngleTrig &p
 // All 2*NP angles (longitude increments, latitudes) go through one lock-step atan2.
 //
 // SMALL (the caller has checked step_is_small): every point moves by an angular distance
-// <= 2^-7 rad (50 km) and stays below 81 degrees of latitude.  Then the longitude increment is
-// atan(east/north) with |east/north| <= 2^-4, cos(lat2) = north sqrt(1 + (east/north)^2), and the
-// latitude INCREMENT is asin(up cos(lat1) - cos(lat2) sin(lat1)) with |.| <= 2^-7: three short
+// <= 2^-6 rad (100 km) and stays below 76 degrees of latitude.  Then the longitude increment is
+// atan(east/north) with |east/north| <= 0.0645, cos(lat2) = north sqrt(1 + (east/north)^2), and the
+// latitude INCREMENT is asin(up cos(lat1) - cos(lat2) sin(lat1)) with |.| <= 2^-6: three short
 // Maclaurin series replace the square root and the two full-range atan2 (no selects, 40 % fewer
 // FP64 operations per point).
 template <bool LIB, int NP, bool SMALL = false>
