@@ -35,8 +35,8 @@ N_STEPS = 1024
 BYTES_FWD, BYTES_BWD = 200.0, 344.0  # algorithmic bytes per track-step at k = 1
 # FP64 operations the kernels issue per track-step, counted from SASS with ncu (profiles/r01_*):
 # 2 * DFMA + DMUL + DADD, forward (with smoother statistics) and backward (from statistics).
-FLOPS_FWD, FLOPS_BWD = 2801.0, 570.0
-FP64_INSTR_FWD, FP64_INSTR_BWD = 1835.0, 328.0  # DFMA + DMUL + DADD + DSETP warp-instructions per track-step
+FLOPS_FWD, FLOPS_BWD = 2754.0, 570.0
+FP64_INSTR_FWD, FP64_INSTR_BWD = 1802.0, 328.0  # DFMA + DMUL + DADD + DSETP warp-instructions per track-step
 MODEL = dict(H=[1.0, 1.0, 0.0, 0.0], R=[1e-3, 1e-3, 0.0, 0.0], Q=[1e-2, 1e-2, 1e-4, 1e-4], P=[1.0, 1.0, 1.0, 1.0])
 METRIC = "track-steps/sec (UKF+URTSS fp64)"
 UNIT = "track-steps/s"
