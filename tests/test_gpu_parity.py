@@ -146,6 +146,38 @@ def test_single_step_predict_update_against_oracle(cuda, native_lib):
         assert 0.0 <= ukf.x[3, 0] < 360.0
 
 
+def test_predict_at_the_edges_of_the_small_displacement_tier(cuda, native_lib):
+    """One predict on either side of the limits that select the geodetic step's small-displacement
+    series (2^-6 rad per step, 75 degrees of latitude, offsets bounded by sqrt(3 P_rr)): both tiers
+    must reproduce the oracle's predict, so the choice is invisible at 1e-12."""
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics
+
+    P = np.diag([2e-3, 3e-3, 0.4, 1.5])
+    P[0, 1] = P[1, 0] = 5e-4
+    P[2, 3] = P[3, 2] = 0.1
+    off_u, off_lat = np.sqrt(3 * P[2, 2]), np.sqrt(3 * P[1, 1])
+    edge_u = 2.0 ** -6 * 6371.0      # km per 1 h step
+    cases = []
+    for du in (-1e-6, 1e-6, -0.5, 0.5):                       # speed just inside / outside, offsets included
+        cases.append((20.0, 40.0, edge_u - off_u + du, 123.0, 1.0))
+        cases.append((-70.0, -10.0, -(edge_u - off_u + du), 300.0, 1.0))
+    for dl in (-1e-9, 1e-9, -0.3, 0.3):                       # latitude just inside / outside
+        cases.append((5.0, 75.0 - off_lat + dl, 30.0, 45.0, 1.0))
+        cases.append((5.0, -(75.0 - off_lat + dl), 30.0, 200.0, 2.5))
+    cases += [(0.0, 0.0, 0.0, 0.0, 1.0), (179.99, 10.0, 45.0, 90.0, 1.0), (10.0, 74.9, 99.0, 0.0, 1.0)]
+    for lon, lat, u, cog, dt in cases:
+        x = np.array([lon, lat, u, cog])
+        ukf = UnscentedKalmanFilter(H=H_POS, Q=Q_DEF, R=R_POS, P=P.copy(), x0=x, non_linear_process=geodetic_dynamics, noise="zero")
+        ukf.predict(dt=dt, c=None, sog_rate=0.01, cog_rate=0.3)
+        xr, Pr, _, X1 = O.predict(x, P, Q_DEF, dt, 0.01, 0.3, O.ZeroNoise())
+        assert mean_err(ukf.x[:, 0][None], xr[None]) <= 1e-12, (lon, lat, u)
+        assert cov_err(ukf.P[None], Pr[None]) <= 1e-10, (lon, lat, u)
+        d = ukf.sigma_points - X1
+        d[0] = (d[0] + 180.0) % 360.0 - 180.0
+        assert np.max(np.abs(d)) <= 1e-11, (lon, lat, u)
+
+
 def test_sigma_points_reference_unit_tests(cuda, native_lib):
     """reference tests/test_unscented_kf.py:24-87 (n = 2) against the CUDA sigma-point kernel."""
     from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter
