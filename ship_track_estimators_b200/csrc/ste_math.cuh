@@ -194,8 +194,8 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 // eps at a median of 2.5e-6, 99.95 % below 1e-4 (benchmark tracks): one sweep + series, a second
 // sweep only for the rare lane above the threshold (-150 FP64 operations per step).  With
 // sub-steps or irregular updates about half of the steps are above 1e-4 after one sweep, every
-// warp would run both sweeps AND the longer finish, so the schedule stays two unconditional sweeps
-// + diagonal finish.
+// warp would run both sweeps AND the longer finish, so the schedule there is sweeps until the
+// off-diagonals are at rounding level (two to four, tested from the second on) + diagonal finish.
 // Anything else - singular, indefinite, slowly converging - goes to the out-of-line finish.
 constexpr double kSqrtSeriesEps2 = 1e-8;     // eps^2 limit of the series finish
 constexpr double kSqrtDiagonalEps2 = 1e-30;  // eps^2 limit of the diagonal finish
@@ -218,22 +218,24 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], con
     for (int i = 0; i < 10; ++i) a[i] = A[i] * scale;
 #pragma unroll
     for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    bool series_ok = false;
+    bool series_ok = false, diagonal = false;
 #pragma unroll 1
-    for (int sweep = 0; sweep < 2; ++sweep) {
+    for (int sweep = 0; sweep < (expect_diagonal ? 2 : 4); ++sweep) {
         jacobi_sweep(a, V);
-        if (expect_diagonal && (series_ok = jacobi_off_within(a, kSqrtSeriesEps2))) break;
-    }
-    if (!expect_diagonal) {
-        if (jacobi_off_within(a, kSqrtDiagonalEps2)) {
-            double f[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) f[k] = fast_sqrt(a[SYM(k, k)]);
-            sym_from_eig(V, f, M);
-            return false;
+        if (expect_diagonal) {
+            if ((series_ok = jacobi_off_within(a, kSqrtSeriesEps2))) break;
+        } else if (sweep >= 1) {
+            // irregular schedules: half of the steps are not at rounding level after two sweeps
+            // (measured on ragged sub-stepped tracks: 50-76 %), nearly all are after three
+            if ((diagonal = jacobi_off_within(a, kSqrtDiagonalEps2))) break;
         }
-        // (sending what two sweeps left between 1e-15 and 1e-4 through the series instead of the
-        // out-of-line finish was measured slower on ragged tiles: a third inline finish in mixed warps)
+    }
+    if (diagonal) {
+        double f[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = fast_sqrt(a[SYM(k, k)]);
+        sym_from_eig(V, f, M);
+        return false;
     }
     if (!series_ok) {
         double Mt[10];
