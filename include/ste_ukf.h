@@ -32,7 +32,9 @@
 extern "C" {
 #endif
 
-#define STE_ABI_VERSION 2   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
+#define STE_ABI_VERSION 3   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
+                            /* 3: smooth_stats holds STE_STATS_PLANES = 19 planes per step (was 30)                                          */
+#define STE_STATS_PLANES 19
 #define STE_DIM 4
 #define STE_NSIGMA 9
 
@@ -118,11 +120,13 @@ typedef struct SteOutputs {
     uint8_t *gate_iters; /* [max_obs][ld] robustification iterations per update, or NULL              */
     double *gate_lambda; /* [max_obs][ld] final lambda factor per update, or NULL                     */
     double *gate_scale;  /* [max_obs][ld] accumulated scale of R (product of lambdas), or NULL        */
-    double *smooth_stats; /* [max_steps][30][ld] or NULL.  Written by the forward pass, read by the   */
-                         /* backward pass: per predict step the noise-free predicted-mean offset (4), */
-                         /* the predicted covariance about the filtered mean (10 unique) and the      */
-                         /* cross covariance (16) that rts_step recomputes from the same sigma points */
-                         /* (unscented.py:299-330).  NULL: the backward pass recomputes them.         */
+    double *smooth_stats; /* [max_steps][STE_STATS_PLANES][ld] or NULL.  Written by the forward pass,  */
+                         /* read by the backward pass: per predict step the noise-free predicted-mean */
+                         /* offset (4), the predicted covariance about the filtered mean (7 entries)  */
+                         /* and the cross covariance (8 entries) that rts_step recomputes from the    */
+                         /* same sigma points (unscented.py:299-330); the entries that follow from    */
+                         /* the filtered covariance (linear speed / course rows) are not stored.      */
+                         /* NULL: the backward pass recomputes them.                                  */
 } SteOutputs;
 
 /* library / device -------------------------------------------------------------------------- */

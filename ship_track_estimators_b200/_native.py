@@ -13,7 +13,7 @@ from typing import Optional
 from . import build as _build
 
 # --- mirror of include/ste_ukf.h ------------------------------------------------------------ #
-STE_ABI_VERSION = 2
+STE_ABI_VERSION = 3
 STE_OK, STE_ERR_INVALID_ARG, STE_ERR_CUDA, STE_ERR_UNSUPPORTED = 0, -1, -2, -3
 STE_FLAG_GATING, STE_FLAG_FORCE_GENERIC, STE_FLAG_PACKED_COV, STE_FLAG_LONG_STEPS = 0x1, 0x2, 0x4, 0x8
 STE_STATUS_NONFINITE = 0x1
@@ -22,7 +22,7 @@ STE_STATUS_GATE_CAP = 0x4
 STE_STATUS_OBS_OVERRUN = 0x8
 STE_STATUS_RANK_DEFICIENT = 0x10
 STE_STATUS_SMOOTH_RECOMPUTE = 0x100
-STATS_PLANES = 30
+STATS_PLANES = 19
 STE_GEODESY_SPHERE, STE_GEODESY_WGS84 = 0, 1
 
 _dptr = C.c_void_p  # device pointers travel as plain integers

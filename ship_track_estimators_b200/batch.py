@@ -300,7 +300,7 @@ class TrackResults:
     gate_iters: Optional[torch.Tensor] = None
     gate_lambda: Optional[torch.Tensor] = None
     gate_scale: Optional[torch.Tensor] = None
-    smooth_stats: Optional[torch.Tensor] = None  # [N][30][T] device-side tape between the two passes (not a result)
+    smooth_stats: Optional[torch.Tensor] = None  # [N][19][T] device-side tape between the two passes (not a result)
     n_steps_host: Optional[np.ndarray] = None
 
     @property

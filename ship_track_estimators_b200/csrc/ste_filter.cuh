@@ -34,11 +34,23 @@ constexpr int kScratchSlotsFwd = 40;
 
 // Smoother statistics ("tape") the forward pass can emit for every predict, so that the backward
 // pass need not regenerate and re-propagate the sigma points of the same filtered state (the
-// reference recomputes them, unscented.py:299-330; they are the same numbers).  Per step, 30 planes:
+// reference recomputes them, unscented.py:299-330; they are the same numbers).  Per step, 19 planes:
 //   [0..3]   delta = sum W_i f(X_i) - x          noise-free predicted mean minus the filtered mean
-//   [4..13]  P_b   = sum W_i d_i d_i^T + Q        about the filtered mean (10 unique entries)
-//   [14..29] D     = sum W_i (X_i - x) f(X_i)^T   cross covariance, row-major
-constexpr int kStatsPlanes = 30;
+//   [4..10]  P_b   = sum W_i d_i d_i^T + Q        about the filtered mean: entries 00 01 02 03 11 12 13
+//   [11..18] D[q][r], q = 0..3, r = 0..1          cross covariance sum W_i (X_i - x) f(X_i)^T, its
+//                                                 longitude and latitude columns (plane 11 + 2 q + r)
+// What is NOT on the tape follows from the filtered covariance P the backward pass reads anyway:
+// speed and course propagate linearly (y_2 = x_2 + sog_rate dt, y_3 = x_3 + cog_rate dt,
+// non_linear_process.py:72-78), so their sigma-point deviations are +-m_c exactly and, with
+// M M = 3 P and 2 W_i = 1/3,
+//   D[q][r]   = 2 W_i sum_c m_c[q] m_c[r] = P[q][r]                       (r = 2, 3)
+//   P_b[q][r] = P[q][r] + Q[q][r] + delta_q delta_r                       (q, r in {2, 3})
+// (the reference forms the same sums numerically and lands within rounding of these values).  The
+// identity needs M M = 3 P, i.e. no clamped negative eigenvalue: a track whose root clamped one
+// (STE_STATUS_INDEFINITE) is flagged STE_STATUS_SMOOTH_RECOMPUTE and smoothed by recomputation.
+constexpr int kStatsPlanes = 19;
+constexpr int kStatsPb = 4;     // 7 planes, SYM() indices 0..6
+constexpr int kStatsD = 11;     // 8 planes
 
 STE_DEV void stash_root(const Scratch &sc, const double (&M)[10]) {
 #pragma unroll
@@ -88,10 +100,18 @@ STE_DEV bool step_is_small(const double (&x)[4], const double (&P)[10], double d
 // ------------------------------------------------------------------------------------------ //
 // The rolled loop over the four root columns, one instance per tier of the geodetic step (SMALL:
 // see step_is_small) so that the hot tier is straight-line code in the instruction stream.
+//
+// Only longitude and latitude are non-linear.  Speed and course of a propagated sigma point are
+// y_2 = x_2 +- m_2 + sog_rate dt and y_3 = x_3 +- m_3 + cog_rate dt, so their deviations from the
+// propagated centre are +-m_c[2], +-m_c[3] and never have to be formed.  The loop therefore only
+// PARKS, per column c, the sums and differences of the mirror pair's longitude / latitude deviations
+//     Sigma_c[r] = (y+[r] - c[r]) + (y-[r] - c[r]),   Delta_c[r] = y+[r] - y-[r]      (r = 0, 1)
+// (4 scratch slots per column); every moment is assembled after the loop from these 16 numbers and
+// the root itself, with no accumulator live across the trigonometry.
 template <bool LIB, bool SMALL>
 STE_DEV void sigma_pair_loop(const double (&x)[4], const AngleTrig &base, const double (&c)[4], double dt, double dtR,
                              double sog_rate, double cog_rate, const Scratch &sc, double *sig_prior, double *sig_post,
-                             const bool keep_delta, int64_t ld, double (&s1)[4], double (&s2)[10]) {
+                             int64_t ld) {
 #ifndef STE_PAIR_UNROLL
 #define STE_PAIR_UNROLL 1
 #endif
@@ -123,33 +143,23 @@ STE_DEV void sigma_pair_loop(const double (&x)[4], const AngleTrig &base, const 
                 sig_post[(r * 9 + 5 + col) * ld] = ym[r];
             }
         }
-        if (keep_delta) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) sc.at(kScratchDeltaFwd + col * 4 + r) = yp[r] - ym[r];
+        for (int r = 0; r < 2; ++r) {
+            sc.at(kScratchDeltaFwd + col * 4 + r) = (yp[r] - c[r]) + (ym[r] - c[r]);
+            sc.at(kScratchDeltaFwd + col * 4 + 2 + r) = yp[r] - ym[r];
         }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            yp[r] -= c[r];
-            ym[r] -= c[r];
-            s1[r] += yp[r] + ym[r];
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int q = r; q < 4; ++q) s2[SYM(r, q)] = fma(yp[r], yp[q], fma(ym[r], ym[q], s2[SYM(r, q)]));
     }
 }
 
+// `clamped`: the root dropped a negative eigenvalue (M M != 3 P); the speed/course block of the
+// predicted covariance is then summed from the root's columns as the reference does.
 template <bool LIB>
 STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, double dt, double dtR,
                              double sog_rate, double cog_rate, const double (&e)[4], const Scratch &sc,
-                             double *sig_prior, double *sig_post, double *stats, int64_t ld, const bool small = false) {
+                             double *sig_prior, double *sig_post, double *stats, int64_t ld, const bool small = false,
+                             const bool clamped = false) {
     const AngleTrig base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
     double c[4];
-    double s1[4] = {0.0, 0.0, 0.0, 0.0};
-    double s2[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) s2[k] = 0.0;
     if (!LIB && small) {
         geodetic_finish<LIB, true>(x, base, dt, sog_rate, cog_rate, c);
         if (sig_prior) {
@@ -159,7 +169,7 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
                 sig_post[(r * 9) * ld] = c[r];
             }
         }
-        sigma_pair_loop<LIB, true>(x, base, c, dt, dtR, sog_rate, cog_rate, sc, sig_prior, sig_post, stats != nullptr, ld, s1, s2);
+        sigma_pair_loop<LIB, true>(x, base, c, dt, dtR, sog_rate, cog_rate, sc, sig_prior, sig_post, ld);
     } else {
         geodetic_finish<LIB, false>(x, base, dt, sog_rate, cog_rate, c);
         if (sig_prior) {
@@ -169,58 +179,103 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
                 sig_post[(r * 9) * ld] = c[r];
             }
         }
-        sigma_pair_loop<LIB, false>(x, base, c, dt, dtR, sog_rate, cog_rate, sc, sig_prior, sig_post, stats != nullptr, ld, s1, s2);
+        sigma_pair_loop<LIB, false>(x, base, c, dt, dtR, sog_rate, cog_rate, sc, sig_prior, sig_post, ld);
     }
-    double mu[4], delta[4];
+    // ---- moments from the parked Sigma_c, Delta_c (r = 0, 1) and the root columns m_c ---- //
+    double sg[4][2], dl[4][2], mc[4][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        mu[r] = kWi * s1[r];
-        delta[r] = (c[r] - x[r]) + mu[r];
-        x[r] = c[r] + (mu[r] + e[r]);
+    for (int col = 0; col < 4; ++col) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            sg[col][r] = sc.at(kScratchDeltaFwd + col * 4 + r);
+            dl[col][r] = sc.at(kScratchDeltaFwd + col * 4 + 2 + r);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mc[col][q] = sc.at(kScratchRoot + col * 4 + q);
     }
+    // mean: mu = Wi sum_i d_i (zero for speed and course), delta = mean - x (noise-free)
+    double mu[2], delta[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) mu[r] = kWi * ((sg[0][r] + sg[1][r]) + (sg[2][r] + sg[3][r]));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) delta[r] = (c[r] - x[r]) + (r < 2 ? mu[r] : 0.0);
+    // G[q][r] = sum_c m_c[q] Delta_c[r]: Wi G is the cross covariance D[q][r] and, for q >= 2, also
+    // the predicted covariance between position row r and speed / course
+    double G[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            double acc = mc[0][q] * dl[0][r];
+#pragma unroll
+            for (int col = 1; col < 4; ++col) acc = fma(mc[col][q], dl[col][r], acc);
+            G[q][r] = kWi * acc;
+        }
+    double cov[10];
+    // position block: sum_i d_i d_i^T = 1/2 sum_c (Sigma_c Sigma_c^T + Delta_c Delta_c^T)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = r; q < 2; ++q) {
+            double acc = sg[0][r] * sg[0][q];
+            acc = fma(dl[0][r], dl[0][q], acc);
+#pragma unroll
+            for (int col = 1; col < 4; ++col) acc = fma(sg[col][r], sg[col][q], fma(dl[col][r], dl[col][q], acc));
+            cov[SYM(r, q)] = fma(0.5 * kWi, acc, fma(-mu[r], mu[q], Q[r * 4 + q]));
+        }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 2; q < 4; ++q) cov[SYM(r, q)] = G[q][r] + Q[r * 4 + q];
+    // speed / course block: 2 Wi sum_c m_c m_c^T = 2 Wi (M M) = P when the root is exact
+    if (!clamped) {
+#pragma unroll
+        for (int r = 2; r < 4; ++r)
+#pragma unroll
+            for (int q = r; q < 4; ++q) cov[SYM(r, q)] = P[SYM(r, q)] + Q[r * 4 + q];
+    } else {
+#pragma unroll
+        for (int r = 2; r < 4; ++r)
+#pragma unroll
+            for (int q = r; q < 4; ++q) {
+                double acc = mc[0][r] * mc[0][q];
+#pragma unroll
+                for (int col = 1; col < 4; ++col) acc = fma(mc[col][r], mc[col][q], acc);
+                cov[SYM(r, q)] = fma(2.0 * kWi, acc, Q[r * 4 + q]);
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = c[r] + ((r < 2 ? mu[r] : 0.0) + e[r]);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int q = r; q < 4; ++q) {
-            const double cov = fma(kWi, s2[SYM(r, q)], fma(-mu[r], mu[q], Q[r * 4 + q]));   // about the mean, + Q
-            P[SYM(r, q)] = fma(e[r], e[q], cov);
-            if (stats) STE_STORE_STREAM(stats + (4 + SYM(r, q)) * ld, fma(delta[r], delta[q], cov));   // about x
+            P[SYM(r, q)] = fma(e[r], e[q], cov[SYM(r, q)]);
+            if (stats && SYM(r, q) < 7) STE_STORE_STREAM(stats + (kStatsPb + SYM(r, q)) * ld, fma(delta[r], delta[q], cov[SYM(r, q)]));   // about x
         }
     if (stats) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) STE_STORE_STREAM(stats + r * ld, delta[r]);
-        // D = Wi sum_c m_c Delta_c^T: the centre point has X_0 - x = 0 and sum W_i (X_i - x) = 0
-        double D[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) D[k] = 0.0;
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int col = 0; col < 4; ++col) {
-            double dl[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) dl[r] = sc.at(kScratchDeltaFwd + col * 4 + r);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double wm = kWi * sc.at(kScratchRoot + col * 4 + q);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) D[q * 4 + r] = fma(wm, dl[r], D[q * 4 + r]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) STE_STORE_STREAM(stats + (14 + k) * ld, D[k]);
+            for (int r = 0; r < 2; ++r) STE_STORE_STREAM(stats + (kStatsD + q * 2 + r) * ld, G[q][r]);
     }
 }
 
 // library-math version of the same step for out-of-range arguments; out of line (never hot)
 STE_COLD void predict_moments_cold(double *x_io, double *P_out, const double *Q, double dt, double dtR, double sog_rate,
                                    double cog_rate, const double *e_in, Scratch sc, double *sig_prior, double *sig_post,
-                                   double *stats, int64_t ld) {
+                                   double *stats, int64_t ld, bool clamped) {
     double x[4], P[10], e[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         x[r] = x_io[r];
         e[r] = e_in[r];
     }
-    predict_moments<true>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) P[k] = P_out[k];
+    predict_moments<true>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld, false, clamped);
 #pragma unroll
     for (int r = 0; r < 4; ++r) x_io[r] = x[r];
 #pragma unroll
@@ -233,14 +288,16 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
                          int64_t ld, const bool every_step_updates = false, const bool allow_small = true) {
     const double dtR = dt * (1.0 / kEarthRadiusKm);
     const bool fast = step_in_fast_range(x, P, dtR);
+    bool clamped;
     {
         double M[10];
-        if (sqrt_psd4(P, kSigmaScale, M, every_step_updates)) status |= STE_STATUS_INDEFINITE;
+        clamped = sqrt_psd4(P, kSigmaScale, M, every_step_updates);
+        if (clamped) status |= STE_STATUS_INDEFINITE;
         stash_root(sc, M);
     }
     if (fast) {
         predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld,
-                               allow_small && step_is_small(x, P, dtR));
+                               allow_small && step_is_small(x, P, dtR), clamped);
     } else {
         double xt[4], Pt[10], et[4];
 #pragma unroll
@@ -248,7 +305,9 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
             xt[r] = x[r];
             et[r] = e[r];
         }
-        predict_moments_cold(xt, Pt, Q, dt, dtR, sog_rate, cog_rate, et, sc, sig_prior, sig_post, stats, ld);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) Pt[k] = P[k];
+        predict_moments_cold(xt, Pt, Q, dt, dtR, sog_rate, cog_rate, et, sc, sig_prior, sig_post, stats, ld, clamped);
 #pragma unroll
         for (int r = 0; r < 4; ++r) x[r] = xt[r];
 #pragma unroll
@@ -671,16 +730,28 @@ STE_DEV void urtss_gain(const double (&xf)[4], const double (&Pf)[10], const dou
 
 // One backward iteration from the statistics the forward pass stored for this step (kStatsPlanes
 // planes at `stats`): no sigma points, no square root - a pseudo-inverse and three small products.
+// The speed / course columns of D and block of P_b come from the filtered covariance (see kStatsPlanes).
 STE_DEV void urtss_step_from_stats(const double (&xf)[4], const double (&Pf)[10], const double *stats, int64_t ld,
-                                   const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status,
+                                   const double *Q, const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status,
                                    const Scratch &sc) {
-    double xb[4], Pb[10], D[16];
+    double dlt[4], xb[4], Pb[10], D[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) xb[r] = STE_LOAD_STREAM(stats + r * ld) + e[r];
+    for (int r = 0; r < 4; ++r) dlt[r] = STE_LOAD_STREAM(stats + r * ld);
 #pragma unroll
-    for (int k = 0; k < 10; ++k) Pb[k] = STE_LOAD_STREAM(stats + (4 + k) * ld);
+    for (int k = 0; k < 7; ++k) Pb[k] = STE_LOAD_STREAM(stats + (kStatsPb + k) * ld);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) D[k] = STE_LOAD_STREAM(stats + (14 + k) * ld);
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) D[q * 4 + r] = STE_LOAD_STREAM(stats + (kStatsD + q * 2 + r) * ld);
+#pragma unroll
+        for (int r = 2; r < 4; ++r) D[q * 4 + r] = Pf[SYM(q, r)];
+    }
+#pragma unroll
+    for (int r = 2; r < 4; ++r)
+#pragma unroll
+        for (int q = r; q < 4; ++q) Pb[SYM(r, q)] = fma(dlt[r], dlt[q], Pf[SYM(r, q)] + Q[r * 4 + q]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xb[r] = dlt[r] + e[r];
     double Pbinv[10];
     if (pinv_spd4(Pb, Pbinv) > 0) status |= STE_STATUS_RANK_DEFICIENT;
     double K[16];

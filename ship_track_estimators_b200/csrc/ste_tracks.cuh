@@ -226,7 +226,8 @@ struct ForwardTrack {
     STE_DEV void end() {
         unpark();
         if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
-        if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;
+        // the tape omits what follows from M M = 3 P: not valid once a root clamped an eigenvalue
+        if (a.out.smooth_stats && (!consistent || (status & STE_STATUS_INDEFINITE))) status |= STE_STATUS_SMOOTH_RECOMPUTE;
         a.out.status[t] = status;
         if (a.out.n_updates) a.out.n_updates[t] = ui + 1;
     }
@@ -321,8 +322,8 @@ struct BackwardTrack {
         if (STATS_ONLY || (use_stats && step > 0)) {
             double Pf[10];
             load_cov(cf, ld, packed, Pf);
-            urtss_step_from_stats(xf, Pf, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, e, xs, Ps,
-                                  status, sc);
+            urtss_step_from_stats(xf, Pf, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, a.prob.Q, e, xs,
+                                  Ps, status, sc);
         } else {
             double s1[4], Pb[10];
             const double dt = a.in.dt[(int64_t)step * ld + t];

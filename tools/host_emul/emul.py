@@ -8,11 +8,26 @@ import numpy as np, torch
 from ship_track_estimators_b200 import _native as nat
 from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch, TrackResults
 
+_EMUL = None
+
+
 def build():
+    """Compile the host build once per process (and only when a source is newer than the library)."""
+    global _EMUL
+    if _EMUL is not None:
+        return _EMUL
     so = os.path.join(HERE, "libste_emul.so")
+    csrc = os.path.join(REPO, "ship_track_estimators_b200", "csrc")
+    deps = [os.path.join(HERE, "emul.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps) or os.environ.get("STE_EMUL_FLAGS"):
+        _compile(so)
+    _EMUL = C.CDLL(so)
+    return _EMUL
+
+
+def _compile(so):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=fast", "-march=native", *os.environ.get("STE_EMUL_FLAGS", "").split(), "-fPIC", "-shared", "-x", "c++",
                            os.path.join(HERE, "emul.cpp"), "-o", so])
-    return C.CDLL(so)
 
 class HostUKF(BatchedUKF):
     """BatchedUKF whose launches go to the host build (CPU tensors)."""
