@@ -16,21 +16,27 @@ struct Model {
     const double *R;   // [16]
 };
 
-// Per-thread scratch slots outside the register file (shared memory on the device, a plain
-// array in the host sandbox).  Slot k of this thread lives at base[k * stride].  It holds the
-// square-root factor so that the sigma-point loop can stay ROLLED (one instance of the
-// trigonometric code in the instruction cache) and index its columns at run time.
-struct Scratch {
-    double *base;
-    int stride;
-    STE_DEV double &at(int slot) const { return base[(long)slot * stride]; }
-};
-constexpr int kScratchRoot = 0;   // 16 slots: M[r][c] at kScratchRoot + c * 4 + r (column-major)
-constexpr int kScratchSlots = 16;          // single-step kernels: the root only
-constexpr int kScratchDeltaFwd = 16;       // forward filter with smoother statistics: Delta_c, 16 slots
-constexpr int kScratchObs = 32;            // 4 slots: the observation staged for this step's update
-constexpr int kScratchIn = 36;             // 3 slots: dt, sog_rate, cog_rate staged for the next step
-constexpr int kScratchSlotsFwd = 40;
+// Per-thread scratch slots (struct Scratch, ste_math.cuh): shared memory on the device.  They hold
+// the square-root factor so that the sigma-point loop can stay ROLLED (one instance of the
+// trigonometric code in the instruction cache) and index its columns at run time, the parked
+// deviations of the sigma pairs, and - while the root is being taken, when those are dead - the
+// rotation parameters of the Jacobi sweeps.  One layout for the forward and the backward pass:
+//   [0, 14)   forward: observation staged for this step's update (4), dt and the two rates staged
+//             for the next step (3); backward: the carried smoothed state xs (4), Ps (10)
+//   [14, 30)  root M, column-major: M[r][c] at kScratchRoot + c * 4 + r
+//   [30, 46)  forward: Sigma_c / Delta_c of the pair loop; backward by recomputation: Delta_c
+//   [14, 50)  rotation parameters during sqrt_psd4 (kSqrtRotSlots = 36)
+constexpr int kScratchObs = 0;             // 4 slots
+constexpr int kScratchIn = 4;              // 3 slots
+constexpr int kScratchXs = 0;              // 4 slots  (backward)
+constexpr int kScratchPs = 4;              // 10 slots (backward)
+constexpr int kScratchRoot = 14;           // 16 slots
+constexpr int kScratchDeltaFwd = 30;       // 16 slots
+constexpr int kScratchDelta = 30;          // 16 slots (backward by recomputation)
+constexpr int kScratchRot = kScratchRoot;  // kSqrtRotSlots slots, live only inside sqrt_psd4
+constexpr int kScratchSlots = kScratchRot + kSqrtRotSlots;   // 50
+constexpr int kScratchSlotsFwd = kScratchSlots;
+constexpr int kScratchSlotsBwd = kScratchSlots;
 
 // Smoother statistics ("tape") the forward pass can emit for every predict, so that the backward
 // pass need not regenerate and re-propagate the sigma points of the same filtered state (the
@@ -285,13 +291,13 @@ STE_COLD void predict_moments_cold(double *x_io, double *P_out, const double *Q,
 STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, double dt,
                          double sog_rate, double cog_rate, const double (&e)[4],
                          int &status, const Scratch &sc, double *sig_prior, double *sig_post, double *stats,
-                         int64_t ld, const bool every_step_updates = false, const bool allow_small = true) {
+                         int64_t ld, const bool allow_small = true) {
     const double dtR = dt * (1.0 / kEarthRadiusKm);
     const bool fast = step_in_fast_range(x, P, dtR);
     bool clamped;
     {
         double M[10];
-        clamped = sqrt_psd4(P, kSigmaScale, M, every_step_updates);
+        clamped = sqrt_psd4(P, kSigmaScale, M, sc, kScratchRot);
         if (clamped) status |= STE_STATUS_INDEFINITE;
         stash_root(sc, M);
     }
@@ -558,10 +564,6 @@ STE_DEV void ukf_update_position(double (&x)[4], double (&P)[10], const Model &m
 // The smoothed state of step+1 (xs, Ps) is only touched in phase 2 and lives in scratch between
 // steps; Pf is re-read by the caller for phase 2 instead of being held across phase 1.
 // ------------------------------------------------------------------------------------------ //
-constexpr int kScratchXs = 16;      // 4 slots
-constexpr int kScratchPs = 20;      // 10 slots
-constexpr int kScratchDelta = 30;   // 16 slots: Delta_c[r] at kScratchDelta + c * 4 + r
-constexpr int kScratchSlotsBwd = 46;
 
 template <bool LIB>
 STE_DEV void urtss_moments_impl(const double (&xf)[4], const double *Q, double dt, double dtR, double sog_rate,
@@ -631,7 +633,7 @@ STE_DEV void urtss_moments(const double (&xf)[4], const double (&Pf)[10], const 
     const bool fast = step_in_fast_range(xf, Pf, dtR);
     {
         double M[10];
-        if (sqrt_psd4(Pf, kSigmaScale, M)) status |= STE_STATUS_INDEFINITE;
+        if (sqrt_psd4(Pf, kSigmaScale, M, sc, kScratchRot)) status |= STE_STATUS_INDEFINITE;
         stash_root(sc, M);
     }
     if (fast) {

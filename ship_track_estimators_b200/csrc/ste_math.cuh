@@ -29,6 +29,14 @@ STE_HD constexpr int SYM(int i, int j) {
     return i <= j ? (i * 4 - (i * (i - 1)) / 2 + (j - i)) : (j * 4 - (j * (j - 1)) / 2 + (i - j));
 }
 
+// Per-thread scratch slots outside the register file (shared memory on the device, a plain
+// array in the host sandbox).  Slot k of this thread lives at base[k * stride].
+struct Scratch {
+    double *base;
+    int stride;
+    STE_DEV double &at(int slot) const { return base[(long)slot * stride]; }
+};
+
 // Python / numpy floored modulo by 360 (result in [0, 360], sign of the divisor).
 STE_DEV double py_mod360(double a) {
     double r = fmod(a, 360.0);
@@ -72,6 +80,44 @@ STE_DEV void jacobi_params(const double (&app)[N], const double (&aqq)[N], const
 }
 
 template <int P_, int Q_>
+STE_DEV void jacobi_apply_a(double (&a)[10], double c, double s, double t) {
+    const double apq = a[SYM(P_, Q_)];
+    a[SYM(P_, P_)] = fma(-t, apq, a[SYM(P_, P_)]);
+    a[SYM(Q_, Q_)] = fma(t, apq, a[SYM(Q_, Q_)]);
+    a[SYM(P_, Q_)] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r != P_ && r != Q_) {
+            const double arp = a[SYM(r, P_)], arq = a[SYM(r, Q_)];
+            a[SYM(r, P_)] = fma(c, arp, -s * arq);
+            a[SYM(r, Q_)] = fma(s, arp, c * arq);
+        }
+    }
+}
+
+// S <- J S J^T for the rotation J that jacobi_apply_a used as a <- J^T a J (undoes the change of
+// basis on a symmetric matrix expressed in the rotated basis).  With d = S_qq - S_pp:
+//   S_pp += h, S_qq -= h, h = s^2 d + 2cs S_pq;   S_pq <- (c^2 - s^2) S_pq + cs d
+template <int P_, int Q_>
+STE_DEV void jacobi_unapply(double (&S)[10], double c, double s) {
+    const double cs = c * s, s2 = s * s;
+    const double w = fma(c, c, -s2), u = cs + cs;
+    const double spq = S[SYM(P_, Q_)], d = S[SYM(Q_, Q_)] - S[SYM(P_, P_)];
+    const double h = fma(s2, d, u * spq);
+    S[SYM(P_, P_)] += h;
+    S[SYM(Q_, Q_)] -= h;
+    S[SYM(P_, Q_)] = fma(w, spq, cs * d);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r != P_ && r != Q_) {
+            const double srp = S[SYM(r, P_)], srq = S[SYM(r, Q_)];
+            S[SYM(r, P_)] = fma(c, srp, s * srq);
+            S[SYM(r, Q_)] = fma(c, srq, -s * srp);
+        }
+    }
+}
+
+template <int P_, int Q_>
 STE_DEV void jacobi_apply(double (&a)[10], double (&V)[16], double c, double s, double t) {
     const double apq = a[SYM(P_, Q_)];
     a[SYM(P_, P_)] = fma(-t, apq, a[SYM(P_, P_)]);
@@ -103,6 +149,39 @@ STE_DEV void jacobi_rotate2(double (&a)[10], double (&V)[16]) {
     jacobi_params<2>(app, aqq, apq, c, s, t);
     jacobi_apply<P1, Q1>(a, V, c[0], s[0], t[0]);
     jacobi_apply<P2, Q2>(a, V, c[1], s[1], t[1]);
+}
+
+// The same pair of rotations without an eigenvector matrix: (c, s) of both go to four scratch
+// slots so that the change of basis can be undone later (jacobi_unrotate2).
+template <int P1, int Q1, int P2, int Q2>
+STE_DEV void jacobi_rotate2_store(double (&a)[10], const Scratch &sc, int slot) {
+    const double app[2] = {a[SYM(P1, P1)], a[SYM(P2, P2)]}, aqq[2] = {a[SYM(Q1, Q1)], a[SYM(Q2, Q2)]},
+                 apq[2] = {a[SYM(P1, Q1)], a[SYM(P2, Q2)]};
+    double c[2], s[2], t[2];
+    jacobi_params<2>(app, aqq, apq, c, s, t);
+    jacobi_apply_a<P1, Q1>(a, c[0], s[0], t[0]);
+    jacobi_apply_a<P2, Q2>(a, c[1], s[1], t[1]);
+    sc.at(slot + 0) = c[0];
+    sc.at(slot + 1) = s[0];
+    sc.at(slot + 2) = c[1];
+    sc.at(slot + 3) = s[1];
+}
+template <int P1, int Q1, int P2, int Q2>
+STE_DEV void jacobi_unrotate2(double (&S)[10], const Scratch &sc, int slot) {
+    const double c0 = sc.at(slot + 0), s0 = sc.at(slot + 1), c1 = sc.at(slot + 2), s1 = sc.at(slot + 3);
+    jacobi_unapply<P1, Q1>(S, c0, s0);   // disjoint index pairs: the two commute
+    jacobi_unapply<P2, Q2>(S, c1, s1);
+}
+constexpr int kSweepSlots = 12;   // scratch slots one sweep's rotation parameters take
+STE_DEV void jacobi_sweep_store(double (&a)[10], const Scratch &sc, int slot) {
+    jacobi_rotate2_store<0, 1, 2, 3>(a, sc, slot);
+    jacobi_rotate2_store<0, 2, 1, 3>(a, sc, slot + 4);
+    jacobi_rotate2_store<0, 3, 1, 2>(a, sc, slot + 8);
+}
+STE_DEV void jacobi_unsweep(double (&S)[10], const Scratch &sc, int slot) {
+    jacobi_unrotate2<0, 3, 1, 2>(S, sc, slot + 8);
+    jacobi_unrotate2<0, 2, 1, 3>(S, sc, slot + 4);
+    jacobi_unrotate2<0, 1, 2, 3>(S, sc, slot);
 }
 
 STE_DEV void jacobi_sweep(double (&a)[10], double (&V)[16]) {
@@ -179,26 +258,24 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 // (scipy returns a complex root there and numpy's float assignment drops the imaginary part,
 // unscented.py:104-105).  Returns true if a negative eigenvalue was clamped.
 //
-// Covariances of a running filter are strongly graded and nearly diagonal, and cyclic Jacobi
-// converges faster than quadratically on them.  Two finishes follow the sweeps:
-//  * diagonal: after two sweeps the off-diagonals are at rounding level (eps <= 1e-15, with
-//    eps = max |a_pq| / sqrt(a_pp a_qq)) and M = V sqrt(D) V^T;
-//  * series: the root of an ALMOST diagonal matrix D + E by its perturbation series, which has no
-//    small denominators (sums of root eigenvalues, never gaps):
-//        sqrt(D + E) = sqrt(D) + X1 + X2 + O(eps^3),   X1_ij = E_ij / (s_i + s_j),
-//        X2_ij = -(X1 X1)_ij / (s_i + s_j),             s = sqrt(diag D),
-//    and M = V (sqrt(D) + X1 + X2) V^T; used for eps <= 1e-4, where the neglected term is below
-//    1e-12 of the smaller root eigenvalue (measured on filter covariances: 4e-14).
-// `expect_diagonal` (uniform over a launch) picks the schedule.  When every predict follows an
-// update (no sub-steps) the filtered covariance is so close to diagonal that ONE sweep leaves
-// eps at a median of 2.5e-6, 99.95 % below 1e-4 (benchmark tracks): one sweep + series, a second
-// sweep only for the rare lane above the threshold (-150 FP64 operations per step).  With
-// sub-steps or irregular updates about half of the steps are above 1e-4 after one sweep, every
-// warp would run both sweeps AND the longer finish, so the schedule there is sweeps until the
-// off-diagonals are at rounding level (two to four, tested from the second on) + diagonal finish.
+// Covariances of a running filter are strongly graded and cyclic Jacobi converges faster than
+// quadratically on them, so the sweeps stop as soon as the matrix is ALMOST diagonal,
+// eps = max |a_pq| / sqrt(a_pp a_qq) <= 1e-4, and the root of D + E is finished by its
+// perturbation series, which has no small denominators (sums of root eigenvalues, never gaps):
+//     sqrt(D + E) = sqrt(D) + X1 + X2 + O(eps^3),   X1_ij = E_ij / (s_i + s_j),
+//     X2_ij = -(X1 X1)_ij / (s_i + s_j),             s = sqrt(diag D);
+// the neglected term is below 1e-12 of the smaller root eigenvalue (measured on filter
+// covariances: 4e-14).  One sweep is enough when every predict follows an update (eps at a median
+// of 2.5e-6 then, 99.95 % below 1e-4 on the benchmark tracks), two or three with sub-steps or
+// irregular updates.  No eigenvector matrix is accumulated: the sweeps leave their rotation
+// parameters (c, s) in scratch (kSweepSlots per sweep, kSqrtRotSlots in all, starting at slot
+// `rot`) and the root S of the rotated matrix is carried back, M = J_1 (... (J_n S J_n^T) ...) J_1^T,
+// rotation by rotation on its 10 unique entries - 114 FP64 operations per sweep instead of 96 for
+// the accumulation plus 104 for V S V^T, and 32 registers fewer across the sweeps.
 // Anything else - singular, indefinite, slowly converging - goes to the out-of-line finish.
 constexpr double kSqrtSeriesEps2 = 1e-8;     // eps^2 limit of the series finish
-constexpr double kSqrtDiagonalEps2 = 1e-30;  // eps^2 limit of the diagonal finish
+constexpr int kSqrtMaxSweeps = 3;
+constexpr int kSqrtRotSlots = kSqrtMaxSweeps * kSweepSlots;
 
 STE_DEV bool jacobi_off_within(const double (&a)[10], double eps2) {
     const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
@@ -212,30 +289,17 @@ STE_DEV bool jacobi_off_within(const double (&a)[10], double eps2) {
     return ok;
 }
 
-STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], const bool expect_diagonal = false) {
-    double a[10], V[16];
+STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], const Scratch &sc, const int rot) {
+    double a[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) a[i] = A[i] * scale;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    bool series_ok = false, diagonal = false;
+    bool series_ok = false;
+    int sweeps = 0;
 #pragma unroll 1
-    for (int sweep = 0; sweep < (expect_diagonal ? 2 : 4); ++sweep) {
-        jacobi_sweep(a, V);
-        if (expect_diagonal) {
-            if ((series_ok = jacobi_off_within(a, kSqrtSeriesEps2))) break;
-        } else if (sweep >= 1) {
-            // irregular schedules: half of the steps are not at rounding level after two sweeps
-            // (measured on ragged sub-stepped tracks: 50-76 %), nearly all are after three
-            if ((diagonal = jacobi_off_within(a, kSqrtDiagonalEps2))) break;
-        }
-    }
-    if (diagonal) {
-        double f[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) f[k] = fast_sqrt(a[SYM(k, k)]);
-        sym_from_eig(V, f, M);
-        return false;
+    while (sweeps < kSqrtMaxSweeps) {
+        jacobi_sweep_store(a, sc, rot + sweeps * kSweepSlots);
+        ++sweeps;
+        if ((series_ok = jacobi_off_within(a, kSqrtSeriesEps2))) break;
     }
     if (!series_ok) {
         double Mt[10];
@@ -285,37 +349,21 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], con
                 if (k != p && k != q) acc = fma(X[SYM(p, k)], X[SYM(k, q)], acc);
             G[SYM(p, q)] = acc;
         }
-    // S = sqrt(D) + X1 + X2
-    double S[10];
+    // S = sqrt(D) + X1 + X2, written into M and carried back to the original basis in place
     {
         int k = 0;
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
-            for (int q = p + 1; q < 4; ++q) S[SYM(p, q)] = fma(-G[SYM(p, q)], rsum[k++], X[SYM(p, q)]);
+            for (int q = p + 1; q < 4; ++q) M[SYM(p, q)] = fma(-G[SYM(p, q)], rsum[k++], X[SYM(p, q)]);
     }
 #pragma unroll
-    for (int p = 0; p < 4; ++p) S[SYM(p, p)] = fma(-G[SYM(p, p)], 0.5 * rs[p], sd[p]);
-    // M = V S V^T
-    double T[16];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double acc = V[i * 4 + 0] * S[SYM(0, j)];
-#pragma unroll
-            for (int k = 1; k < 4; ++k) acc = fma(V[i * 4 + k], S[SYM(k, j)], acc);
-            T[i * 4 + j] = acc;
-        }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = i; j < 4; ++j) {
-            double acc = T[i * 4 + 0] * V[j * 4 + 0];
-#pragma unroll
-            for (int k = 1; k < 4; ++k) acc = fma(T[i * 4 + k], V[j * 4 + k], acc);
-            M[SYM(i, j)] = acc;
-        }
+    for (int p = 0; p < 4; ++p) M[SYM(p, p)] = fma(-G[SYM(p, p)], 0.5 * rs[p], sd[p]);
+#pragma unroll 1
+    while (sweeps > 0) {
+        --sweeps;
+        jacobi_unsweep(M, sc, rot + sweeps * kSweepSlots);
+    }
     return false;
 }
 

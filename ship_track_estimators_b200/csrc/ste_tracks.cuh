@@ -213,9 +213,7 @@ struct ForwardTrack {
             for (int r = 0; r < 4; ++r)
                 e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
-        // launch-uniform: with an update after every predict the covariance is nearly diagonal (sqrt_psd4)
-        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld, !a.in.upd_mask && k_sub == 1,
-                    !(a.prob.flags & STE_FLAG_LONG_STEPS));
+        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld, !(a.prob.flags & STE_FLAG_LONG_STEPS));
         if (advance) ++ui;
         if (upd) assimilate(ui);
         else stage_wait();   // the next step's inputs must have landed before they are read
@@ -377,13 +375,13 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
 // same order per track.
 //
 // Scratch layout of the fused kernel (slots per thread):
-//   [0, 46)   the forward pass's slots (40 used); after the loop, the backward recomputation
-//             (step 0, or every step of a track whose statistics are unusable) reuses them in
-//             the stand-alone backward layout (root 0..15, xs/Ps 16..29, Delta 30..45)
-//   [46, 60)  (xs, Ps) of the backward pass while the loop runs
+//   [0, 50)   the forward pass's slots; after the loop, the backward recomputation (step 0, or
+//             every step of a track whose statistics are unusable) reuses them in the stand-alone
+//             backward layout (xs/Ps 0..13, root 14..29, Delta 30..45, rotations 14..49)
+//   [50, 64)  (xs, Ps) of the backward pass while the loop runs
 // ------------------------------------------------------------------------------------------ //
-constexpr int kScratchFusedCarry = 46;
-constexpr int kScratchSlotsFused = 60;
+constexpr int kScratchFusedCarry = kScratchSlots;
+constexpr int kScratchSlotsFused = kScratchSlots + 14;
 
 template <bool POS_ONLY, bool GATING>
 STE_DEV void fused_track(const KernelArgs &a, const KernelArgs &b, const int t, const Scratch &sc) {

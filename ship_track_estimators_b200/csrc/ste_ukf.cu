@@ -35,7 +35,7 @@ constexpr int kThreads = STE_THREADS;
 
 template <bool POS_ONLY, bool GATING>
 __global__ void __launch_bounds__(kThreads, STE_FWD_MIN_BLOCKS) ukf_forward_kernel(const __grid_constant__ KernelArgs a) {
-    __shared__ double scratch[kScratchSlotsFwd * kThreads];
+    extern __shared__ double scratch[];   // kScratchSlotsFwd * kThreads doubles (50 KB: opt-in size)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
@@ -100,7 +100,8 @@ __device__ __forceinline__ void store_xP(const StepArgs &a, int t, const double 
         for (int j = 0; j < 4; ++j) a.P[(i * 4 + j) * ld + t] = P[SYM(i, j)];
 }
 
-__global__ void __launch_bounds__(kThreads) ukf_predict_kernel(const __grid_constant__ StepArgs a) {
+constexpr int kStepThreads = 64;   // single-step predict: 50 scratch slots per thread within the static 48 KB
+__global__ void __launch_bounds__(kStepThreads) ukf_predict_kernel(const __grid_constant__ StepArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.prob.n_tracks) return;
     const int64_t ld = a.prob.ld;
@@ -111,9 +112,9 @@ __global__ void __launch_bounds__(kThreads) ukf_predict_kernel(const __grid_cons
         for (int r = 0; r < 4; ++r) e[r] = a.noise[r * ld + t] * sqrt(a.prob.Q[r * 5]);
     }
     int status = 0;
-    __shared__ double scratch[kScratchSlots * kThreads];
-    ukf_predict(x, P, a.prob.Q, a.dt[t], a.sog_rate[t], a.cog_rate[t], e, status, Scratch{scratch + threadIdx.x, kThreads},
-                a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, nullptr, ld, false,
+    __shared__ double scratch[kScratchSlots * kStepThreads];
+    ukf_predict(x, P, a.prob.Q, a.dt[t], a.sog_rate[t], a.cog_rate[t], e, status, Scratch{scratch + threadIdx.x, kStepThreads},
+                a.sigma_prior ? a.sigma_prior + t : nullptr, a.sigma_post ? a.sigma_post + t : nullptr, nullptr, ld,
                 !(a.prob.flags & STE_FLAG_LONG_STEPS));
     if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
     store_xP(a, t, x, P);
@@ -573,21 +574,26 @@ static KernelArgs kernel_args(const SteProblem *prob, const SteInputs *in, const
     return a;
 }
 
+extern "C++" {
+template <bool POS_ONLY, bool GATING>
+static int launch_forward(const KernelArgs &a, cudaStream_t s) {
+    const dim3 grid((a.prob.n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    const size_t smem = sizeof(double) * kScratchSlotsFwd * kThreads;
+    if (cudaFuncSetAttribute(ukf_forward_kernel<POS_ONLY, GATING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(ukf_forward_kernel)");
+    ukf_forward_kernel<POS_ONLY, GATING><<<grid, block, smem, s>>>(a);
+    return check_launch("ukf_forward_kernel");
+}
+}  // extern "C++"
+
 int ste_ukf_forward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream) {
     if (int rc = validate_forward(prob, in, out)) return rc;
     if (prob->n_tracks == 0) return STE_OK;
     const bool gating = (prob->flags & STE_FLAG_GATING) != 0, pos = position_only(*prob);
     const KernelArgs a = kernel_args(prob, in, out);
-    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
     cudaStream_t s = (cudaStream_t)stream;
-    if (pos) {
-        if (gating) ukf_forward_kernel<true, true><<<grid, block, 0, s>>>(a);
-        else ukf_forward_kernel<true, false><<<grid, block, 0, s>>>(a);
-    } else {
-        if (gating) ukf_forward_kernel<false, true><<<grid, block, 0, s>>>(a);
-        else ukf_forward_kernel<false, false><<<grid, block, 0, s>>>(a);
-    }
-    return check_launch("ukf_forward_kernel");
+    if (pos) return gating ? launch_forward<true, true>(a, s) : launch_forward<true, false>(a, s);
+    return gating ? launch_forward<false, true>(a, s) : launch_forward<false, false>(a, s);
 }
 
 int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutputs *out, void *stream) {
@@ -643,7 +649,7 @@ int ste_ukf_predict_f64(const SteProblem *prob, double *x, double *P, const doub
     a.prob = *prob;
     a.x = x; a.P = P; a.dt = dt; a.sog_rate = sog_rate; a.cog_rate = cog_rate; a.noise = noise;
     a.sigma_prior = sigma_prior; a.sigma_post = sigma_post; a.status = status;
-    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    const dim3 grid((prob->n_tracks + kStepThreads - 1) / kStepThreads), block(kStepThreads);
     ukf_predict_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
     return check_launch("ukf_predict_kernel");
 }
