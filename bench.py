@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""Headline benchmark: fp64 UKF + URTSS track-steps/second on synthetic 1024-step tracks.
+"""Benchmark of the fp64 UKF + URTSS hot path on synthetic ship tracks (BASELINE.json configs 3-5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--config c5|c3|c4] [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[4], the one the metric is quoted on): 16 M tracks x 1024 steps,
-constant dt = 1 h, k = 1, UKF + URTSS, zero noise, track-sharded over the GPUs.  16 M tracks do not
-fit one GPU's HBM at once (inputs alone are 690 GB), so the job is processed in tiles of
-``--tracks`` tracks; a "step" of this benchmark is one pass of the hot path (forward filter +
-backward smoother) over one tile whose inputs are already resident in HBM.  The job is
-embarrassingly parallel over tiles, so whole-job throughput = tile throughput; per-GPU work is
-fixed as N grows (weak scaling) and there is no collective inside the timed region.
+``--config c5`` (default; BASELINE.json configs[4], the one the metric is quoted on): 16 M tracks x
+1024 steps, constant dt = 1 h, k = 1, UKF + URTSS, zero noise, track-sharded over the GPUs.  16 M
+tracks do not fit one GPU's HBM at once (inputs alone are 690 GB), so the job runs as tiles of
+``--tracks`` tracks; a "step" of the benchmark is one pass of the hot path (forward filter +
+backward smoother) over one tile whose inputs are already resident in HBM.  Per-GPU work is fixed
+as N grows (weak scaling) and there is no collective inside the timed region.  The line also
+carries ``job``: the WHOLE 16 M-track job pushed through the tile loop (this rank's
+``sharding.shard_range`` share, per-tile ``track_metrics``, one final NCCL summary), wall-clocked.
+
+``--config c3`` (configs[2]): 1 M x 1024, forward filter only.  ``--config c4`` (configs[3]): 1 M
+ragged tracks of 100-5000 fixes, gaps drawn from {1,2,3,6,12,24} h, k = 2 sub-steps, box smoothing
+2, 1 % displaced fixes, Mahalanobis gating + URTSS, processed as length-sorted tiles
+(``sharding.plan_ragged_tiles``, dealt round-robin to the ranks).
 
 One JSON line is printed by rank 0; see README / DESIGN.md for the keys.  ``--impl reference``
-times the CPU implementation of the same path (the numpy oracle port, which calls the reference's
-own scipy/numpy routines) on all host cores of the box.
+times the reference's own CPU implementation of the same path (the unmodified reference installed
+under ``baseline/_ref`` when present, else the numpy oracle port) on all host cores of the box.
 """
 from __future__ import annotations
 
@@ -24,64 +30,53 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-N_STEPS = 1024
-BYTES_FWD, BYTES_BWD = 200.0, 344.0  # algorithmic bytes per track-step at k = 1
-# FP64 operations the kernels issue per track-step, counted from SASS with ncu (profiles/r01_*):
-# 2 * DFMA + DMUL + DADD, forward (with smoother statistics) and backward (from statistics).
-FLOPS_FWD, FLOPS_BWD = 2754.0, 570.0
-FP64_INSTR_FWD, FP64_INSTR_BWD = 1802.0, 328.0  # DFMA + DMUL + DADD + DSETP warp-instructions per track-step
 MODEL = dict(H=[1.0, 1.0, 0.0, 0.0], R=[1e-3, 1e-3, 0.0, 0.0], Q=[1e-2, 1e-2, 1e-4, 1e-4], P=[1.0, 1.0, 1.0, 1.0])
-METRIC = "track-steps/sec (UKF+URTSS fp64)"
 UNIT = "track-steps/s"
+GRANULE = 148 * 128   # one block of 128 tracks per SM
+
+CONFIGS = {
+    "c5": dict(workload="configs[4]: synthetic 16M tracks x 1024 steps UKF+URTSS fp64, track-sharded; processed in resident tiles",
+               metric="track-steps/sec (UKF+URTSS fp64)", n_steps=1024, k=1, smoother=True, gating=False, ragged=False,
+               job_tracks=16 * 1024 * 1024, scaling="weak", e2e_outputs="smoothed"),
+    "c3": dict(workload="configs[2]: synthetic 1M tracks x 1024 steps, constant dt=1, fp64 UKF forward filter only; processed in resident tiles",
+               metric="track-steps/sec (UKF forward fp64)", n_steps=1024, k=1, smoother=False, gating=False, ragged=False,
+               job_tracks=1024 * 1024, scaling="weak", e2e_outputs="filtered"),
+    "c4": dict(workload="configs[3]: synthetic 1M ragged tracks (100-5000 obs), gaps in {1,2,3,6,12,24} h, k=2 sub-steps, smooth=2, "
+                        "1% displaced fixes, Mahalanobis robustification + URTSS; length-sorted tiles",
+               metric="track-steps/sec (gated UKF+URTSS fp64, ragged)", k=2, smoother=True, gating=True, ragged=True,
+               nobs_min=100, nobs_max=5000, dts_choices=(1.0, 2.0, 3.0, 6.0, 12.0, 24.0), outlier_frac=0.01, smooth_width=2,
+               job_tracks=1024 * 1024, scaling="strong", e2e_outputs="smoothed"),
+}
 
 
-# ------------------------------------------------------------------------------------------- #
-# CPU arm: the oracle port on host cores                                                      #
-# ------------------------------------------------------------------------------------------- #
-def _cpu_worker(job):
-    """One worker = one core: ``n_tracks`` synthetic tracks of ``n_steps`` steps, UKF then URTSS."""
-    seed, n_tracks, n_steps = job
-    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[var] = "1"
-    import numpy as np
-
-    from oracle import ukf_numpy as O
-    from ship_track_estimators_b200.synthetic import make_tracks
-
-    syn = make_tracks(n_tracks, n_steps + 1, seed=seed, device="cpu")
-    H, R, Q, P = (np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
-    t0 = time.perf_counter()
-    done = 0
-    for t in range(n_tracks):
-        z = np.stack([syn.lon[:, t].numpy(), syn.lat[:, t].numpy(), syn.sog[:, t].numpy(), syn.cog[:, t].numpy()])
-        dts = syn.dts[:, t].numpy()
-        O.run_track(z[:, 0], P, H, Q, R, dts, dts, z, syn.sog_rate[:, t].numpy(), syn.cog_rate[:, t].numpy(), smoother=True)
-        done += n_steps
-    return done, time.perf_counter() - t0
+def alg_bytes(k, smoother):
+    """Algorithmic bytes per track-step: forward 168 + 32/k, backward 328 + 16/k."""
+    fwd, bwd = 168.0 + 32.0 / k, 328.0 + 16.0 / k
+    return fwd, (bwd if smoother else 0.0)
 
 
-def _cpu_worker_c(job):
-    """Same sample through the plain-C oracle (oracle/ukf_oracle.c), one process per core."""
-    seed, n_tracks, n_steps = job
-    import numpy as np
+def kernel_counts():
+    """Instruction / flop / DRAM-byte counts per track-step of the kernels, written by
+    tools/ncu_counts.py from an ncu capture (profiles/kernel_counts.json); None when absent."""
+    path = os.path.join(REPO, "profiles", "kernel_counts.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return None
 
-    from oracle import ukf_c as OC
-    from ship_track_estimators_b200.synthetic import make_tracks
 
-    syn = make_tracks(n_tracks, n_steps + 1, seed=seed, device="cpu")
-    H, R, Q, P = (np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
-    args = (syn.x0().numpy(), syn.dts.numpy(), syn.lon.numpy(), syn.lat.numpy(), syn.sog_rate.numpy(), syn.cog_rate.numpy(), H, Q, R, P)
-    OC.load()
-    t0 = time.perf_counter()
-    OC.run_batch(*args, substeps=1, smoother=True)
-    return n_tracks * n_steps, time.perf_counter() - t0
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def host_cores() -> int:
@@ -91,19 +86,98 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-class CpuPool:
-    """One spawned process per host core, each running the oracle port single-threaded."""
+def np_model():
+    import numpy as np
 
-    def __init__(self, cores: int):
+    return tuple(np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
+
+
+# ------------------------------------------------------------------------------------------- #
+# CPU arm: the reference (or its oracle port) on host cores                                   #
+# ------------------------------------------------------------------------------------------- #
+def _cpu_sample(cfg_name, seed, n_tracks):
+    """Synthetic tracks of the config's shape for the CPU arms (generated with the same generator
+    as the GPU tiles).  The ragged config is sampled at a bounded length (its mean is 2550 fixes)."""
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    cfg = CONFIGS[cfg_name]
+    if cfg["ragged"]:
+        return make_tracks(n_tracks, 640, seed=seed, device="cpu", nobs_min=384, dts_choices=cfg["dts_choices"],
+                           outlier_frac=cfg["outlier_frac"], smooth_width=cfg["smooth_width"])
+    return make_tracks(n_tracks, cfg["n_steps"] + 1, seed=seed, device="cpu")
+
+
+def _cpu_worker(job):
+    """One worker = one core: a few synthetic tracks through the reference's run / run_rts_smoother
+    (kind "reference") or through the numpy oracle port (kind "port")."""
+    kind, cfg_name, seed, n_tracks = job
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    import numpy as np
+
+    import scipy.linalg  # noqa: F401  (imported once per worker by the warm-up job)
+    import torch  # noqa: F401
+
+    if n_tracks == 0:
+        return 0, 0.0
+    cfg = CONFIGS[cfg_name]
+    syn = _cpu_sample(cfg_name, seed, n_tracks)
+    H, R, Q, P = np_model()
+    if kind == "reference":
+        from oracle import reference_arm as RA
+        RA.load()
+    else:
+        from oracle import ukf_numpy as O
+    t0 = time.perf_counter()
+    done = 0
+    for t in range(n_tracks):
+        m = int(syn.nobs[t])
+        z = np.stack([syn.lon[:m, t].numpy(), syn.lat[:m, t].numpy(), syn.sog[:m, t].numpy(), syn.cog[:m, t].numpy()])
+        dts = syn.dts[: m - 1, t].numpy()
+        sr, cr = syn.sog_rate[:m, t].numpy(), syn.cog_rate[:m, t].numpy()
+        if kind == "reference":
+            RA.run_track(z, dts, cfg["k"], H, Q, R, P, sr, cr, smoother=cfg["smoother"], gating=cfg["gating"])
+        else:
+            O.run_track(z[:, 0], P, H, Q, R, O.generate_dts(dts, cfg["k"]), dts, z, sr, cr, smoother=cfg["smoother"], gating=cfg["gating"])
+        done += (m - 1) * cfg["k"]
+    return done, time.perf_counter() - t0
+
+
+def _cpu_worker_c(job):
+    """Uniform tracks through the plain-C oracle (oracle/ukf_oracle.c), one process per core."""
+    _, cfg_name, seed, n_tracks = job
+    from oracle import ukf_c as OC
+
+    cfg = CONFIGS[cfg_name]
+    syn = _cpu_sample(cfg_name, seed, n_tracks)
+    H, R, Q, P = np_model()
+    args = (syn.x0().numpy(), syn.dts.numpy(), syn.lon.numpy(), syn.lat.numpy(), syn.sog_rate.numpy(), syn.cog_rate.numpy(), H, Q, R, P)
+    OC.load()
+    t0 = time.perf_counter()
+    OC.run_batch(*args, substeps=cfg["k"], smoother=cfg["smoother"])
+    return n_tracks * cfg["n_steps"] * cfg["k"], time.perf_counter() - t0
+
+
+def reference_kind() -> str:
+    from oracle import reference_arm as RA
+
+    return "reference" if RA.locate() else "port"
+
+
+class CpuPool:
+    """One spawned process per host core, each running the CPU implementation single-threaded."""
+
+    def __init__(self, cores: int, kind: str, cfg_name: str):
         import multiprocessing as mp
 
-        self.cores = cores
+        self.cores, self.kind, self.cfg_name = cores, kind, cfg_name
         self.pool = mp.get_context("spawn").Pool(cores)
-        self.pool.map(_cpu_worker, [(0, 1, 2)] * cores)  # import numpy/scipy/torch once per worker
+        self.pool.map(_cpu_worker, [("port", "c5", 0, 0)] * cores)  # import numpy/scipy/torch once per worker
 
-    def run(self, tracks_per_core: int, n_steps: int, seed: int, worker=None):
+    def run(self, tracks_per_core: int, seed: int, worker=None):
         """-> (aggregate track-steps/s, track-steps done, slowest worker's busy seconds)."""
-        out = self.pool.map(worker or _cpu_worker, [(seed + c, tracks_per_core, n_steps) for c in range(self.cores)], chunksize=1)
+        jobs = [(self.kind, self.cfg_name, seed + c, tracks_per_core) for c in range(self.cores)]
+        out = self.pool.map(worker or _cpu_worker, jobs, chunksize=1)
         steps, busy = sum(o[0] for o in out), max(o[1] for o in out)
         return steps / busy, steps, busy
 
@@ -112,28 +186,38 @@ class CpuPool:
         self.pool.join()
 
 
+def cpu_sample_text(kind, cfg_name, cores, tracks_per_core, steps, busy):
+    cfg = CONFIGS[cfg_name]
+    what = {"reference": "the UNMODIFIED reference (baseline/_ref: UnscentedKalmanFilter.run"
+                         + (" + run_rts_smoother" if cfg["smoother"] else "") + ", np.random.normal pinned to zero"
+                         + (", robustification line re-enabled by a subclass" if cfg["gating"] else "") + ")",
+            "port": "numpy oracle port calling the reference's own scipy.linalg.sqrtm / numpy.linalg.pinv"}[kind]
+    shape = "384-640 fixes, k=2 (bounded-length sample of the ragged shape)" if cfg["ragged"] else f"{cfg['n_steps']} steps"
+    return (f"{cores} single-threaded processes x {tracks_per_core} track(s) x {shape} of the same synthetic workload, zero noise; {what}: "
+            f"{steps} track-steps, slowest worker {busy:.1f} s")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = host_cores()
-    pool = CpuPool(cores)
-    tracks_per_core, sample_steps = 1, N_STEPS
+    cfg = CONFIGS[args.config]
+    cores, kind = host_cores(), reference_kind()
+    pool = CpuPool(cores, kind, args.config)
     done = []
     for i in range(args.warmup + args.steps):
-        _, steps, busy = pool.run(tracks_per_core, sample_steps, seed=100 + 1000 * i)
+        _, steps, busy = pool.run(1, seed=100 + 1000 * i)
         if i >= args.warmup:
             done.append((steps, busy))
     pool.close()
     value = sum(s for s, _ in done) / sum(b for _, b in done)
-    sample = (f"each bench step = {cores} processes x {tracks_per_core} track x {sample_steps} steps (UKF then URTSS, zero noise); "
-              "numpy oracle port calling the reference's own scipy.linalg.sqrtm / numpy.linalg.pinv")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(b for _, b in done), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, per_gpu_tracks=None),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "per_core": value / cores,
+                         "sample": "each bench step = " + cpu_sample_text(kind, args.config, cores, 1, done[-1][0], done[-1][1])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -144,15 +228,21 @@ def run_reference_arm(args):
 # helpers                                                                                     #
 # ------------------------------------------------------------------------------------------- #
 def workload_config(args, per_gpu_tracks):
-    return {
-        "workload": "configs[4]: synthetic 16M tracks x 1024 steps UKF+URTSS fp64, track-sharded; processed in resident tiles",
-        "steps_per_track": N_STEPS, "substeps": 1, "dt_hours": 1.0, "noise": "zero",
-        "tile_tracks_per_gpu": per_gpu_tracks, "job_tracks": 16 * 1024 * 1024,
+    cfg = CONFIGS[args.config]
+    out = {
+        "workload": cfg["workload"], "config": args.config, "substeps": cfg["k"], "noise": "zero",
+        "tile_tracks_per_gpu": per_gpu_tracks, "job_tracks": cfg["job_tracks"],
         "H": MODEL["H"], "R": MODEL["R"], "Q": MODEL["Q"], "P0": MODEL["P"],
-        "cache": "inputs+outputs per step are GBs (>> 126 MB L2); two input tiles alternate",
+        "cache": "inputs+outputs per step are GBs (>> 126 MB L2); input tiles alternate",
         "cov_storage": "full16" if getattr(args, "full_cov", False) else "packed10 (symmetric 4x4 stored as its 10 unique entries)",
         "parallelism": f"tracks sharded over {args.gpus} GPU(s), no data-path collective",
     }
+    if cfg["ragged"]:
+        out.update(nobs=[cfg["nobs_min"], cfg["nobs_max"]], dts_hours=list(cfg["dts_choices"]), smooth=cfg["smooth_width"],
+                   outlier_frac=cfg["outlier_frac"], gating_chi=50.0)
+    else:
+        out.update(steps_per_track=cfg["n_steps"], dt_hours=1.0)
+    return out
 
 
 class ClockSampler:
@@ -206,233 +296,426 @@ class ClockSampler:
                 "samples_under_load": len(sm), "samples": len(self.rows)}
 
 
-def measured_traffic():
-    """DRAM bytes per track-step of each kernel from the committed ncu capture (or None)."""
-    path = os.path.join(REPO, "profiles", "r01_traffic.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            return json.load(fh)
-    return None
+class Dist:
+    """torch.distributed plumbing of the bench: barrier, max / sum over ranks (NCCL)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, value: float, op: str) -> float:
+        if self.world == 1:
+            return float(value)
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-def measured_peaks():
-    path = os.path.join(REPO, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+def fp64_probe(lib, nat, torch, dev):
+    """DFMA peak of this GPU (TFLOP/s) from the library's dependent-free FMA probe."""
+    blocks, threads, iters = 148 * 16, 256, 20000
+    sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
+    nat.check(lib.ste_probe_fp64_fma(blocks, threads, 200, nat.ptr(sink), nat.current_stream()))
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    nat.check(lib.ste_probe_fp64_fma(blocks, threads, iters, nat.ptr(sink), nat.current_stream()))
+    p1.record()
+    torch.cuda.synchronize()
+    return 2.0 * 8 * iters * blocks * threads / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+
+def roofline_block(cfg, track_steps_per_launch, f_ms, b_ms, fp64_peak, full_cov):
+    """`roofline` object of the JSON line: the dominant kernel against the measured HBM peak
+    (algorithmic bytes), both kernels, the whole step, and the FP64-pipe view from the counted
+    instructions (profiles/kernel_counts.json)."""
+    peak, peak_src = measured_peaks()
+    bytes_f, bytes_b = alg_bytes(cfg["k"], cfg["smoother"])
+    counts = kernel_counts() or {}
+    fwd_key = "forward" if cfg["smoother"] else "forward_no_tape"
+    per_kernel = {}
+    for key, ckey, alg, ms in (("forward", fwd_key, bytes_f, f_ms), ("backward", "backward", bytes_b, b_ms)):
+        if ms is None or ms <= 0.0:
+            continue
+        gbs = alg * track_steps_per_launch / (ms * 1e-3) / 1e9
+        per_kernel[key] = {"ms": ms, "algorithmic_bytes_per_track_step": alg, "algorithmic_gbs": gbs, "frac": gbs / peak}
+        c = counts.get(ckey) or {}
+        dram = c.get("dram_bytes_full_cov" if full_cov else "dram_bytes")
+        if dram:
+            dg = dram * track_steps_per_launch / (ms * 1e-3) / 1e9
+            per_kernel[key].update(dram_bytes_per_track_step=dram, dram_gbs=dg, dram_frac=dg / peak)
+        if c.get("fp64_instr"):
+            per_kernel[key].update(
+                fp64_instr_per_track_step=c["fp64_instr"], flops_per_track_step=c.get("flops"),
+                tflops=(c.get("flops") or 0.0) * track_steps_per_launch / (ms * 1e-3) / 1e12,
+                fp64_pipe_busy=c["fp64_instr"] * track_steps_per_launch / 32.0 * 2.05 / (ms * 1e-3 * 592 * 1.965e9))
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+    d = per_kernel[dom]
+    total_ms = sum(v["ms"] for v in per_kernel.values())
+    step_gbs = (bytes_f + bytes_b) * track_steps_per_launch / (total_ms * 1e-3) / 1e9
+    traffic = d.get("dram_bytes_per_track_step")
+    return {
+        "bound": "hbm", "kernel": {"forward": "ukf_forward_kernel", "backward": "urtss_backward_kernel"}[dom],
+        "achieved": d["algorithmic_gbs"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
+        "traffic": traffic * track_steps_per_launch if traffic else None, "traffic_source": counts.get("source"),
+        "peak_source": peak_src, "algorithmic_bytes_per_track_step": d["algorithmic_bytes_per_track_step"],
+        "kernel_ms": d["ms"], "kernels": per_kernel,
+        "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_track_step": bytes_f + bytes_b},
+        "fp64_pipe": {"peak_tflops_measured": fp64_peak,
+                      "note": "flops = 2*DFMA + DMUL + DADD and fp64_instr = DFMA + DMUL + DADD + DSETP warp-instructions per track-step, "
+                              "counted with ncu (profiles/kernel_counts.json); peak = DFMA probe (ste_probe_fp64_fma); fp64_pipe_busy = "
+                              "fp64_instr x 2.05 cycles issue interval over 592 sub-partitions at 1965 MHz"},
+    }
+
+
+def cpu_baseline_block(args, cfg_name):
+    """The reference's CPU path on the box's host cores, a bounded sample (rank 0, N = 1 only)."""
+    cores, kind = host_cores(), reference_kind()
+    cfg = CONFIGS[cfg_name]
+    pool = CpuPool(cores, kind, cfg_name)
+    per_core = args.cpu_tracks_per_core if not cfg["ragged"] else max(1, args.cpu_tracks_per_core // 2)
+    v, steps, busy = pool.run(per_core, seed=4321)
+    block = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "per_core": v / cores,
+             "sample": cpu_sample_text(kind, cfg_name, cores, per_core, steps, busy)}
+    compiled = None
+    if not cfg["ragged"]:
+        vc, steps_c, busy_c = pool.run(64 * args.cpu_tracks_per_core, seed=8765, worker=_cpu_worker_c)
+        compiled = {"value": vc, "unit": UNIT, "cores": cores, "per_core": vc / cores, "kind": "port",
+                    "sample": (f"plain-C restatement (oracle/ukf_oracle.c, gcc -O2, one process per core): "
+                               f"{steps_c} track-steps, slowest worker {busy_c:.1f} s")}
+    pool.close()
+    job_steps = cfg["job_tracks"] * (cfg["n_steps"] if not cfg["ragged"] else (cfg["nobs_min"] + cfg["nobs_max"]) // 2 * cfg["k"])
+    block["job_extrapolation"] = {
+        "labelled": "EXTRAPOLATION from the sample above, not a measurement",
+        "job_track_steps": job_steps, "core_seconds": job_steps / (v / cores), "hours_on_this_box": job_steps / v / 3600.0}
+    return block, compiled
 
 
 # ------------------------------------------------------------------------------------------- #
-# GPU arm                                                                                      #
+# GPU arm, uniform tiles (configs 3 and 5)                                                     #
 # ------------------------------------------------------------------------------------------- #
-def run_gpu_arm(args):
+def run_uniform(args, D):
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     from ship_track_estimators_b200 import _native as nat
     from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
-    from ship_track_estimators_b200.sharding import local_summary, reduce_summary
+    from ship_track_estimators_b200.performance_metrics import track_metrics
+    from ship_track_estimators_b200.sharding import reduce_summary, shard_range
     from ship_track_estimators_b200.synthetic import make_tracks
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    cfg = CONFIGS[args.config]
+    N, smoother = cfg["n_steps"], cfg["smoother"]
+    dev, rank, world = D.dev, D.rank, D.world
     lib = nat.load()  # raises if the CUDA library is missing: no fallback
-    H, R, Q, P = (np.diag(MODEL[k]) for k in ("H", "R", "Q", "P"))
-    ukf = BatchedUKF(H, Q, R, P, packed_cov=not args.full_cov)
+    H, R, Q, P = np_model()
+    ukf = BatchedUKF(H, Q, R, P, packed_cov=not args.full_cov, long_steps=False)   # 5-60 km/h x 1 h: every step is short
     T = args.tracks
 
     # two resident input tiles (different seeds per rank and per tile) and one set of output buffers
     tiles = []
     for j in range(2):
-        syn = make_tracks(T, N_STEPS + 1, seed=1000 + 17 * rank + j, device=str(dev))
+        syn = make_tracks(T, N + 1, seed=1000 + 17 * rank + j, device=str(dev))
         tiles.append(TrackBatch.from_synthetic(syn, substeps=1))
         del syn
-    res = ukf.allocate(tiles[0], smoother=True, in_place=args.in_place)
+    res = ukf.allocate(tiles[0], smoother=smoother, in_place=args.in_place)
     torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    fwd_ms, bwd_ms = [], []
 
     def step(i, record):
         b = tiles[i % 2]
+        marks = [ev() for _ in range(3)] if record else None
         if record:
-            e0, e1, e2 = ev(), ev(), ev()
-            e0.record()
-            ukf.forward(b, res)
-            e1.record()
-            ukf.backward(b, res)
-            e2.record()
-            return e0, e1, e2
+            marks[0].record()
         ukf.forward(b, res)
-        ukf.backward(b, res)
-        return None
+        if record:
+            marks[1].record()
+        if smoother:
+            ukf.backward(b, res)
+        if record:
+            marks[2].record()
+        return marks
 
     for i in range(args.warmup):
         step(i, False)
-    barrier()
-    with ClockSampler(local_rank) as clocks:
+    D.barrier()
+    with ClockSampler(D.local_rank) as clocks:
         t_start, t_end = ev(), ev()
         t_start.record()
         marks = [step(args.warmup + i, True) for i in range(args.steps)]
         t_end.record()
-        barrier()
-    total_ms = t_start.elapsed_time(t_end)
-    for e0, e1, e2 in marks:
-        fwd_ms.append(e0.elapsed_time(e1))
-        bwd_ms.append(e1.elapsed_time(e2))
-    if world > 1:
-        tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        total_ms = float(tmax.item())
-
-    tile_steps = T * N_STEPS
+        D.barrier()
+    total_ms = D.reduce(t_start.elapsed_time(t_end), "max")
+    f_ms = statistics.mean(m[0].elapsed_time(m[1]) for m in marks)
+    b_ms = statistics.mean(m[1].elapsed_time(m[2]) for m in marks) if smoother else None
+    tile_steps = T * N
     value = world * tile_steps * args.steps / (total_ms * 1e-3)
-    summary = reduce_summary(local_summary(res, tile_steps * args.steps), device=dev)  # outside the timed region
+    launches = (2 if smoother else 1) * args.steps
+
+    # ---- the whole job through the tile loop ---- #
+    job = None
+    if not args.no_job:
+        lo, hi = shard_range(cfg["job_tracks"], rank, world)
+        mine = hi - lo
+        n_full, rest = divmod(mine, T)
+        partial = None
+        if rest:   # the last, narrower tile of this rank's share (contiguous copies; set up before the clock starts)
+            src = tiles[n_full % 2]
+            partial = src._map(lambda t: t[..., :rest].contiguous())
+            partial.n_steps_host = None if src.n_steps_host is None else src.n_steps_host[:rest]
+            partial_res = ukf.allocate(partial, smoother=smoother, in_place=args.in_place)
+        which = "smoothed" if smoother else "filtered"
+        acc = torch.zeros(4, dtype=torch.float64, device=dev)      # sum over tracks of the per-track rmse, per state row
+        flagged = torch.zeros((), dtype=torch.int64, device=dev)
+        D.barrier()
+        w0 = time.perf_counter()
+        j0, j1 = ev(), ev()
+        j0.record()
+        for i in range(n_full + (1 if rest else 0)):
+            b, r = (tiles[i % 2], res) if i < n_full else (partial, partial_res)
+            ukf.forward(b, r)
+            if smoother:
+                ukf.backward(b, r)
+            m = track_metrics(ukf, b, r, which=which)
+            acc += torch.nan_to_num(m["rmse"]).sum(dim=1)
+            flagged += (r.status & ~nat.STE_STATUS_SMOOTH_RECOMPUTE != 0).sum()
+        j1.record()
+        local = {"tracks": float(mine), "track_steps": float(mine) * N, "flagged": float(flagged.item()),
+                 **{f"sum_rmse_{n}": float(v) for n, v in zip(("lon", "lat", "sog", "cog"), acc.tolist())}}
+        summary = reduce_summary(local, device=dev)      # the job's only collective (NCCL all_reduce of 7 doubles)
+        D.barrier()
+        wall = D.reduce(time.perf_counter() - w0, "max")
+        dev_s = D.reduce(j0.elapsed_time(j1) * 1e-3, "max")
+        job = {"tracks": int(summary["tracks"]), "track_steps": summary["track_steps"], "tiles_per_gpu": n_full + (1 if rest else 0),
+               "wall_s": wall, "device_s": dev_s, "value": summary["track_steps"] / wall, "unit": UNIT,
+               "per_tile": "forward" + (" + backward" if smoother else "") + f" + track_metrics({which}) + on-device accumulation; one NCCL all_reduce at the end",
+               "inputs": "two resident seeded tiles per GPU, alternating (16 M distinct tracks would be 690 GB of inputs); every tile's "
+                         "filtering, smoothing and metrics are executed in full",
+               "mean_rmse_deg": {n: summary[f"sum_rmse_{n}"] / summary["tracks"] for n in ("lon", "lat")},
+               "flagged_tracks": int(summary["flagged"])}
+        launches_job = (3 if smoother else 2) * (n_full + (1 if rest else 0))
+        job["gpu_launches"] = launches_job
+        if partial is not None:
+            del partial, partial_res
 
     # ---- end-to-end through the public API with HOST buffers ---- #
-    # BatchedUKF.run_host_pipelined: pinned host inputs -> device, forward + backward, all four result
-    # arrays -> pinned host, tile after tile with the copy engines overlapped with the kernels.
-    Te = args.e2e_tracks
-    host_tiles = []
-    for j in range(2):
-        syn = make_tracks(Te, N_STEPS + 1, seed=5000 + 31 * rank + j, device=str(dev))
-        host_tiles.append(TrackBatch.from_synthetic(syn, substeps=1).pin_memory())
-        del syn
-    proto = ukf.allocate(host_tiles[0].to(dev), smoother=True)
-    host_outs = [proto.host_like(pinned=True) for _ in range(2)]
-    del proto
-    torch.cuda.empty_cache()
-    e2e_steps = max(4, min(args.steps, 6))
-    seq_in = [host_tiles[i % 2] for i in range(e2e_steps)]
-    seq_out = [host_outs[i % 2] for i in range(e2e_steps)]
-    moved = ukf.run_host_pipelined(seq_in[:2], seq_out[:2], device=dev)  # warm-up
-    barrier()
-    t0, t1 = ev(), ev()
-    t0.record()
-    moved = ukf.run_host_pipelined(seq_in, seq_out, device=dev)
-    t1.record()
-    barrier()
-    e2e_ms = t0.elapsed_time(t1)
-    if world > 1:
-        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tmax.item())
-    e2e_value = world * Te * N_STEPS * e2e_steps / (e2e_ms * 1e-3)
-    assert bool(torch.isfinite(host_outs[0].mean_s).all()) and float(host_outs[0].mean_s.abs().sum()) > 0.0
+    e2e = run_e2e(args, D, ukf, cfg, lambda j: TrackBatch.from_synthetic(
+        make_tracks(args.e2e_tracks, N + 1, seed=5000 + 31 * rank + j, device=str(dev)), substeps=1), args.e2e_tracks * N)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        f_ms, b_ms = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
-        dominant = "urtss_backward_kernel" if b_ms >= f_ms else "ukf_forward_kernel"
-        dom_bytes, dom_ms = (BYTES_BWD, b_ms) if b_ms >= f_ms else (BYTES_FWD, f_ms)
-        achieved = dom_bytes * tile_steps / (dom_ms * 1e-3) / 1e9
-        step_gbs = (BYTES_FWD + BYTES_BWD) * tile_steps / ((f_ms + b_ms) * 1e-3) / 1e9
-        traffic = measured_traffic()
-        if traffic and args.full_cov:
-            traffic = dict(traffic["full_cov"], source=traffic["source"])
-        dom_key = "backward" if b_ms >= f_ms else "forward"
-        traffic_launch = traffic[dom_key]["dram_bytes_per_track_step"] * tile_steps if traffic else None
-        # both kernels: algorithmic GB/s and, from the committed ncu traffic per track-step, DRAM GB/s
-        per_kernel = {}
-        for key, alg, ms in (("forward", BYTES_FWD, f_ms), ("backward", BYTES_BWD, b_ms)):
-            per_kernel[key] = {"ms": ms, "algorithmic_gbs": alg * tile_steps / (ms * 1e-3) / 1e9,
-                               "frac": alg * tile_steps / (ms * 1e-3) / 1e9 / peak}
-            if traffic:
-                gbs = traffic[key]["dram_bytes_per_track_step"] * tile_steps / (ms * 1e-3) / 1e9
-                per_kernel[key].update(dram_gbs=gbs, dram_frac=gbs / peak)
-        # FP64 pipe: probe the DFMA peak on this GPU, compare with the counted instructions
-        blocks, threads, iters = 148 * 16, 256, 20000
-        sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
-        nat.check(lib.ste_probe_fp64_fma(blocks, threads, 200, nat.ptr(sink), nat.current_stream()))
-        p0, p1 = ev(), ev()
-        p0.record()
-        nat.check(lib.ste_probe_fp64_fma(blocks, threads, iters, nat.ptr(sink), nat.current_stream()))
-        p1.record()
-        torch.cuda.synchronize()
-        fp64_peak = 2.0 * 8 * iters * blocks * threads / (p0.elapsed_time(p1) * 1e-3) / 1e12
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, T),
-            "roofline": {
-                "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic_launch, "traffic_source": (traffic or {}).get("source"),
-                "peak_source": peak_src, "algorithmic_bytes_per_track_step": dom_bytes,
-                "kernel_ms": dom_ms, "forward_ms": f_ms, "backward_ms": b_ms, "kernels": per_kernel,
-                "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_track_step": BYTES_FWD + BYTES_BWD},
-                "fp64_pipe": {
-                    "peak_tflops_measured": fp64_peak,
-                    "achieved_tflops_step": (FLOPS_FWD + FLOPS_BWD) * tile_steps / ((f_ms + b_ms) * 1e-3) / 1e12,
-                    "achieved_tflops_forward": FLOPS_FWD * tile_steps / (f_ms * 1e-3) / 1e12,
-                    "frac_forward": FLOPS_FWD * tile_steps / (f_ms * 1e-3) / 1e12 / fp64_peak,
-                    "pipe_busy_forward": FP64_INSTR_FWD * tile_steps / 32.0 * 2.05 / (f_ms * 1e-3 * 592 * 1.965e9),
-                    "note": "flops = 2*DFMA + DMUL + DADD counted with ncu (profiles/); peak = DFMA probe (ste_probe_fp64_fma); "
-                            "pipe_busy = FP64 warp-instructions x 2.05 cycles issue interval over 592 sub-partitions at 1965 MHz",
-                },
-            },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"], "d2h_bytes_per_step": moved["d2h_bytes"],
-                    "tile_tracks": Te, "steps": e2e_steps,
-                    "outputs": ("filtered + smoothed means and covariances ("
-                                + ("full 4x4" if args.full_cov else "10 unique entries each, TrackResults.track() expands to 4x4")
-                                + ") to pinned host; H2D, kernels and D2H of successive tiles overlap (run_host_pipelined)")},
-            "gpu_launches": 2 * args.steps,
-            "clocks": clocks.summary(),
-            "summary": summary,
-        }
+        line = base_line(args, cfg, value, world, total_ms / args.steps, T)
+        line["roofline"] = roofline_block(cfg, tile_steps, f_ms, b_ms, fp64_probe(lib, nat, torch, dev), args.full_cov)
+        line["roofline"]["forward_ms"], line["roofline"]["backward_ms"] = f_ms, b_ms
+        line["e2e"], line["gpu_launches"], line["clocks"] = e2e, launches, clocks.summary()
+        if job:
+            line["job"] = job
         if world == 1 and not args.no_cpu_baseline:
-            cores = host_cores()
-            pool = CpuPool(cores)
-            v, steps, busy = pool.run(args.cpu_tracks_per_core, N_STEPS, seed=4321)
-            vc, steps_c, busy_c = pool.run(64 * args.cpu_tracks_per_core, N_STEPS, seed=8765, worker=_cpu_worker_c)
-            pool.close()
-            line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": (f"{cores} processes x {args.cpu_tracks_per_core} tracks x {N_STEPS} steps of the same synthetic workload (UKF then URTSS, "
-                           f"zero noise), numpy oracle port calling the reference's scipy/numpy routines: {steps} track-steps, slowest worker {busy:.1f} s"),
-                "compiled_port": {"value": vc, "unit": UNIT, "cores": cores,
-                                  "sample": (f"plain-C restatement (oracle/ukf_oracle.c, gcc -O2, one process per core): "
-                                             f"{steps_c} track-steps, slowest worker {busy_c:.1f} s")},
-            }
+            line["cpu_baseline"], compiled = cpu_baseline_block(args, args.config)
+            if compiled:
+                line["compiled_port"] = compiled
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def base_line(args, cfg, value, world, ms_per_step, tile_tracks):
+    return {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, tile_tracks)}
+
+
+def run_e2e(args, D, ukf, cfg, make_tile, tile_track_steps):
+    """Same metric through BatchedUKF.run_host_pipelined: pinned HOST inputs -> device, forward
+    (+ backward), the selected outputs -> pinned host, tile after tile with the copy engines
+    overlapped with the kernels.  The headline set is the config's product (the smoothed track and
+    its variances; filtered for the forward-only config); the other sets are timed beside it."""
+    import torch
+
+    dev, world, smoother = D.dev, D.world, cfg["smoother"]
+    host_tiles = [make_tile(j).pin_memory() for j in range(2)]
+    torch.cuda.empty_cache()
+    n_tiles = max(4, min(args.steps, 6))
+    seq_in = [host_tiles[i % 2] for i in range(n_tiles)]
+    sets = [cfg["e2e_outputs"]]
+    if not args.e2e_headline_only:   # ragged tiles are tens of GB of pinned memory per full output set: headline + summary only
+        sets += [s for s in (("summary",) if cfg["ragged"] else ("all", "cli", "summary")) if smoother]
+    out, by_set = None, {}
+    for name in sets:
+        host_outs = [ukf.host_outputs(host_tiles[0], outputs=name, smoother=smoother) for _ in range(2)]
+        seq_out = [host_outs[i % 2] for i in range(n_tiles)]
+        ukf.run_host_pipelined(seq_in[:2], seq_out[:2], smoother=smoother, device=dev, outputs=name)  # warm-up
+        D.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        moved = ukf.run_host_pipelined(seq_in, seq_out, smoother=smoother, device=dev, outputs=name)
+        t1.record()
+        D.barrier()
+        ms = D.reduce(t0.elapsed_time(t1), "max")
+        v = world * tile_track_steps * n_tiles / (ms * 1e-3)
+        first = next(iter(host_outs[0].values()))
+        assert bool(torch.isfinite(first.double()).all()) and float(first.double().abs().sum()) > 0.0
+        entry = {"value": v, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"] // n_tiles, "d2h_bytes_per_step": moved["d2h_bytes"] // n_tiles,
+                 "outputs": list(ukf.OUTPUT_SETS[name])}
+        by_set[name] = entry
+        if out is None:
+            out = dict(entry, output_set=name, tile_tracks=host_tiles[0].n_tracks, steps=n_tiles,
+                       api="BatchedUKF.run_host_pipelined (H2D, kernels and D2H of successive tiles overlap on three streams)")
+        del host_outs, seq_out
+        torch.cuda.empty_cache()
+    out["by_output_set"] = by_set
+    return out
+
+
+# ------------------------------------------------------------------------------------------- #
+# GPU arm, ragged fleet (config 4)                                                             #
+# ------------------------------------------------------------------------------------------- #
+def run_ragged(args, D):
+    import numpy as np
+    import torch
+
+    from ship_track_estimators_b200 import _native as nat
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.sharding import plan_ragged_tiles, reduce_summary, shard_tiles_round_robin
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    cfg = CONFIGS[args.config]
+    k, dev, rank, world = cfg["k"], D.dev, D.rank, D.world
+    lib = nat.load()
+    H, R, Q, P = np_model()
+    # long_steps=None: the tier of the geodetic step is chosen per tile from its own legs (no user knob)
+    ukf = BatchedUKF(H, Q, R, P, gating=cfg["gating"], packed_cov=not args.full_cov)
+    need = ukf.model.rows_needed()
+
+    # the fleet: 1 M lengths drawn once (seeded), sorted by decreasing length, cut into tiles by a
+    # budget of stored states, dealt round-robin to the ranks
+    rng = np.random.default_rng(2024)
+    nobs_all = np.sort(rng.integers(cfg["nobs_min"], cfg["nobs_max"] + 1, size=cfg["job_tracks"]))[::-1].astype(np.int32)
+    plan = plan_ragged_tiles((nobs_all.astype(np.int64) - 1) * k, state_budget=args.state_budget, granule=GRANULE)
+    mine = shard_tiles_round_robin(len(plan), rank, world)
+    # all of this rank's tiles (--full-job), or K of them evenly spaced through the sorted fleet after W warm-up tiles
+    def spaced(n, count):
+        return [min(n - 1, int((i + 0.5) * n / count)) for i in range(count)] if n and count else []
+
+    if args.full_job:
+        pick, n_warm = list(mine), 0
+    else:
+        warm = [mine[i] for i in spaced(len(mine), args.warmup)]
+        pick, n_warm = warm + [mine[i] for i in spaced(len(mine), min(args.steps, len(mine)))], len(warm)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def make_tile(ti):
+        lo, hi = plan[ti]
+        lengths = torch.from_numpy(nobs_all[lo:hi].copy())
+        syn = make_tracks(hi - lo, int(lengths.max()), seed=7000 + ti, device=str(dev), dts_choices=cfg["dts_choices"],
+                          outlier_frac=cfg["outlier_frac"], smooth_width=cfg["smooth_width"], lengths=lengths)
+        return TrackBatch.from_synthetic(syn, substeps=k, need_rows=need)
+
+    recs, gated, flagged, long_tiles = [], 0, 0, 0
+    D.barrier()
+    with ClockSampler(D.local_rank) as clocks:
+        for n, ti in enumerate(pick):
+            b = make_tile(ti)                                    # untimed: input generation on the device
+            r = ukf.allocate(b, smoother=True, in_place=True)    # smoothed states overwrite the filtered ones (memory)
+            long_tiles += int(ukf._long_steps_for(b))            # (cached per tile; decided before the clock starts)
+            torch.cuda.synchronize()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            ukf.forward(b, r)
+            e1.record()
+            ukf.backward(b, r)
+            e2.record()
+            torch.cuda.synchronize()
+            if n >= n_warm:
+                recs.append((b.track_steps(), e0.elapsed_time(e1), e1.elapsed_time(e2), b.n_tracks, b.max_steps))
+                gated += int((r.gate_iters > 0).sum())
+                flagged += int(((r.status & ~nat.STE_STATUS_SMOOTH_RECOMPUTE) != 0).sum())
+            del b, r
+            torch.cuda.empty_cache()
+        D.barrier()
+    steps_local = float(sum(x[0] for x in recs))
+    f_ms, b_ms = sum(x[1] for x in recs), sum(x[2] for x in recs)
+    total_ms = D.reduce(f_ms + b_ms, "max")
+    summary = reduce_summary({"track_steps": steps_local, "tracks": float(sum(x[3] for x in recs)), "gated_updates": float(gated),
+                              "flagged": float(flagged)}, device=dev)
+    value = summary["track_steps"] / (total_ms * 1e-3)
+
+    # end to end: one mid-fleet tile shape through the host-buffer API
+    mid = mine[len(mine) // 2]
+    lo, hi = plan[mid]
+    hi = min(hi, lo + max(128, args.e2e_tracks // 4))
+    lengths = torch.from_numpy(nobs_all[lo:hi].copy())
+
+    def e2e_tile(j):
+        syn = make_tracks(hi - lo, int(lengths.max()), seed=9000 + 13 * rank + j, device=str(dev), dts_choices=cfg["dts_choices"],
+                          outlier_frac=cfg["outlier_frac"], smooth_width=cfg["smooth_width"], lengths=lengths)
+        return TrackBatch.from_synthetic(syn, substeps=k, need_rows=need)
+
+    e2e = run_e2e(args, D, ukf, cfg, e2e_tile, int((lengths.to(torch.int64) - 1).sum()) * k)
+
+    if rank == 0:
+        line = base_line(args, cfg, value, world, total_ms / max(len(recs), 1), None)
+        line["steps"], line["warmup"] = len(recs), n_warm
+        line["config"].update(
+            tiling=f"sharding.plan_ragged_tiles: {len(plan)} tiles of the length-sorted fleet (state budget {args.state_budget:.3g}, "
+                   f"widths {min(h - l for l, h in plan)}-{max(h - l for l, h in plan)} tracks), dealt round-robin to {world} rank(s)",
+            timed="a 'step' is one tile: forward + backward timed with CUDA events per tile, inputs generated on the device between "
+                  "tiles (untimed); value = track-steps of the timed tiles / sum of their device times (max over ranks)",
+            tiles_timed=[{"tracks": x[3], "max_steps": x[4], "track_steps": x[0], "forward_ms": x[1], "backward_ms": x[2]} for x in recs],
+            full_job=bool(args.full_job), smoothing="in place", long_steps_tiles=f"{long_tiles} of {len(pick)} tiles pinned to the full-range geodetic tier (automatic)")
+        line["roofline"] = roofline_block(cfg, steps_local, f_ms, b_ms, fp64_probe(lib, nat, torch, dev), args.full_cov)
+        line["roofline"]["forward_ms"], line["roofline"]["backward_ms"] = f_ms, b_ms
+        line["e2e"], line["gpu_launches"], line["clocks"] = e2e, 2 * len(recs), clocks.summary()
+        line["summary"] = summary
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline_block(args, args.config)
+        print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tracks", type=int, default=148 * 128 * 8, help="tracks per resident tile per GPU")
-    ap.add_argument("--e2e-tracks", type=int, default=148 * 128, help="tracks of the host-buffer end-to-end tile")
+    ap.add_argument("--tracks", type=int, default=8 * GRANULE, help="tracks per resident tile per GPU (uniform configs)")
+    ap.add_argument("--e2e-tracks", type=int, default=GRANULE, help="tracks of the host-buffer end-to-end tile")
+    ap.add_argument("--e2e-headline-only", action="store_true", help="time only the config's own output set end to end")
+    ap.add_argument("--state-budget", type=float, default=4.0e8, help="stored states per ragged tile (config c4)")
+    ap.add_argument("--full-job", action="store_true", help="c4: run every tile of this rank's share, not a stratified K-tile subset")
+    ap.add_argument("--no-job", action="store_true", help="c3/c5: skip the whole-job pass")
     ap.add_argument("--in-place", action="store_true", help="smooth in place (halves the state memory)")
     ap.add_argument("--full-cov", action="store_true", help="store full 4x4 covariances (default: the 10 unique entries)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tracks-per-core", type=int, default=16)
     args = ap.parse_args()
-    if args.impl == "b200":
-        args.warmup = max(args.warmup, 3)  # timing rule: at least three warm-up steps
+    args.state_budget = int(args.state_budget)
     if args.impl == "reference":
         run_reference_arm(args)
-    else:
-        run_gpu_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)  # timing rule: at least three warm-up steps
+    D = Dist(args)
+    try:
+        (run_ragged if CONFIGS[args.config]["ragged"] else run_uniform)(args, D)
+    finally:
+        D.close()
 
 
 if __name__ == "__main__":

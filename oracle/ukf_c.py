@@ -10,21 +10,32 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "libukf_oracle.so")
+LIB_FMA = os.path.join(HERE, "_build", "libukf_oracle_fma.so")   # rounding variant (see Makefile)
+LIB_EXT = os.path.join(HERE, "_build", "libukf_oracle_ext.so")   # x87 extended precision (see ukf_oracle.c: REAL)
 _lib = None
+_lib_fma = None
+_lib_ext = None
 _d = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 
-def load():
-    global _lib
+def load(variant=False):
+    """The oracle library; ``variant=True``: the same source built with FMA contraction (a
+    rounding-only variant used to measure the oracle's self-uncertainty)."""
+    global _lib, _lib_fma, _lib_ext
     if _lib is None:
         src = os.path.join(HERE, "ukf_oracle.c")
-        if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        if any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(src) for p in (LIB, LIB_FMA, LIB_EXT)):
             subprocess.check_call(["make", "-C", HERE, "-s"])
-        _lib = C.CDLL(LIB)
-        _lib.oracle_forward.restype = C.c_int
-        _lib.oracle_smoother.restype = C.c_int
-        _lib.oracle_batch.restype = C.c_int
-    return _lib
+        _lib, _lib_fma, _lib_ext = C.CDLL(LIB), C.CDLL(LIB_FMA), C.CDLL(LIB_EXT)
+        for lib in (_lib, _lib_fma):
+            lib.oracle_forward.restype = C.c_int
+            lib.oracle_smoother.restype = C.c_int
+            lib.oracle_batch.restype = C.c_int
+        for lib in (_lib, _lib_fma, _lib_ext):
+            lib.oracle_track.restype = C.c_int
+    if variant == "extended":
+        return _lib_ext
+    return _lib_fma if variant else _lib
 
 
 def _p(a):
@@ -35,11 +46,12 @@ def _c(a, dtype=np.float64):
     return None if a is None else np.ascontiguousarray(a, dtype=dtype)
 
 
-def run_track(x0, P0, H, Q, R, dt_array, dts, z, sog_rate, cog_rate, smoother=True, noise=None, gating=False, mask=None):
+def run_track(x0, P0, H, Q, R, dt_array, dts, z, sog_rate, cog_rate, smoother=True, noise=None, gating=False, mask=None,
+              variant=False):
     """Same contract as oracle.ukf_numpy.run_track; ``noise`` = dict(pred, upd, bwd) of unit normals."""
     from . import ukf_numpy as O
 
-    lib = load()
+    lib = load(variant)
     dt_array = _c(dt_array)
     n, nobs = len(dt_array), z.shape[1]
     mask = O.update_mask(dt_array, dts) if mask is None else mask
@@ -65,6 +77,33 @@ def run_track(x0, P0, H, Q, R, dt_array, dts, z, sog_rate, cog_rate, smoother=Tr
         if rc < 0:
             raise IndexError("smoother rate index out of range")
         out["means_s"], out["covs_s"] = ms, cs
+    return out
+
+
+def run_track_precision(x0, P0, H, Q, R, dt_array, dts, z, sog_rate, cog_rate, smoother=True, gating=False, mask=None,
+                        precision="extended"):
+    """One zero-noise track through ``oracle_track`` of the build named by ``precision``: ``"double"``
+    (the pinned oracle), ``"fma"`` (its FMA-contracted rounding variant) or ``"extended"`` (the same
+    formulas in x87 extended precision, filtered states handed to the smoother unrounded): the
+    yardstick that tells, per track, how far an fp64 evaluation is from the exact value."""
+    from . import ukf_numpy as O
+
+    lib = load({"double": False, "fma": True, "extended": "extended"}[precision])
+    dt_array = _c(dt_array)
+    n, nobs = len(dt_array), z.shape[1]
+    mask = O.update_mask(dt_array, dts) if mask is None else mask
+    m8 = _c(mask, np.uint8)
+    out = dict(means=np.zeros((n + 1, 4)), covs=np.zeros((n + 1, 4, 4)), mask=np.asarray(mask, dtype=bool))
+    if smoother:
+        out.update(means_s=np.zeros((n + 1, 4)), covs_s=np.zeros((n + 1, 4, 4)))
+    gi, gl = np.zeros(nobs, dtype=np.int32), np.ones(nobs)
+    rep = int((n + 1) / len(dts))
+    got = lib.oracle_track(n, nobs, rep, _p(_c(x0)), _p(_c(P0)), _p(_c(H)), _p(_c(Q)), _p(_c(R)), _p(dt_array), _p(m8), _p(_c(z)),
+                           _p(_c(sog_rate)), _p(_c(cog_rate)), int(gating), C.c_double(50.0), 10000, _p(out["means"]), _p(out["covs"]),
+                           _p(out.get("means_s")), _p(out.get("covs_s")), _p(gi), _p(gl))
+    if got < 0:
+        raise IndexError("update or smoother rate index ran past the observations")
+    out.update(gate_iters=gi[:got].copy(), gate_lambda=gl[:got].copy())
     return out
 
 

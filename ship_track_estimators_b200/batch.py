@@ -106,6 +106,10 @@ class TrackBatch:
     noise_upd: Optional[torch.Tensor] = None  # [max_obs][4][T]
     noise_bwd: Optional[torch.Tensor] = None  # [max_steps][4][T]
     n_steps_host: Optional[np.ndarray] = None  # host copy for result slicing
+    # ragged tiles are packed in order of decreasing length (warps retire together, freed block slots
+    # take the next longest tracks): column j holds the caller's track order[j]; None = caller's order
+    order: Optional[np.ndarray] = None
+    _long_fraction: Optional[float] = field(default=None, repr=False, compare=False)
 
     @property
     def n_tracks(self) -> int:
@@ -131,11 +135,39 @@ class TrackBatch:
             return int(self.n_steps.sum().item())
         return self.n_tracks * self.max_steps
 
+    def check(self) -> None:
+        """Consistency of the tile's own tensors (row counts, track count, dtypes, one device); the
+        kernels trust these shapes, so a mismatch would read or write out of bounds."""
+        T, N, M, dev = self.n_tracks, self.max_steps, self.max_obs, self.device
+        f64, expect = torch.float64, []
+        expect += [("x0", self.x0, (4, T), f64), ("dt", self.dt, (N, T), f64), ("sog_rate", self.sog_rate, (M, T), f64),
+                   ("cog_rate", self.cog_rate, (M, T), f64), ("upd_mask", self.upd_mask, (N, T), torch.uint8),
+                   ("n_steps", self.n_steps, (T,), torch.int32), ("rate_repeat", self.rate_repeat, (T,), torch.int32),
+                   ("P0", self.P0, (16, T), f64), ("noise_pred", self.noise_pred, (N, 4, T), f64),
+                   ("noise_upd", self.noise_upd, (M, 4, T), f64), ("noise_bwd", self.noise_bwd, (N, 4, T), f64)]
+        expect += [(f"z[{r}]", zr, (M, T), f64) for r, zr in enumerate(self.z)]
+        for name, t, shape, dtype in expect:
+            if t is None:
+                continue
+            if tuple(t.shape) != shape or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+                raise ValueError(f"TrackBatch.{name}: expected a contiguous {dtype} tensor of shape {shape} on {dev}, "
+                                 f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+        if len(self.z) != 4:
+            raise ValueError("TrackBatch.z must list the four observation rows (None for an absent row)")
+        if self.order is not None and len(self.order) != T:
+            raise ValueError("TrackBatch.order must have one entry per track")
+
     def long_step_fraction(self, limit_km: float = 90.0) -> float:
         """Fraction of the tile's legs (fix to next fix, divided over the sub-steps) longer than
         ``limit_km`` - a little inside the 100 km range of the geodetic step's small-displacement tier.
-        A value well between 0 and 1 means the lanes of a warp would split between the two tiers:
-        build the filter with ``BatchedUKF(long_steps=True)`` then (see ``STE_FLAG_LONG_STEPS``)."""
+        A value well between 0 and 1 means the lanes of a warp would split between the two tiers;
+        ``BatchedUKF`` then keeps the tile on the full-range tier (``STE_FLAG_LONG_STEPS``).  Computed
+        once per tile (one device reduction) and cached."""
+        if self._long_fraction is None:
+            self._long_fraction = self._long_step_fraction(limit_km)
+        return self._long_fraction
+
+    def _long_step_fraction(self, limit_km: float) -> float:
         lon, lat = self.z[0], self.z[1]
         if lon is None or lat is None or lon.shape[0] < 2:
             return 0.0
@@ -158,7 +190,8 @@ class TrackBatch:
     def _map(self, fn) -> "TrackBatch":
         kw = {name: (None if getattr(self, name) is None else fn(getattr(self, name))) for name in self._TENSORS}
         return TrackBatch(z=[None if r is None else fn(r) for r in self.z], substeps=self.substeps,
-                          rate_repeat_all=self.rate_repeat_all, n_steps_host=self.n_steps_host, **kw)
+                          rate_repeat_all=self.rate_repeat_all, n_steps_host=self.n_steps_host, order=self.order,
+                          _long_fraction=self._long_fraction, **kw)
 
     def to(self, device, non_blocking: bool = False) -> "TrackBatch":
         """Copy of the tile on ``device`` (host->device copies are asynchronous from pinned memory)."""
@@ -182,14 +215,31 @@ class TrackBatch:
         is ``generate_dts(dts, substeps)`` per track and the update cadence is every ``substeps``-th
         step, which is what the exact-equality rule yields for ``dts / k`` re-summed ``k`` times when
         ``k`` is a power of two (and for k = 1)."""
-        if substeps < 1 or (substeps & (substeps - 1)) != 0:
-            raise ValueError("from_synthetic supports power-of-two substeps (exact re-summation)")
+        if substeps < 1:
+            raise ValueError("substeps must be >= 1")
         k = int(substeps)
         dts = syn.dts
-        if not bool((torch.round(dts * 1024.0) == dts * 1024.0).all().item()):
-            raise ValueError("from_synthetic needs dts on a 2^-10 h grid so that sub-step sums are exact; use from_tracks")
-        dt = (dts / k).repeat_interleave(k, dim=0).contiguous() if k > 1 else dts.contiguous()
         nobs = syn.nobs
+        valid_gap = torch.arange(dts.shape[0], device=dts.device)[:, None] < (nobs.to(torch.int64) - 1)[None, :]
+        if not bool(((dts > 0) | ~valid_gap).all().item()):
+            raise ValueError("from_synthetic needs strictly positive gaps between fixes (the reference's update rule matches "
+                             "accumulated times against np.cumsum(dts); use from_tracks for such data)")
+        dt = (dts / k).repeat_interleave(k, dim=0).contiguous() if k > 1 else dts.contiguous()
+        # "every k-th step" is what the reference's exact-equality rule gives when dts / k re-summed k
+        # times is exact: k a power of two and the gaps on a 2^-10 h grid.  Anything else (k = 3, 6,
+        # 7 ... or arbitrary gaps) gets its mask from the reference's own arithmetic, track by track.
+        upd_mask = None
+        exact = (k & (k - 1)) == 0 and bool((torch.round(dts * 1024.0) == dts * 1024.0).all().item())
+        if not exact:
+            dts_h, dt_h, nobs_h = dts.cpu().numpy(), dt.cpu().numpy(), nobs.cpu().numpy()
+            mask = np.zeros(dt_h.shape, dtype=np.uint8)
+            for t in range(dt_h.shape[1]):
+                m = int(nobs_h[t])
+                mk = exact_update_mask(dt_h[: (m - 1) * k, t], dts_h[: m - 1, t])
+                if 1 + int(mk.sum()) > m:
+                    raise IndexError(f"track {t}: {1 + int(mk.sum())} update times matched but only {m} observations")
+                mask[: (m - 1) * k, t] = mk
+            upd_mask = torch.from_numpy(mask).to(dts.device)
         uniform = bool((nobs == nobs[0]).all().item())
         n_steps = None if uniform else ((nobs - 1) * k).to(torch.int32).contiguous()
         rows = [syn.lon, syn.lat, syn.sog, syn.cog]
@@ -203,7 +253,7 @@ class TrackBatch:
             rate_rep = torch.from_numpy(rep_host).to(syn.lon.device)
         return cls(
             x0=syn.x0().contiguous(), dt=dt, sog_rate=syn.sog_rate.contiguous(), cog_rate=syn.cog_rate.contiguous(),
-            z=z, upd_mask=None, n_steps=n_steps, rate_repeat=rate_rep, substeps=k, rate_repeat_all=rate_rep_all,
+            z=z, upd_mask=upd_mask, n_steps=n_steps, rate_repeat=rate_rep, substeps=k, rate_repeat_all=rate_rep_all,
             n_steps_host=nsteps_host,
         )
 
@@ -217,9 +267,16 @@ class TrackBatch:
         time0: float = 0.0,
         noise: Optional[Sequence[Optional[Dict[str, np.ndarray]]]] = None,
         smoother: bool = True,
+        sort_by_length: bool = True,
     ):
         """Pack ``ShipTrack``-like objects (attributes ``dts, z, sog_rate, cog_rate``) with their step
         grids ``dt_arrays`` (what ``run(nsteps, dt, ship_track)`` receives).
+
+        Ragged fleets are packed in order of decreasing length (``sort_by_length``; stable, so equal
+        lengths keep the caller's order): the threads of a warp then finish together and a tile runs
+        as long as its work, not as its longest track times its width.  ``TrackBatch.order`` records
+        the permutation and ``TrackResults.track(i)`` undoes it - ``i`` is always the caller's index,
+        and every track's numbers are bit-identical to the unsorted packing.
 
         Raises ``IndexError`` where the reference would: more matched observation times than
         observations (``kalman_filter.py:101-108``) or a smoother rate index past the repeated rate
@@ -229,6 +286,14 @@ class TrackBatch:
         if T == 0:
             raise ValueError("empty batch")
         dt_arrays = [np.asarray(d, dtype=np.float64).reshape(-1) for d in dt_arrays]
+        order = None
+        lengths = np.array([len(d) for d in dt_arrays])
+        if sort_by_length and T > 1 and np.any(lengths[:-1] < lengths[1:]):
+            order = np.argsort(-lengths, kind="stable")
+            tracks = [tracks[j] for j in order]
+            dt_arrays = [dt_arrays[j] for j in order]
+            x0 = None if x0 is None else [x0[j] for j in order]
+            noise = None if noise is None else [noise[j] for j in order]
         nsteps = np.array([len(d) for d in dt_arrays], dtype=np.int32)
         nobs = np.array([np.asarray(tr.z).shape[1] for tr in tracks], dtype=np.int32)
         N, M = int(nsteps.max()), int(nobs.max())
@@ -283,7 +348,7 @@ class TrackBatch:
         return cls(
             x0=up(x0a), dt=up(dt), sog_rate=up(sr), cog_rate=up(cr), z=[up(z[r]) for r in range(4)],
             upd_mask=up(mask), n_steps=up(nsteps), rate_repeat=up(rep), substeps=1, rate_repeat_all=1,
-            n_steps_host=nsteps.copy(), **kw,
+            n_steps_host=nsteps.copy(), order=order, **kw,
         )
 
 
@@ -302,6 +367,9 @@ class TrackResults:
     gate_scale: Optional[torch.Tensor] = None
     smooth_stats: Optional[torch.Tensor] = None  # [N][19][T] device-side tape between the two passes (not a result)
     n_steps_host: Optional[np.ndarray] = None
+    order: Optional[np.ndarray] = None  # TrackBatch.order of the tile these results belong to
+    filtered_by: Optional[int] = field(default=None, repr=False, compare=False)  # id() of the tile last filtered into these buffers
+    _column_of: Optional[np.ndarray] = field(default=None, repr=False, compare=False)
 
     @property
     def packed_cov(self) -> bool:
@@ -327,7 +395,7 @@ class TrackResults:
         kw = {n: mk(getattr(self, n)) for n in self._TENSORS}
         if self.mean_s is self.mean_f:
             kw["mean_s"], kw["cov_s"] = kw["mean_f"], kw["cov_f"]
-        return TrackResults(n_steps_host=self.n_steps_host, **kw)
+        return TrackResults(n_steps_host=self.n_steps_host, order=self.order, **kw)
 
     def copy_to(self, other: "TrackResults", non_blocking: bool = True) -> int:
         """Copy every buffer into ``other`` (e.g. device -> pinned host); returns the bytes moved."""
@@ -341,12 +409,51 @@ class TrackResults:
             moved += src.numel() * src.element_size()
         return moved
 
+    def to_host(self, pinned: bool = False) -> "TrackResults":
+        """Host copy of every buffer (one device->host transfer per array); ``track(i)`` on the copy
+        costs no further transfers - the form the fleet writers use."""
+        if not self.mean_f.is_cuda:
+            return self
+        host = self.host_like(pinned=pinned)
+        self.copy_to(host, non_blocking=pinned)
+        if pinned:
+            torch.cuda.current_stream(self.mean_f.device).synchronize()
+        return host
+
+    def check_status(self, raise_on: int = nat.STE_STATUS_NONFINITE | nat.STE_STATUS_OBS_OVERRUN) -> Dict[str, int]:
+        """Per-track status bits (``STE_STATUS_*``) summarised as counts; raises ``FloatingPointError``
+        for non-finite states and ``IndexError`` for an observation overrun (where the reference
+        raises, ``kalman_filter.py:101-108``) unless masked out of ``raise_on``."""
+        st = self.status.cpu().numpy()
+        names = {"nonfinite": nat.STE_STATUS_NONFINITE, "indefinite": nat.STE_STATUS_INDEFINITE, "gate_cap": nat.STE_STATUS_GATE_CAP,
+                 "obs_overrun": nat.STE_STATUS_OBS_OVERRUN, "rank_deficient": nat.STE_STATUS_RANK_DEFICIENT,
+                 "smooth_recompute": nat.STE_STATUS_SMOOTH_RECOMPUTE}
+        counts = {k: int(np.count_nonzero(st & bit)) for k, bit in names.items()}
+        if raise_on & nat.STE_STATUS_OBS_OVERRUN and counts["obs_overrun"]:
+            col = int(np.flatnonzero(st & nat.STE_STATUS_OBS_OVERRUN)[0])
+            raise IndexError(f"{counts['obs_overrun']} track(s) matched more update times than they have observations "
+                             f"(first: column {col})")
+        if raise_on & nat.STE_STATUS_NONFINITE and counts["nonfinite"]:
+            col = int(np.flatnonzero(st & nat.STE_STATUS_NONFINITE)[0])
+            raise FloatingPointError(f"{counts['nonfinite']} track(s) produced non-finite states (first: column {col})")
+        return counts
+
     def _cov_np(self, cov: torch.Tensor, n: int, i: int) -> np.ndarray:
         c = cov[: n + 1, :, i].cpu().numpy()
         return self.expand_cov(c) if cov.shape[1] == 10 else c.reshape(n + 1, 4, 4)
 
+    def column(self, i: int) -> int:
+        """Column of the caller's track ``i`` (tiles are packed by decreasing length, ``order``)."""
+        if self.order is None:
+            return int(i)
+        if self._column_of is None:
+            self._column_of = np.empty(len(self.order), dtype=np.int64)
+            self._column_of[self.order] = np.arange(len(self.order))
+        return int(self._column_of[i])
+
     def track(self, i: int) -> Dict[str, np.ndarray]:
-        """Host copies for one track in the reference's shapes: means (N+1, 4), covs (N+1, 4, 4)."""
+        """Host copies for the caller's track ``i`` in the reference's shapes: means (N+1, 4), covs (N+1, 4, 4)."""
+        i = self.column(i)
         n = int(self.n_steps_host[i]) if self.n_steps_host is not None else self.mean_f.shape[0] - 1
         out = {
             "means": self.mean_f[: n + 1, :, i].cpu().numpy(),
@@ -374,7 +481,7 @@ class BatchedUKF:
     """
 
     def __init__(self, H, Q=None, R=None, P=None, *, gating=False, gate_chi=50.0, gate_max_iter=100, force_generic=False,
-                 packed_cov=False, long_steps=False):
+                 packed_cov=False, long_steps=None):
         if H is None:
             raise ValueError("Set proper system dynamics.")  # reference unscented.py:52-53
         eye = np.eye(4)
@@ -388,9 +495,12 @@ class BatchedUKF:
         self.packed_cov = bool(packed_cov)
         # The geodetic step has a cheaper tier for displacements <= 100 km per predict, chosen per
         # step and track.  A tile that MIXES such steps with longer ones (sparse historical fixes
-        # beside dense ones) makes the lanes of a warp run both tiers; long_steps=True keeps every
-        # step on the full-range tier instead.  Results agree to 1 ulp either way.
-        self.long_steps = bool(long_steps)
+        # beside dense ones) makes the lanes of a warp run both tiers; STE_FLAG_LONG_STEPS keeps every
+        # step on the full-range tier instead.  Results agree to 1 ulp either way.  None (default):
+        # decided per tile from TrackBatch.long_step_fraction() (one cached device reduction the first
+        # time a tile is launched); True / False pin the choice (no reduction, no synchronisation).
+        self.long_steps = None if long_steps is None else bool(long_steps)
+        self._pipe = None   # streams of run_host_pipelined, created once
 
     # ------------------------------------------------------------------ #
     def _problem(self, b: TrackBatch) -> nat.SteProblem:
@@ -399,12 +509,22 @@ class BatchedUKF:
         p.n_tracks, p.max_steps, p.max_obs = b.n_tracks, b.max_steps, b.max_obs
         p.substeps, p.rate_repeat = int(b.substeps), int(b.rate_repeat_all)
         p.flags = ((nat.STE_FLAG_GATING if m.gating else 0) | (nat.STE_FLAG_FORCE_GENERIC if m.force_generic else 0)
-                   | (nat.STE_FLAG_PACKED_COV if self.packed_cov else 0) | (nat.STE_FLAG_LONG_STEPS if self.long_steps else 0))
+                   | (nat.STE_FLAG_PACKED_COV if self.packed_cov else 0) | (nat.STE_FLAG_LONG_STEPS if self._long_steps_for(b) else 0))
         p.gate_max_iter, p.gate_chi = int(m.gate_max_iter), float(m.gate_chi)
         p.ld = b.n_tracks
         for name, M in (("H", m.H), ("Q", m.Q), ("R", m.R), ("P0", m.P0)):
             getattr(p, name)[:] = M.reshape(-1).tolist()
         return p
+
+    #: a tile whose share of > 90 km legs lies between these bounds mixes the two geodetic tiers
+    #: inside most warps and is pinned to the full-range tier
+    LONG_STEP_MIX = (0.02, 1.0)
+
+    def _long_steps_for(self, b: TrackBatch) -> bool:
+        if self.long_steps is not None:
+            return self.long_steps
+        lo, hi = self.LONG_STEP_MIX
+        return lo < b.long_step_fraction() <= hi
 
     @staticmethod
     def _inputs(b: TrackBatch) -> nat.SteInputs:
@@ -434,7 +554,7 @@ class BatchedUKF:
         res = TrackResults(
             mean_f=mean_f, cov_f=cov_f, mean_s=mean_s, cov_s=cov_s,
             status=torch.zeros(T, dtype=torch.int32, device=dev), n_updates=torch.zeros(T, dtype=torch.int32, device=dev),
-            n_steps_host=b.n_steps_host,
+            n_steps_host=b.n_steps_host, order=b.order,
         )
         if smoother and reuse_stats:
             res.smooth_stats = torch.empty(max(b.max_steps, 1), nat.STATS_PLANES, T, **f64)
@@ -463,24 +583,57 @@ class BatchedUKF:
         if res.packed_cov != self.packed_cov:
             raise ValueError("result buffers were allocated with a different covariance layout (packed_cov)")
 
+    def _check_shapes(self, b: TrackBatch, res: TrackResults, smoother: bool = False) -> None:
+        """The kernels receive raw pointers: every buffer of ``res`` must have been allocated for a
+        tile of exactly ``b``'s shape (``allocate(b)``), on ``b``'s device."""
+        b.check()
+        self._check_layout(res)
+        T, S, dev = b.n_tracks, b.max_steps + 1, b.device
+        planes = 10 if self.packed_cov else 16
+        expect = [("mean_f", res.mean_f, (S, 4, T)), ("cov_f", res.cov_f, (S, planes, T)), ("status", res.status, (T,)),
+                  ("n_updates", res.n_updates, (T,))]
+        if smoother:
+            if res.mean_s is None or res.cov_s is None:
+                raise ValueError("results were allocated without smoother buffers")
+            expect += [("mean_s", res.mean_s, (S, 4, T)), ("cov_s", res.cov_s, (S, planes, T))]
+        if res.smooth_stats is not None:
+            expect.append(("smooth_stats", res.smooth_stats, (max(b.max_steps, 1), nat.STATS_PLANES, T)))
+        for name in ("gate_iters", "gate_lambda", "gate_scale"):
+            if getattr(res, name) is not None:
+                expect.append((name, getattr(res, name), (b.max_obs, T)))
+        for name, t, shape in expect:
+            if t is None or tuple(t.shape) != shape or t.device != dev or not t.is_contiguous():
+                got = "None" if t is None else f"{tuple(t.shape)} on {t.device}"
+                raise ValueError(f"TrackResults.{name}: expected a contiguous tensor of shape {shape} on {dev} for this tile, got {got}")
+        if self.model.gating and res.gate_iters is None:
+            raise ValueError("results were allocated without gating buffers (allocate() with a gating model)")
+
     def forward(self, b: TrackBatch, res: TrackResults) -> None:
         """Launch the forward filter (asynchronous on the current stream)."""
         self._check_rows(b)
-        self._check_layout(res)
+        self._check_shapes(b, res)
         if self.model.gating and b.noise_upd is not None:
             raise NotImplementedError("gating with measurement noise tapes (data-dependent draw count)")
         p, i, o = self._problem(b), self._inputs(b), self._outputs(res)
+        res.filtered_by = id(b)
         with torch.cuda.device(b.device):
             nat.check(self._lib.ste_ukf_forward_f64(C.byref(p), C.byref(i), C.byref(o), nat.current_stream()))
 
     def backward(self, b: TrackBatch, res: TrackResults) -> None:
         """Launch the URTSS backward pass over the filtered states in ``res``."""
-        if res.mean_s is None:
-            raise ValueError("results were allocated without smoother buffers")
-        self._check_layout(res)
+        self._check_shapes(b, res, smoother=True)
+        self._check_filtered(b, res)
         p, i, o = self._problem(b), self._inputs(b), self._outputs(res)
         with torch.cuda.device(b.device):
             nat.check(self._lib.ste_urtss_backward_f64(C.byref(p), C.byref(i), C.byref(o), nat.current_stream()))
+
+    @staticmethod
+    def _check_filtered(b: TrackBatch, res: TrackResults) -> None:
+        """The backward pass reads the filtered states, status bits and statistics tape the forward
+        pass of THE SAME tile left in ``res``; a stale tape from another tile would be used silently."""
+        by = getattr(res, "filtered_by", None)
+        if by is not None and by != id(b):
+            raise ValueError("these results were last filtered from a different tile: run forward() on this tile first")
 
     def fused(self, fwd_batch: TrackBatch, fwd_res: TrackResults, bwd_batch: TrackBatch, bwd_res: TrackResults) -> None:
         """ONE launch: the forward filter of ``fwd_batch`` and the backward smoother of ``bwd_batch``
@@ -488,16 +641,16 @@ class BatchedUKF:
         ``forward(fwd_batch, fwd_res); backward(bwd_batch, bwd_res)``; the smoother's memory
         latency hides behind the filter's arithmetic.  The two result sets must be distinct."""
         self._check_rows(fwd_batch)
-        self._check_layout(fwd_res)
-        self._check_layout(bwd_res)
-        if bwd_res.mean_s is None:
-            raise ValueError("results were allocated without smoother buffers")
+        self._check_shapes(fwd_batch, fwd_res)
+        self._check_shapes(bwd_batch, bwd_res, smoother=True)
+        self._check_filtered(bwd_batch, bwd_res)
         if self.model.gating and fwd_batch.noise_upd is not None:
             raise NotImplementedError("gating with measurement noise tapes (data-dependent draw count)")
         if fwd_batch.device != bwd_batch.device:
             raise ValueError("both tiles of a fused pass must live on one device")
         pf, i_f, of = self._problem(fwd_batch), self._inputs(fwd_batch), self._outputs(fwd_res)
         pb, ib, ob = self._problem(bwd_batch), self._inputs(bwd_batch), self._outputs(bwd_res)
+        fwd_res.filtered_by = id(fwd_batch)
         with torch.cuda.device(fwd_batch.device):
             nat.check(self._lib.ste_ukf_fused_f64(C.byref(pf), C.byref(i_f), C.byref(of), C.byref(pb), C.byref(ib), C.byref(ob),
                                                   nat.current_stream()))
@@ -518,32 +671,131 @@ class BatchedUKF:
             else:
                 self.fused(batches[i], results[i], batches[i - 1], results[i - 1])
 
-    def run_host(self, host_batch: TrackBatch, host_out: TrackResults, dev_res: TrackResults, smoother: bool = True,
-                 device="cuda") -> Dict[str, int]:
-        """End-to-end call on HOST buffers: pinned inputs -> device, forward (+ backward), results ->
-        pinned ``host_out``.  Asynchronous on the current stream; synchronise before reading
-        ``host_out``.  Returns the bytes copied in each direction."""
+    # ------------------------------------------------------------------ #
+    # host-buffer (end-to-end) entry points                              #
+    # ------------------------------------------------------------------ #
+    #: named selections of what travels back to the host per tile.  Per stored state: "all" 224 B
+    #: (packed covariances; 320 B full), "cli" 128 B - what the reference CLI writes, means and
+    #: diag(P) of the filtered and the smoothed pass (main_cli.py:146-167) -, "smoothed" 64 B - the
+    #: smoothed track with its variances -, "summary" nothing per state: per track the last filtered
+    #: state and the fit metrics of performance_metrics.track_metrics.
+    OUTPUT_SETS = {
+        "all": ("mean_f", "cov_f", "mean_s", "cov_s"),
+        "cli": ("mean_f", "diag_f", "mean_s", "diag_s"),
+        "filtered": ("mean_f", "diag_f"),
+        "smoothed": ("mean_s", "diag_s"),
+        "summary": ("final", "metrics"),
+    }
+
+    def _output_names(self, outputs, smoother: bool):
+        names = self.OUTPUT_SETS[outputs] if isinstance(outputs, str) else tuple(outputs)
+        known = {"mean_f", "cov_f", "mean_s", "cov_s", "diag_f", "diag_s", "final", "metrics"}
+        for n in names:
+            if n not in known:
+                raise ValueError(f"unknown output {n!r}; choose from {sorted(known)} or a set name {sorted(self.OUTPUT_SETS)}")
+            if not smoother and n.endswith("_s"):
+                raise ValueError(f"output {n!r} needs the smoother")
+        return names
+
+    def host_outputs(self, b: TrackBatch, outputs="all", smoother: bool = True, pinned: bool = True) -> Dict[str, torch.Tensor]:
+        """Host buffers (page-locked by default) for the selected outputs of a tile shaped like ``b``,
+        plus the always-returned per-track ``status`` and ``n_updates``."""
+        T, S, C_ = b.n_tracks, b.max_steps + 1, (10 if self.packed_cov else 16)
+        shapes = {"mean_f": (S, 4, T), "mean_s": (S, 4, T), "cov_f": (S, C_, T), "cov_s": (S, C_, T), "diag_f": (S, 4, T),
+                  "diag_s": (S, 4, T), "final": (4 + C_, T), "metrics": (12, T)}
+        out = {}
+        for n in self._output_names(outputs, smoother) + ("status", "n_updates"):
+            t = torch.empty(shapes.get(n, (T,)), dtype=torch.int32 if n in ("status", "n_updates") else torch.float64)
+            out[n] = t.pin_memory() if pinned else t
+        return out
+
+    def _extract(self, b: TrackBatch, res: TrackResults, names, smoother: bool, scratch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Device tensors for the selected outputs (views where the result buffers already hold them,
+        small gathers into ``scratch`` otherwise)."""
+        dev = b.device
+        dsel = scratch.get("_diag_idx")
+        if dsel is None:
+            dsel = scratch["_diag_idx"] = torch.tensor([0, 4, 7, 9] if self.packed_cov else [0, 5, 10, 15], device=dev)
+        out = {"status": res.status, "n_updates": res.n_updates}
+        for n in names:
+            if n in ("mean_f", "cov_f", "mean_s", "cov_s"):
+                out[n] = getattr(res, n)
+            elif n in ("diag_f", "diag_s"):
+                cov = res.cov_f if n == "diag_f" else res.cov_s
+                buf = scratch.get(n)
+                if buf is None or buf.shape != (cov.shape[0], 4, cov.shape[2]):
+                    buf = scratch[n] = torch.empty(cov.shape[0], 4, cov.shape[2], dtype=torch.float64, device=dev)
+                torch.index_select(cov, 1, dsel, out=buf)
+                out[n] = buf
+            elif n == "final":
+                if b.n_steps is None:
+                    out[n] = torch.cat([res.mean_f[-1], res.cov_f[-1]], dim=0)
+                else:
+                    last = b.n_steps.to(torch.int64)[None, None, :]
+                    out[n] = torch.cat([torch.gather(res.mean_f, 0, last.expand(1, 4, -1))[0],
+                                        torch.gather(res.cov_f, 0, last.expand(1, res.cov_f.shape[1], -1))[0]], dim=0)
+            elif n == "metrics":
+                from .performance_metrics import track_metrics
+
+                m = track_metrics(self, b, res, which="smoothed" if smoother else "filtered")
+                out[n] = torch.cat([m["rmse"], m["cum_abs"], m["max_abs"]], dim=0)
+        return out
+
+    @staticmethod
+    def _copy_out(dev_out: Dict[str, torch.Tensor], host_out) -> int:
+        moved = 0
+        for n, src in dev_out.items():
+            dst = host_out.get(n) if isinstance(host_out, dict) else getattr(host_out, n, None)
+            if dst is None:
+                continue
+            dst.copy_(src, non_blocking=True)
+            moved += src.numel() * src.element_size()
+        return moved
+
+    def run_host(self, host_batch: TrackBatch, host_out, dev_res: Optional[TrackResults] = None, smoother: bool = True,
+                 device="cuda", outputs="all") -> Dict[str, int]:
+        """End-to-end call on HOST buffers: pinned inputs -> device, forward (+ backward), the selected
+        ``outputs`` -> pinned ``host_out`` (a dict from :meth:`host_outputs`, or a ``TrackResults`` of
+        host tensors for ``outputs="all"``).  Asynchronous on the current stream; synchronise before
+        reading ``host_out``.  Returns the bytes copied in each direction."""
+        names = self._output_names(outputs, smoother)
         dev_batch = host_batch.to(device, non_blocking=True)
-        self.run(dev_batch, smoother=smoother, res=dev_res)
-        d2h = dev_res.copy_to(host_out, non_blocking=True)
+        dev_res = self.run(dev_batch, smoother=smoother, res=dev_res)
+        d2h = self._copy_out(self._extract(dev_batch, dev_res, names, smoother, {}), host_out)
         return {"h2d_bytes": host_batch.input_bytes(), "d2h_bytes": d2h}
 
-    def run_host_pipelined(self, host_batches: Sequence[TrackBatch], host_outs: Sequence[TrackResults], smoother: bool = True,
-                           device="cuda") -> Dict[str, int]:
+    def run_host_pipelined(self, host_batches: Sequence[TrackBatch], host_outs: Sequence, smoother: bool = True,
+                           device="cuda", outputs="all") -> Dict[str, int]:
         """End-to-end over a sequence of HOST tiles with the three engines overlapped: while tile i
         is filtered and smoothed, tile i+1's inputs travel host->device and tile i-1's results
         device->host (PCIe is full duplex and the copy engines run beside the SMs).  Two device
-        buffer sets alternate.  ``host_batches`` / ``host_outs`` live in pinned memory; all tiles
-        share one shape.  Returns the bytes copied per tile in each direction; synchronise (or call
-        ``torch.cuda.synchronize``) before reading ``host_outs``."""
+        buffer sets alternate.  ``host_batches`` / ``host_outs`` live in pinned memory
+        (``host_outs[i]``: a dict from :meth:`host_outputs`, or a host ``TrackResults`` for
+        ``outputs="all"``); all tiles must share one shape.  ``outputs`` selects what is copied back
+        (``OUTPUT_SETS``): PCIe carries ~50 GB/s, so the bytes per state decide the end-to-end rate.
+        Returns the bytes copied over all tiles in each direction; synchronise before reading ``host_outs``."""
         dev = torch.device(device)
+        names = self._output_names(outputs, smoother)
+        n = len(host_batches)
+        if n != len(host_outs):
+            raise ValueError("one host output set per tile")
+        shape0 = (host_batches[0].n_tracks, host_batches[0].max_steps, host_batches[0].max_obs) if n else None
+        for hb in host_batches:
+            if (hb.n_tracks, hb.max_steps, hb.max_obs) != shape0:
+                raise ValueError("run_host_pipelined: all tiles must share one shape (n_tracks, max_steps, max_obs); "
+                                 f"got {(hb.n_tracks, hb.max_steps, hb.max_obs)} after {shape0}")
         cur = torch.cuda.current_stream(dev)
-        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        if self._pipe is None or self._pipe["device"] != dev:
+            self._pipe = {"device": dev, "streams": [torch.cuda.Stream(dev) for _ in range(3)], "res": [None, None],
+                          "scratch": [{}, {}], "shape": None}
+        pipe = self._pipe
+        key = (shape0, smoother, self.packed_cov)
+        if pipe["shape"] != key:                 # device result buffers are kept across calls of one shape
+            pipe["res"], pipe["scratch"], pipe["shape"] = [None, None], [{}, {}], key
+        s_in, s_run, s_out = pipe["streams"]
         for s_ in (s_in, s_run, s_out):
             s_.wait_stream(cur)
-        n = len(host_batches)
         dev_in: List[Optional[TrackBatch]] = [None, None]
-        dev_res = [None, None]
         in_done = [torch.cuda.Event() for _ in range(n)]
         run_done = [torch.cuda.Event() for _ in range(n)]
         out_done = [torch.cuda.Event() for _ in range(n)]
@@ -559,15 +811,18 @@ class BatchedUKF:
                 s_run.wait_event(in_done[i])
                 if i >= 2:
                     s_run.wait_event(out_done[i - 2])       # this result slot has been copied out
-                if dev_res[k] is None:
-                    dev_res[k] = self.allocate(dev_in[k], smoother=smoother)
-                self.run(dev_in[k], smoother=smoother, res=dev_res[k])
+                if pipe["res"][k] is None:
+                    pipe["res"][k] = self.allocate(dev_in[k], smoother=smoother)
+                res = pipe["res"][k]
+                res.n_steps_host, res.order = dev_in[k].n_steps_host, dev_in[k].order
+                self.run(dev_in[k], smoother=smoother, res=res)
+                dev_out = self._extract(dev_in[k], res, names, smoother, pipe["scratch"][k])
                 run_done[i].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(run_done[i])
-                moved["d2h_bytes"] = dev_res[k].copy_to(host_outs[i], non_blocking=True)
+                moved["d2h_bytes"] += self._copy_out(dev_out, host_outs[i])
                 out_done[i].record(s_out)
-            moved["h2d_bytes"] = host_batches[i].input_bytes()
+            moved["h2d_bytes"] += host_batches[i].input_bytes()
         for s_ in (s_in, s_run, s_out):
             cur.wait_stream(s_)
         return moved

@@ -35,6 +35,7 @@ def write_fleet_outputs(prefix: str, fleet, results, substeps: int, directory: s
     from ..utils import generate_dts
 
     n = 0
+    results = results.to_host()   # one device->host transfer per array, not eight small ones per ship
     for i in (range(fleet.n_tracks) if ships is None else ships):
         tr = results.track(i)
         lat, lon, dts = fleet.track(i)
@@ -66,5 +67,6 @@ def estimate_fleet(track_file: str, settings: dict, id_col: str = "id", lat_col:
     ukf = BatchedUKF(H, Q, R, P)
     batch = fleet.to_batch(device=device, substeps=substeps, smooth_width=width, need_rows=ukf.model.rows_needed(), geodesy=geodesy)
     results = ukf.run(batch, smoother=apply_rts_smoother)
+    results.check_status()   # IndexError / FloatingPointError where the per-ship reference run would fail
     write_fleet_outputs(output_prefix, fleet, results, substeps, directory)
     return fleet, results

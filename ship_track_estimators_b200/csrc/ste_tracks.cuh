@@ -214,8 +214,9 @@ struct ForwardTrack {
                 e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
         ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld, !(a.prob.flags & STE_FLAG_LONG_STEPS));
-        if (advance) ++ui;
-        if (upd) assimilate(ui);
+        // more matched update times than observation rows: the reference raises IndexError here
+        // (kalman_filter.py:101-108); the track is flagged and the update skipped, nothing is re-read
+        if (advance) assimilate(++ui);
         else stage_wait();   // the next step's inputs must have landed before they are read
         store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, packed, x, P);
         park();

@@ -44,15 +44,26 @@ class FleetFixes:
                           self.dts[: max(n - 1, 0), keep].copy(), self.n_obs[keep].copy())
 
     def to_batch(self, device="cuda", substeps: int = 1, smooth_width: int = 0, need_rows=(True, True, False, False),
-                 geodesy: str = "sphere"):
-        """Upload the fixes and build the filter inputs on the device (ships need >= 2 fixes)."""
+                 geodesy: str = "sphere", sort_by_length: bool = True):
+        """Upload the fixes and build the filter inputs on the device (ships need >= 2 fixes).
+
+        Ships are packed in order of decreasing length (``sort_by_length``, stable): the lanes of a
+        warp then finish together.  The permutation is recorded in ``TrackBatch.order`` and undone by
+        ``TrackResults.track(i)``, so ``i`` keeps meaning ship ``ids[i]``."""
         from .derive import batch_from_fixes
 
         if self.n_tracks and int(self.n_obs.min()) < 2:
             raise ValueError("every ship needs at least two fixes; drop the others with select()")
+        order = None
+        lon, lat, dts, n_obs = self.lon, self.lat, self.dts, self.n_obs
+        if sort_by_length and self.n_tracks > 1 and np.any(n_obs[:-1] < n_obs[1:]):
+            order = np.argsort(-n_obs.astype(np.int64), kind="stable")
+            lon, lat, dts, n_obs = lon[:, order], lat[:, order], dts[:, order], n_obs[order]
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)   # noqa: E731
-        return batch_from_fixes(up(self.lon), up(self.lat), up(self.dts), up(self.n_obs), substeps=substeps,
-                                smooth_width=smooth_width, need_rows=need_rows, geodesy=geodesy)
+        batch = batch_from_fixes(up(lon), up(lat), up(dts), up(n_obs), substeps=substeps,
+                                 smooth_width=smooth_width, need_rows=need_rows, geodesy=geodesy)
+        batch.order = order
+        return batch
 
 
 def read_csv_fleet(csv_file: str, id_col: str = "id", lat_col: str = "lat", lon_col: str = "lon",

@@ -54,6 +54,7 @@ def track_metrics(ukf, batch, res, which: str = "smoothed", keep_abs_diff: bool 
     mean = {"smoothed": res.mean_s, "filtered": res.mean_f}[which]
     if mean is None:
         raise ValueError("results hold no smoothed states")
+    ukf._check_shapes(batch, res, smoother=(which == "smoothed"))
     dev, T, ld = batch.device, batch.n_tracks, int(mean.shape[-1])
     out = {k: torch.full((4, ld), float("nan"), dtype=torch.float64, device=dev) for k in ("rmse", "cum_abs", "max_abs")}
     n_pairs = torch.zeros(ld, dtype=torch.int32, device=dev)

@@ -100,6 +100,7 @@ def make_tracks(
     outlier_frac: float = 0.0,
     smooth_width: int = 0,
     obs_sigma_deg: float = 0.05,
+    lengths: Optional[torch.Tensor] = None,
 ) -> SyntheticTracks:
     """Generate ``n_tracks`` tracks with up to ``nobs`` fixes each.
 
@@ -107,7 +108,8 @@ def make_tracks(
     sorted by decreasing length.  ``dts_choices``: hours between fixes, drawn per gap.
     ``outlier_frac``: fraction of fixes displaced by 5-50 degrees.  ``smooth_width`` >= 2 applies
     the CLI's box smoothing to SOG and COG before the rates are differenced
-    (reference ``main_cli.py:99-108``).
+    (reference ``main_cli.py:99-108``).  ``lengths`` ([T] int, each in [2, nobs]) fixes the number
+    of fixes per track instead of drawing it (a tile of a length-sorted fleet).
     """
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
@@ -121,7 +123,11 @@ def make_tracks(
     def normal(*shape):
         return torch.randn(*shape, generator=gen, **f64)
 
-    if nobs_min is None or nobs_min >= nobs:
+    if lengths is not None:
+        lengths = torch.as_tensor(lengths).to(device=dev, dtype=torch.int32)
+        if lengths.shape != (T,) or int(lengths.min()) < 2 or int(lengths.max()) > nobs:
+            raise ValueError("lengths must hold one value in [2, nobs] per track")
+    elif nobs_min is None or nobs_min >= nobs:
         lengths = torch.full((T,), nobs, dtype=torch.int32, device=dev)
     else:
         lengths = torch.randint(nobs_min, nobs + 1, (T,), generator=gen, device=dev, dtype=torch.int32)

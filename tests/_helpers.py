@@ -8,6 +8,7 @@ Tolerances (BASELINE.json north_star "1e-9 relative"):
 from __future__ import annotations
 
 import os
+import re
 import sys
 
 import numpy as np
@@ -20,10 +21,12 @@ if REPO not in sys.path:
 TOL = 1e-9
 # Where the reference's own output moves by more than TOL under a rounding-only change of its
 # LAPACK calls (fixture key ``unc``, see tests/golden/make_golden.py: rounding_variant), parity is
-# asserted at UNC_FACTOR x that self-uncertainty instead: the smoother inverts covariances with
+# asserted at that self-uncertainty instead (factor 1): the smoother inverts covariances with
 # condition numbers up to ~1e10 on long-gap tracks, which bounds what "equal to the reference"
-# can mean there.
-UNC_FACTOR = 10.0
+# can mean there.  On the fixtures this widens the bound on 48 of 97 tracks, to at most 1.0e-7
+# (smoothed means of c4_ragged_ungated); only that fixture has errors above 1e-9 at all.
+UNC_FACTOR = 1.0
+WORST = {}   # label -> worst [filtered mean, filtered cov, smoothed mean, smoothed cov] error seen (printed by the GPU tests)
 
 
 def load_golden(name):
@@ -91,7 +94,10 @@ def assert_track_close(got, ref, tol=TOL, smoother=True, label="", unc=None):
     if unc is None:
         unc = ref.get("unc", np.zeros(4))
     names = ("filtered mean", "filtered cov", "smoothed mean", "smoothed cov")
-    for name, e, u in zip(names, track_errors(got, ref, smoother), unc):
+    errs = track_errors(got, ref, smoother)
+    key = re.sub(r"\[\d+\]|\s+\d+$", "", label.split(" track")[0].split(" ship")[0]).strip() or "unlabelled"
+    WORST[key] = np.fmax(WORST.get(key, np.zeros(4)), np.nan_to_num(np.asarray(errs, dtype=float)))
+    for name, e, u in zip(names, errs, unc):
         if np.isnan(e):
             continue
         bound = max(tol, UNC_FACTOR * float(u))

@@ -35,3 +35,13 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.fail("a gpu-marked test ran without a CUDA device")
     return torch.device("cuda:0")
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Worst parity error per fixture / test label (filtered mean, filtered cov, smoothed mean, smoothed cov)."""
+    from _helpers import WORST
+
+    if WORST:
+        terminalreporter.write_line("worst parity errors (filtered mean, filtered cov, smoothed mean, smoothed cov):")
+        for key in sorted(WORST):
+            terminalreporter.write_line(f"  {key:40s} " + " ".join(f"{v:9.2e}" for v in WORST[key]))

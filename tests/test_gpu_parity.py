@@ -65,9 +65,9 @@ def test_gated_synthetic_against_oracle(cuda, native_lib):
             ref = _oracle_track(syn, t, k, H_POS, Q_DEF, R, P_DEF, gating=True)
             got = res.track(t)
             assert np.array_equal(got["gate_iters"], ref["gate_iters"]), f"track {t} generic={force_generic}"
-            np.testing.assert_allclose(got["gate_lambda"], ref["gate_lambda"], rtol=1e-8)
+            np.testing.assert_allclose(got["gate_lambda"], ref["gate_lambda"], rtol=1e-9)
             gated += int((ref["gate_iters"] > 0).sum())
-            assert_track_close(got, ref, tol=1e-8, label=f"gated track {t}", unc=np.zeros(4))
+            assert_track_close(got, ref, tol=TOL, label=f"gated synthetic track {t}", unc=np.zeros(4))
         assert gated > 0
 
 
@@ -773,3 +773,201 @@ def test_fleet_estimator_writes_the_cli_files(cuda, native_lib, tmp_path, monkey
             else:
                 assert np.max(np.abs(many - one) / np.max(np.abs(one), axis=1, keepdims=True)) <= 1e-9, (sid, name)
         assert np.array_equal(np.loadtxt(tmp_path / f"original_{sid}_track.txt"), np.loadtxt(tmp_path / "fleet" / f"original_{sid}_track.txt"))
+
+
+def test_bench_shape_tile_against_c_oracle(cuda, native_lib):
+    """The configuration bench.py times (BASELINE configs 3 / 5): 1 024-step tracks, dt = 1 h, k = 1, an update
+    after every predict, no mask, the small-displacement tier enabled and the tile not checked for long legs
+    (long_steps=False as in bench.py) - every state of every track of a 1 024-track tile against the plain-C oracle
+    at 1e-9, for the UKF + URTSS pass (with the statistics tape) and for the forward-only pass (without)."""
+    from oracle import ukf_c as OC
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    T, N = 1024, 1024
+    syn = make_tracks(T, N + 1, seed=1000, device="cpu")
+    ref = OC.run_batch(syn.x0().numpy(), syn.dts.numpy(), syn.lon.numpy(), syn.lat.numpy(), syn.sog_rate.numpy(), syn.cog_rate.numpy(),
+                       H_POS, Q_DEF, R_POS, P_DEF, substeps=1)
+    batch = TrackBatch.from_synthetic(syn, substeps=1).to(cuda)
+    assert batch.upd_mask is None and batch.n_steps is None
+    for packed, smoother in ((True, True), (False, True), (True, False)):
+        ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF, packed_cov=packed, long_steps=False)
+        res = ukf.run(batch, smoother=smoother)
+        assert int(res.status.abs().sum()) == 0
+        keys = [("mean_f", res.mean_f), ("cov_f", res.cov_f)] + ([("mean_s", res.mean_s), ("cov_s", res.cov_s)] if smoother else [])
+        for key, got in keys:
+            g, r = got.cpu().numpy(), ref[key]
+            if key.startswith("mean"):
+                d = g - r
+                d[:, 3] = (d[:, 3] + 180.0) % 360.0 - 180.0
+                err = float(np.max(np.abs(d) / np.maximum(1.0, np.abs(r))))
+            else:
+                if packed:
+                    g = g[:, [0, 1, 2, 3, 1, 4, 5, 6, 2, 5, 7, 8, 3, 6, 8, 9], :]
+                err = float(np.max(np.max(np.abs(g - r), axis=1) / np.max(np.abs(r), axis=1)))
+            print(f"bench-shape tile packed={packed} smoother={smoother} {key}: worst error {err:.2e}")
+            assert err <= TOL, (key, packed, smoother, err)
+
+
+def _c4_shape_fleet(T, nobs_max, seed):
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    return make_tracks(T, nobs_max, seed=seed, device="cpu", nobs_min=100, dts_choices=(1, 2, 3, 6, 12, 24), outlier_frac=0.01,
+                       smooth_width=2)
+
+
+def test_c4_shape_4096_tracks_against_the_oracles(cuda, native_lib):
+    """BASELINE config 4 at its named shape: 4 096 ragged tracks of 100-5 000 fixes, gaps drawn from {1,2,3,6,12,24} h,
+    k = 2 sub-steps, box smoothing 2, 1 % of the fixes displaced by 5-50 degrees, Mahalanobis gating + URTSS, the model of
+    bench.py --config c4 - EVERY track against the plain-C oracle.
+
+    Decisions: the gating iteration count of every update of every track must equal the oracle's.
+    States: on tracks of thousands of 1-24 h legs the smoother inverts covariances with condition numbers ~1e9-1e10, and
+    two correct fp64 evaluations of the reference's own formulas differ by 1e-8..3e-7 there (the C oracle against its
+    FMA-contracted build).  So the yardstick is the SAME formulas evaluated in x87 extended precision with the filtered
+    states handed to the smoother unrounded (oracle/ukf_oracle.c -DORACLE_EXTENDED): per track and quantity, the CUDA
+    path's distance from that near-exact value must be <= max(1e-9, 4 x the larger distance of the two fp64 oracle
+    builds from it), the median over tracks of (CUDA distance / fp64-oracle distance) must be <= 1, and wherever the
+    fp64 oracles are within 1e-9 of the exact value the CUDA path is held to 1e-9 x 4 as well."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    from _helpers import track_errors
+    from oracle import ukf_c as OC
+    from oracle import ukf_numpy as O
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch, TrackResults
+
+    T, k = 4096, 2
+    syn = _c4_shape_fleet(T, 5000, seed=404)
+    assert int(syn.nobs.max()) > 4990 and int(syn.nobs.min()) < 110
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF, gating=True, packed_cov=True)     # long_steps: automatic
+    batch = TrackBatch.from_synthetic(syn, substeps=k, need_rows=ukf.model.rows_needed()).to(cuda)
+    res = ukf.run(batch)
+    counts = res.check_status()
+    assert counts["nonfinite"] == 0 and counts["gate_cap"] == 0
+    OC.load()
+
+    def oracles(t):
+        m = int(syn.nobs[t])
+        z = np.stack([syn.lon[:m, t].numpy(), syn.lat[:m, t].numpy(), syn.sog[:m, t].numpy(), syn.cog[:m, t].numpy()])
+        dts = syn.dts[: m - 1, t].numpy()
+        a = (z[:, 0], P_DEF, H_POS, Q_DEF, R_POS, O.generate_dts(dts, k), dts, z, syn.sog_rate[:m, t].numpy(), syn.cog_rate[:m, t].numpy())
+        kw = dict(gating=True, mask=np.tile(np.arange(1, k + 1) == k, m - 1))
+        return tuple(OC.run_track_precision(*a, precision=p, **kw) for p in ("double", "fma", "extended"))
+
+    ratios, worst, gated, held_strict = [], np.zeros(4), 0, 0
+    chunk = 256
+    with ThreadPoolExecutor(max(2, min(32, (os.cpu_count() or 2)))) as pool:
+        for lo in range(0, T, chunk):
+            hi = min(T, lo + chunk)
+            sub = TrackResults(mean_f=res.mean_f[:, :, lo:hi].cpu(), cov_f=res.cov_f[:, :, lo:hi].cpu(), mean_s=res.mean_s[:, :, lo:hi].cpu(),
+                               cov_s=res.cov_s[:, :, lo:hi].cpu(), status=res.status[lo:hi].cpu(), n_updates=res.n_updates[lo:hi].cpu(),
+                               gate_iters=res.gate_iters[:, lo:hi].cpu(), gate_lambda=res.gate_lambda[:, lo:hi].cpu(),
+                               gate_scale=res.gate_scale[:, lo:hi].cpu(), n_steps_host=batch.n_steps_host[lo:hi])
+            for t, (ref, fma, ext) in zip(range(lo, hi), pool.map(oracles, range(lo, hi))):
+                got = sub.track(t - lo)
+                assert got["n_updates"] == int(syn.nobs[t])
+                assert np.array_equal(got["gate_iters"], ref["gate_iters"]), f"track {t}: gating decisions differ"
+                gated += int((ref["gate_iters"] > 0).sum())
+                e = np.asarray(track_errors(got, ext))
+                u = np.maximum(np.asarray(track_errors(ref, ext)), np.asarray(track_errors(fma, ext)))
+                bound = np.maximum(TOL, 4.0 * u)
+                assert np.all(e <= bound), f"track {t} ({int(syn.nobs[t])} fixes): error {e} against extended precision, fp64 oracles {u}"
+                held_strict += int(np.all(bound <= 4.0 * TOL))
+                ratios.append(float(np.max(e / np.maximum(TOL, u))))
+                worst = np.maximum(worst, e)
+    r = np.asarray(ratios)
+    print(f"C4 shape, {T} tracks, {gated} gated updates: CUDA error / fp64-oracle error (both against extended precision) median "
+          f"{np.median(r):.2f}, 99th percentile {np.percentile(r, 99):.2f}, max {r.max():.2f}; worst absolute errors {worst}; "
+          f"{held_strict} tracks held to 4e-9 on every quantity")
+    assert np.median(r) <= 1.0 and gated > 100000
+
+
+def test_ragged_packing_order_does_not_change_results(cuda, native_lib):
+    """TrackBatch.from_tracks packs by decreasing length; every track's numbers are bit-identical to the
+    caller's order, and track(i) keeps addressing the caller's i."""
+    from types import SimpleNamespace
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.utils import generate_dts
+
+    tracks, _ = load_golden("c2_historical_batch")
+    tracks = tracks[:24]
+    sts = [SimpleNamespace(dts=tr["dts"], z=tr["z"], sog_rate=tr["sog_rate"], cog_rate=tr["cog_rate"]) for tr in tracks]
+    dt_arrays = [tr["dt_array"] for tr in tracks]
+    ukf = BatchedUKF(tracks[0]["H"], tracks[0]["Q"], tracks[0]["R"], tracks[0]["P0"])
+    a = TrackBatch.from_tracks(sts, dt_arrays, device=cuda, sort_by_length=True)
+    b = TrackBatch.from_tracks(sts, dt_arrays, device=cuda, sort_by_length=False)
+    assert a.order is not None and b.order is None
+    assert np.all(np.diff(a.n_steps_host) <= 0)
+    ra, rb = ukf.run(a), ukf.run(b)
+    for i in range(len(tracks)):
+        x, y = ra.track(i), rb.track(i)
+        for key in ("means", "covs", "means_s", "covs_s"):
+            assert np.array_equal(x[key], y[key]), (i, key)
+        assert x["means"].shape[0] == len(dt_arrays[i]) + 1
+
+
+def test_shape_checks_refuse_mismatched_buffers(cuda, native_lib):
+    """Result buffers of another tile shape, a stale tape, or inconsistent batch tensors raise instead of
+    letting a kernel write out of bounds."""
+    import dataclasses
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+    small = TrackBatch.from_synthetic(make_tracks(64, 17, seed=1, device="cpu"), substeps=1).to(cuda)
+    wide = TrackBatch.from_synthetic(make_tracks(96, 17, seed=2, device="cpu"), substeps=1).to(cuda)
+    long_ = TrackBatch.from_synthetic(make_tracks(64, 33, seed=3, device="cpu"), substeps=1).to(cuda)
+    res = ukf.allocate(small)
+    for other in (wide, long_):
+        with pytest.raises(ValueError, match="TrackResults"):
+            ukf.forward(other, res)
+    ukf.forward(small, res)
+    twin = TrackBatch.from_synthetic(make_tracks(64, 17, seed=4, device="cpu"), substeps=1).to(cuda)
+    with pytest.raises(ValueError, match="different tile"):
+        ukf.backward(twin, res)
+    ukf.backward(small, res)
+    bad = dataclasses.replace(small, cog_rate=small.cog_rate[:-1].contiguous())
+    with pytest.raises(ValueError, match="cog_rate"):
+        ukf.forward(bad, ukf.allocate(small))
+    with pytest.raises(ValueError, match="share one shape"):
+        ukf.run_host_pipelined([small.pin_memory(), long_.pin_memory()],
+                               [ukf.host_outputs(small), ukf.host_outputs(long_)], device=cuda)
+
+
+def test_pipelined_output_sets(cuda, native_lib):
+    """run_host_pipelined(outputs=...): every named output set returns exactly what the full results hold."""
+    import torch
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.performance_metrics import track_metrics
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF, packed_cov=True)
+    tiles = [TrackBatch.from_synthetic(make_tracks(256, 41, seed=50 + j, device="cpu", dts_choices=(1, 2), nobs_min=20), substeps=2) for j in range(3)]
+    full = [ukf.run(t.to(cuda)) for t in tiles]
+    pinned = [t.pin_memory() for t in tiles]
+    for name, keys in ukf.OUTPUT_SETS.items():
+        outs = [ukf.host_outputs(pinned[0], outputs=name) for _ in tiles]
+        moved = ukf.run_host_pipelined(pinned, outs, device=cuda, outputs=name)
+        torch.cuda.synchronize()
+        assert moved["d2h_bytes"] == sum(v.numel() * v.element_size() for o in outs for v in o.values())
+        for j, (o, f) in enumerate(zip(outs, full)):
+            dev_tile = tiles[j].to(cuda)
+            assert torch.equal(o["status"], f.status.cpu())
+            for key in keys:
+                if key in ("mean_f", "cov_f", "mean_s", "cov_s"):
+                    want = getattr(f, key).cpu()
+                elif key.startswith("diag"):
+                    want = (f.cov_f if key == "diag_f" else f.cov_s)[:, [0, 4, 7, 9], :].cpu()
+                elif key == "final":
+                    n = torch.from_numpy(tiles[j].n_steps_host.astype(np.int64))
+                    cols = torch.arange(len(n))
+                    want = torch.cat([f.mean_f.cpu()[n, :, cols].T, f.cov_f.cpu()[n, :, cols].T], dim=0)
+                else:
+                    m = track_metrics(ukf, dev_tile, f, which="smoothed")
+                    want = torch.cat([m["rmse"], m["cum_abs"], m["max_abs"]], dim=0).cpu()
+                assert torch.equal(torch.nan_to_num(o[key]), torch.nan_to_num(want)), (name, key, j)

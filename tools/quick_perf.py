@@ -13,6 +13,9 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--generic", action="store_true")
 ap.add_argument("--packed", action="store_true")
 ap.add_argument("--fused", action="store_true")
+ap.add_argument("--no-probe", action="store_true")
+ap.add_argument("--no-metrics", action="store_true")
+ap.add_argument("--label", default="")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 lib = nat.load()
@@ -26,51 +29,39 @@ def timed(fn, reps):
         ts.append(e0.elapsed_time(e1))
     return min(ts), ts
 
-# FP64 probe
-blocks, threads, iters = 148 * 16, 256, 20000
-sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
-ms, _ = timed(lambda: nat.check(lib.ste_probe_fp64_fma(blocks, threads, iters, nat.ptr(sink), nat.current_stream())), 3)
-flops = 2.0 * 8 * iters * blocks * threads
-print(json.dumps({"probe": "fp64_fma", "ms": ms, "tflops": flops / ms / 1e9}))
+if not a.no_probe:
+    blocks, threads, iters = 148 * 16, 256, 20000
+    sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
+    ms, _ = timed(lambda: nat.check(lib.ste_probe_fp64_fma(blocks, threads, iters, nat.ptr(sink), nat.current_stream())), 3)
+    print(json.dumps({"probe": "fp64_fma", "ms": ms, "tflops": 2.0 * 8 * iters * blocks * threads / ms / 1e9}))
 
-t0 = time.time()
 syn = make_tracks(a.tracks, a.steps + 1, seed=1, device="cuda:0")
-torch.cuda.synchronize(); print("gen s", time.time() - t0)
 batch = TrackBatch.from_synthetic(syn, substeps=1)
 H = np.diag([1.0, 1, 0, 0]); R = np.diag([1e-3, 1e-3, 0, 0]); Q = np.diag([1e-2, 1e-2, 1e-4, 1e-4]); P = np.eye(4)
-ukf = BatchedUKF(H, Q, R, P, force_generic=a.generic, packed_cov=a.packed)
+ukf = BatchedUKF(H, Q, R, P, force_generic=a.generic, packed_cov=a.packed, long_steps=False)
 res = ukf.allocate(batch, smoother=True)
+res_nt = ukf.allocate(batch, smoother=False)
 f_ms, f_all = timed(lambda: ukf.forward(batch, res), a.reps)
 b_ms, b_all = timed(lambda: ukf.backward(batch, res), a.reps)
+n_ms, n_all = timed(lambda: ukf.forward(batch, res_nt), a.reps)
 ts = a.tracks * a.steps
-print(json.dumps({"tracks": a.tracks, "steps": a.steps, "fwd_ms": f_ms, "bwd_ms": b_ms,
-                  "fwd_steps_per_s": ts / f_ms * 1e3, "bwd_steps_per_s": ts / b_ms * 1e3,
+print(json.dumps({"label": a.label or os.environ.get("STE_UKF_LIB", "default"), "tracks": a.tracks, "steps": a.steps, "fwd_ms": f_ms, "bwd_ms": b_ms, "fwd_no_tape_ms": n_ms,
+                  "fwd_steps_per_s": ts / f_ms * 1e3, "bwd_steps_per_s": ts / b_ms * 1e3, "fwd_no_tape_steps_per_s": ts / n_ms * 1e3,
                   "both_steps_per_s": ts / (f_ms + b_ms) * 1e3,
                   "fwd_GBs": ts * 200 / f_ms / 1e6, "both_GBs": ts * 544 / (f_ms + b_ms) / 1e6,
-                  "status_nonzero": int((res.status != 0).sum().item()), "all": [f_all, b_all]}))
+                  "status_nonzero": int((res.status != 0).sum().item()), "all": [f_all, b_all, n_all]}))
 print("sample smoothed", res.mean_s[0, :, 0].tolist(), res.mean_s[-1, :, 0].tolist())
 
-from ship_track_estimators_b200.performance_metrics import track_metrics
-m_ms, _ = timed(lambda: track_metrics(ukf, batch, res, which="smoothed"), a.reps)
-print(json.dumps({"track_metrics_ms": m_ms, "GBs_algorithmic": ts * 32 / m_ms / 1e6}))
+if not a.no_metrics:
+    from ship_track_estimators_b200.performance_metrics import track_metrics
+    m_ms, _ = timed(lambda: track_metrics(ukf, batch, res, which="smoothed"), a.reps)
+    print(json.dumps({"track_metrics_ms": m_ms, "GBs_algorithmic": ts * 32 / m_ms / 1e6}))
 
 if a.fused:
     syn2 = make_tracks(a.tracks, a.steps + 1, seed=2, device="cuda:0")
     batch2 = TrackBatch.from_synthetic(syn2, substeps=1)
-    res2, ref2 = ukf.allocate(batch2, smoother=True), ukf.allocate(batch2, smoother=True)
-    ukf.forward(batch2, ref2)                       # separate launches: the expected values
-    ukf.forward(batch, res); ukf.backward(batch, res)
-    exp_s, exp_c, exp_f = res.mean_s.clone(), res.cov_s.clone(), ref2.mean_f.clone()
-    res.mean_s.zero_(); res.cov_s.zero_()
+    res2 = ukf.allocate(batch2, smoother=True)
     ukf.forward(batch, res)
-    ukf.fused(batch2, res2, batch, res)            # forward(batch2) + backward(batch) in one launch
-    torch.cuda.synchronize()
-    T = a.tracks
-    same = (torch.equal(res.mean_s[..., :T], exp_s[..., :T]), torch.equal(res.cov_s[..., :T], exp_c[..., :T]),
-            torch.equal(res2.mean_f[..., :T], exp_f[..., :T]), torch.equal(res2.cov_f[..., :T], ref2.cov_f[..., :T]))
-    print("fused bit-identical (mean_s, cov_s, mean_f, cov_f):", same)
-    def both():
-        ukf.forward(batch, res)
     fu_ms, fu_all = timed(lambda: ukf.fused(batch2, res2, batch, res), a.reps)
     print(json.dumps({"fused_ms": fu_ms, "separate_ms": f_ms + b_ms, "fused_steps_per_s": ts / fu_ms * 1e3,
                       "gain": (f_ms + b_ms) / fu_ms, "all": fu_all}))
