@@ -33,8 +33,8 @@ extern "C" {
 #endif
 
 #define STE_ABI_VERSION 3   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
-                            /* 3: smooth_stats holds STE_STATS_PLANES = 19 planes per step (was 30)                                          */
-#define STE_STATS_PLANES 19
+                            /* 3: smooth_stats holds STE_STATS_PLANES = 15 planes per step (was 30)                                          */
+#define STE_STATS_PLANES 15
 #define STE_DIM 4
 #define STE_NSIGMA 9
 
@@ -122,7 +122,7 @@ typedef struct SteOutputs {
     double *gate_scale;  /* [max_obs][ld] accumulated scale of R (product of lambdas), or NULL        */
     double *smooth_stats; /* [max_steps][STE_STATS_PLANES][ld] or NULL.  Written by the forward pass,  */
                          /* read by the backward pass: per predict step the noise-free predicted-mean */
-                         /* offset (4), the predicted covariance about the filtered mean (7 entries)  */
+                         /* offset (4), the predicted covariance about the filtered mean (3 entries)  */
                          /* and the cross covariance (8 entries) that rts_step recomputes from the    */
                          /* same sigma points (unscented.py:299-330); the entries that follow from    */
                          /* the filtered covariance (linear speed / course rows) are not stored.      */
@@ -164,6 +164,13 @@ int ste_ukf_predict_f64(const SteProblem *prob, double *x, double *P, const doub
 int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const double *z,
                        const double *noise, uint8_t *gate_iters, double *gate_lambda,
                        double *gate_scale, int32_t *status, void *stream);
+
+/* UnscentedKalmanFilter.criterion_index and the denominator of update_lambda_factor
+ * (unscented.py:389-483) for T filters: with y = z - x (not z - Hx, no angle wrap) and
+ * S = H P H^T + R (prob->H, prob->R), gamma[t] = |y^T pinv(S) y| and denom[t] = y^T pinv(S) R pinv(S) y,
+ * so that lambda' = lambda + (gamma - chi) / denom.  x [4][ld], P [16][ld], z [4][ld]; gamma, denom [T]. */
+int ste_gate_terms_f64(const SteProblem *prob, const double *x, const double *P, const double *z,
+                       double *gamma, double *denom, void *stream);
 
 /* UnscentedKalmanFilter.compute_sigma_points (unscented.py:76-107), any n <= 8:
  * X[:, 0] = x, X[:, 1+i] = x + M[:, i], X[:, 1+n+i] = x - M[:, i], M = Re sqrtm(scale * P).

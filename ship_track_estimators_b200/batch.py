@@ -365,7 +365,7 @@ class TrackResults:
     gate_iters: Optional[torch.Tensor] = None
     gate_lambda: Optional[torch.Tensor] = None
     gate_scale: Optional[torch.Tensor] = None
-    smooth_stats: Optional[torch.Tensor] = None  # [N][19][T] device-side tape between the two passes (not a result)
+    smooth_stats: Optional[torch.Tensor] = None  # [N][15][T] device-side tape between the two passes (not a result)
     n_steps_host: Optional[np.ndarray] = None
     order: Optional[np.ndarray] = None  # TrackBatch.order of the tile these results belong to
     filtered_by: Optional[int] = field(default=None, repr=False, compare=False)  # id() of the tile last filtered into these buffers

@@ -329,6 +329,18 @@ STE_DEV void small_hypot_scale_v(const double (&a)[N], const double (&e)[N], dou
     STE_LANES out[l] = fma(a[l], e[l] * p[l], a[l]);
 }
 
+// a * (sqrt(1 + e) - 1)
+template <int N>
+STE_DEV void small_hypot_excess_v(const double (&a)[N], const double (&e)[N], double (&out)[N]) {
+    double p[N];
+    STE_LANES p[l] = fma(e[l], kSqrt1pS[5], kSqrt1pS[4]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[3]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[2]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[1]);
+    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[0]);
+    STE_LANES out[l] = a[l] * (e[l] * p[l]);
+}
+
 template <bool X_NONNEG>
 STE_DEV double fast_atan2(double y, double x) {
     const double yv[1] = {y}, xv[1] = {x};

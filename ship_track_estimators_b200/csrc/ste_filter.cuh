@@ -40,23 +40,24 @@ constexpr int kScratchSlotsBwd = kScratchSlots;
 
 // Smoother statistics ("tape") the forward pass can emit for every predict, so that the backward
 // pass need not regenerate and re-propagate the sigma points of the same filtered state (the
-// reference recomputes them, unscented.py:299-330; they are the same numbers).  Per step, 19 planes:
+// reference recomputes them, unscented.py:299-330; they are the same numbers).  Per step, 15 planes:
 //   [0..3]   delta = sum W_i f(X_i) - x          noise-free predicted mean minus the filtered mean
-//   [4..10]  P_b   = sum W_i d_i d_i^T + Q        about the filtered mean: entries 00 01 02 03 11 12 13
-//   [11..18] D[q][r], q = 0..3, r = 0..1          cross covariance sum W_i (X_i - x) f(X_i)^T, its
-//                                                 longitude and latitude columns (plane 11 + 2 q + r)
-// What is NOT on the tape follows from the filtered covariance P the backward pass reads anyway:
-// speed and course propagate linearly (y_2 = x_2 + sog_rate dt, y_3 = x_3 + cog_rate dt,
+//   [4..6]   P_b   = sum W_i d_i d_i^T + Q        about the filtered mean: its position block 00 01 11
+//   [7..14]  D[q][r], q = 0..3, r = 0..1          cross covariance sum W_i (X_i - x) f(X_i)^T, its
+//                                                 longitude and latitude columns (plane 7 + 2 q + r)
+// What is NOT on the tape follows from these and from the filtered covariance P the backward pass
+// reads anyway: speed and course propagate linearly (y_2 = x_2 + sog_rate dt, y_3 = x_3 + cog_rate dt,
 // non_linear_process.py:72-78), so their sigma-point deviations are +-m_c exactly and, with
 // M M = 3 P and 2 W_i = 1/3,
 //   D[q][r]   = 2 W_i sum_c m_c[q] m_c[r] = P[q][r]                       (r = 2, 3)
+//   P_b[r][q] = D[q][r] + Q[r][q] + delta_r delta_q                       (r in {0, 1}, q in {2, 3})
 //   P_b[q][r] = P[q][r] + Q[q][r] + delta_q delta_r                       (q, r in {2, 3})
 // (the reference forms the same sums numerically and lands within rounding of these values).  The
-// identity needs M M = 3 P, i.e. no clamped negative eigenvalue: a track whose root clamped one
-// (STE_STATUS_INDEFINITE) is flagged STE_STATUS_SMOOTH_RECOMPUTE and smoothed by recomputation.
-constexpr int kStatsPlanes = 19;
-constexpr int kStatsPb = 4;     // 7 planes, SYM() indices 0..6
-constexpr int kStatsD = 11;     // 8 planes
+// identities need M M = 3 P, i.e. no clamped negative eigenvalue: a step whose root clamped one
+// marks its tape entry invalid (delta_0 = NaN) and the backward pass recomputes that step.
+constexpr int kStatsPlanes = 15;
+constexpr int kStatsPb = 4;     // 3 planes: 00 01 11
+constexpr int kStatsD = 7;      // 8 planes
 
 STE_DEV void stash_root(const Scratch &sc, const double (&M)[10]) {
 #pragma unroll
@@ -255,13 +256,15 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int q = r; q < 4; ++q) {
-            P[SYM(r, q)] = fma(e[r], e[q], cov[SYM(r, q)]);
-            if (stats && SYM(r, q) < 7) STE_STORE_STREAM(stats + (kStatsPb + SYM(r, q)) * ld, fma(delta[r], delta[q], cov[SYM(r, q)]));   // about x
-        }
+        for (int q = r; q < 4; ++q) P[SYM(r, q)] = fma(e[r], e[q], cov[SYM(r, q)]);
     if (stats) {
+        // position block of P_b (about x); a clamped root invalidates the entry (see kStatsPlanes)
+        STE_STORE_STREAM(stats + (kStatsPb + 0) * ld, fma(delta[0], delta[0], cov[SYM(0, 0)]));
+        STE_STORE_STREAM(stats + (kStatsPb + 1) * ld, fma(delta[0], delta[1], cov[SYM(0, 1)]));
+        STE_STORE_STREAM(stats + (kStatsPb + 2) * ld, fma(delta[1], delta[1], cov[SYM(1, 1)]));
+        STE_STORE_STREAM(stats, clamped ? f64_from_bits(0x7ff8000000000000ull) : delta[0]);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) STE_STORE_STREAM(stats + r * ld, delta[r]);
+        for (int r = 1; r < 4; ++r) STE_STORE_STREAM(stats + r * ld, delta[r]);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -732,15 +735,18 @@ STE_DEV void urtss_gain(const double (&xf)[4], const double (&Pf)[10], const dou
 
 // One backward iteration from the statistics the forward pass stored for this step (kStatsPlanes
 // planes at `stats`): no sigma points, no square root - a pseudo-inverse and three small products.
-// The speed / course columns of D and block of P_b come from the filtered covariance (see kStatsPlanes).
-STE_DEV void urtss_step_from_stats(const double (&xf)[4], const double (&Pf)[10], const double *stats, int64_t ld,
-                                   const double *Q, const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status,
-                                   const Scratch &sc) {
+// What the tape leaves out comes from the filtered covariance and Q (see kStatsPlanes).  `dlt0` is
+// the entry's first plane, already loaded by the caller (NaN = entry invalid, handled there).
+STE_DEV void urtss_step_from_stats(const double (&xf)[4], const double (&Pf)[10], const double dlt0, const double *stats,
+                                   int64_t ld, const double *Q, const double (&e)[4], double (&xs)[4], double (&Ps)[10],
+                                   int &status, const Scratch &sc) {
     double dlt[4], xb[4], Pb[10], D[16];
+    dlt[0] = dlt0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) dlt[r] = STE_LOAD_STREAM(stats + r * ld);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) Pb[k] = STE_LOAD_STREAM(stats + (kStatsPb + k) * ld);
+    for (int r = 1; r < 4; ++r) dlt[r] = STE_LOAD_STREAM(stats + r * ld);
+    Pb[SYM(0, 0)] = STE_LOAD_STREAM(stats + (kStatsPb + 0) * ld);
+    Pb[SYM(0, 1)] = STE_LOAD_STREAM(stats + (kStatsPb + 1) * ld);
+    Pb[SYM(1, 1)] = STE_LOAD_STREAM(stats + (kStatsPb + 2) * ld);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -748,6 +754,10 @@ STE_DEV void urtss_step_from_stats(const double (&xf)[4], const double (&Pf)[10]
 #pragma unroll
         for (int r = 2; r < 4; ++r) D[q * 4 + r] = Pf[SYM(q, r)];
     }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 2; q < 4; ++q) Pb[SYM(r, q)] = fma(dlt[r], dlt[q], D[q * 4 + r] + Q[r * 4 + q]);
 #pragma unroll
     for (int r = 2; r < 4; ++r)
 #pragma unroll

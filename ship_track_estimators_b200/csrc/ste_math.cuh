@@ -568,21 +568,24 @@ template <bool LIB, int NP, bool SMALL = false>
 STE_DEV void geodetic_finish_n(const double (&x)[NP][4], const AngleTrig (&t)[NP], double dt, double sog_rate,
                                double cog_rate, double (&y)[NP][4]) {
     if constexpr (!LIB && SMALL) {
-        double east[NP], north[NP], up[NP], q[NP], e[NP], h[NP], dlon[NP], sdel[NP], dlat[NP];
+        // sin(lat2 - lat1) = up cos(lat1) - cos(lat2) sin(lat1) with cos(lat2) = north sqrt(1 + q^2).  Since
+        // up cos(lat1) - north sin(lat1) = sin(delta) cos(alpha) identically, it equals
+        //     sin(delta) cos(alpha) - sin(lat1) north (sqrt(1 + q^2) - 1):
+        // no cancellation between two O(1) products, and `up` is never formed.
+        double east[NP], north[NP], sdca[NP], q[NP], e[NP], g[NP], dlon[NP], sdel[NP], dlat[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-            const double sdca = t[i].sd * t[i].ca;
+            sdca[i] = t[i].sd * t[i].ca;
             east[i] = t[i].sd * t[i].sa;
-            north[i] = fma(t[i].cp, t[i].cd, -t[i].sp * sdca);
-            up[i] = fma(t[i].sp, t[i].cd, t[i].cp * sdca);
+            north[i] = fma(t[i].cp, t[i].cd, -t[i].sp * sdca[i]);
         }
         fast_div_v<NP>(east, north, q);
 #pragma unroll
         for (int i = 0; i < NP; ++i) e[i] = q[i] * q[i];
-        small_hypot_scale_v<NP>(north, e, h);      // cos(lat2)
+        small_hypot_excess_v<NP>(north, e, g);     // cos(lat2) - north
         small_atan_v<NP>(q, e, dlon);
 #pragma unroll
-        for (int i = 0; i < NP; ++i) sdel[i] = fma(up[i], t[i].cp, -h[i] * t[i].sp);   // sin(lat2 - lat1)
+        for (int i = 0; i < NP; ++i) sdel[i] = fma(-t[i].sp, g[i], sdca[i]);
         small_asin_v<NP>(sdel, dlat);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {

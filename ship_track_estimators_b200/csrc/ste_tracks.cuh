@@ -41,15 +41,20 @@ STE_DEV int cov_plane(bool packed, int i, int j) { return packed ? SYM(i, j) : i
 
 STE_DEV void store_state(double *mean, double *cov, int64_t ld, int64_t s, int t, bool packed,
                          const double (&x)[4], const double (&P)[10]) {
+    // planes are consecutive in both layouts: one 64-bit add per store instead of a plane * ld product
     double *m = mean + (s * 4) * ld + t;
+#pragma unroll
+    for (int r = 0; r < 4; ++r, m += ld) STE_STORE_STREAM(m, x[r]);
     double *c = cov + (s * cov_planes(packed)) * ld + t;
+    if (packed) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) STE_STORE_STREAM(m + r * ld, x[r]);
+        for (int k = 0; k < 10; ++k, c += ld) STE_STORE_STREAM(c, P[k]);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (i <= j || !packed) STE_STORE_STREAM(c + cov_plane(packed, i, j) * ld, P[SYM(i, j)]);
+            for (int j = 0; j < 4; ++j, c += ld) STE_STORE_STREAM(c, P[SYM(i, j)]);
+    }
 }
 
 STE_DEV void load_cov(const double *cov_state, int64_t ld, bool packed, double (&P)[10]) {
@@ -99,6 +104,7 @@ struct ForwardTrack {
     // update index.  They agree on every regular step grid; a track where they do not is flagged
     // and smoothed by recomputation.
     int rep = 1, ri = 0, rc = 0;
+    int sub_left = 1;   // predicts left until the next update when the cadence is "every k-th step"
     bool consistent = true, upd_next = false;
 
     STE_DEV ForwardTrack(const KernelArgs &args, int track, const Scratch &scratch)
@@ -119,8 +125,12 @@ struct ForwardTrack {
         stage_async(&sc.at(kScratchIn + 1), a.in.sog_rate + (int64_t)rate_index * ld + t);
         stage_async(&sc.at(kScratchIn + 2), a.in.cog_rate + (int64_t)rate_index * ld + t);
     }
-    STE_DEV bool step_updates(int s) const {
-        return a.in.upd_mask ? (a.in.upd_mask[(int64_t)s * ld + t] != 0) : ((s + 1) % k_sub == 0);
+    // does step s end on an observation?  (called once per step, in order: s = 0, 1, 2, ...)
+    STE_DEV bool step_updates(int s) {
+        if (a.in.upd_mask) return a.in.upd_mask[(int64_t)s * ld + t] != 0;
+        if (--sub_left > 0) return false;   // (s + 1) % k_sub == 0 without the division
+        sub_left = k_sub;
+        return true;
     }
 
     STE_DEV void assimilate(int u) {
@@ -151,6 +161,7 @@ struct ForwardTrack {
     STE_DEV void begin() {
         nt = a.in.n_steps ? min_(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
         k_sub = a.prob.substeps > 0 ? a.prob.substeps : 1;
+        sub_left = k_sub;
 #pragma unroll
         for (int r = 0; r < 4; ++r) x[r] = a.in.x0[r * ld + t];
 #pragma unroll
@@ -225,8 +236,7 @@ struct ForwardTrack {
     STE_DEV void end() {
         unpark();
         if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
-        // the tape omits what follows from M M = 3 P: not valid once a root clamped an eigenvalue
-        if (a.out.smooth_stats && (!consistent || (status & STE_STATUS_INDEFINITE))) status |= STE_STATUS_SMOOTH_RECOMPUTE;
+        if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;
         a.out.status[t] = status;
         if (a.out.n_updates) a.out.n_updates[t] = ui + 1;
     }
@@ -304,8 +314,6 @@ struct BackwardTrack {
         for (int k = 0; k < kStatsPlanes; ++k) prefetch_l2(st + k * ld);
     }
 
-    // STATS_ONLY: the caller guarantees use_stats && step > 0 (no recomputation code is generated)
-    template <bool STATS_ONLY = false>
     STE_DEV void step(int step) {
         const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
         const double *cf = a.out.cov_f + ((int64_t)step * cov_planes(packed)) * ld + t;
@@ -318,12 +326,18 @@ struct BackwardTrack {
             for (int r = 0; r < 4; ++r)
                 e[r] = a.in.noise_bwd[((int64_t)step * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
-        if (STATS_ONLY || (use_stats && step > 0)) {
-            double Pf[10];
-            load_cov(cf, ld, packed, Pf);
-            urtss_step_from_stats(xf, Pf, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, a.prob.Q, e, xs,
-                                  Ps, status, sc);
-        } else {
+        bool done = false;
+        if (use_stats && step > 0) {
+            const double *st = a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t;
+            const double dlt0 = STE_LOAD_STREAM(st);
+            if (dlt0 == dlt0) {   // NaN: the forward pass's root clamped an eigenvalue at this step; recompute it below
+                double Pf[10];
+                load_cov(cf, ld, packed, Pf);
+                urtss_step_from_stats(xf, Pf, dlt0, st, ld, a.prob.Q, e, xs, Ps, status, sc);
+                done = true;
+            }
+        }
+        if (!done) {
             double s1[4], Pb[10];
             const double dt = a.in.dt[(int64_t)step * ld + t];
             const int ri = min_(step / rep, a.prob.max_obs - 1);
@@ -375,21 +389,17 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
 // Results are bit-identical to the two separate passes: the same step functions run in the
 // same order per track.
 //
-// Scratch layout of the fused kernel (slots per thread):
-//   [0, 50)   the forward pass's slots; after the loop, the backward recomputation (step 0, or
-//             every step of a track whose statistics are unusable) reuses them in the stand-alone
-//             backward layout (xs/Ps 0..13, root 14..29, Delta 30..45, rotations 14..49)
-//   [50, 64)  (xs, Ps) of the backward pass while the loop runs
+// Scratch layout of the fused kernel (slots per thread): [0, 50) the forward pass's slots, [50, 100)
+// the backward pass's (carried xs / Ps, and the root / Delta / rotation slots of a step that has to
+// be recomputed - step 0, a step whose tape entry is invalid, or every step of a flagged track).
 // ------------------------------------------------------------------------------------------ //
-constexpr int kScratchFusedCarry = kScratchSlots;
-constexpr int kScratchSlotsFused = kScratchSlots + 14;
+constexpr int kScratchSlotsFused = 2 * kScratchSlots;
 
 template <bool POS_ONLY, bool GATING>
 STE_DEV void fused_track(const KernelArgs &a, const KernelArgs &b, const int t, const Scratch &sc) {
     const bool has_f = t < a.prob.n_tracks, has_b = t < b.prob.n_tracks;
     ForwardTrack<POS_ONLY, GATING, true> f(a, t, sc);
-    // the carried (xs, Ps) sit at kScratchXs/kScratchPs relative to a shifted base
-    BackwardTrack g(b, t, Scratch{sc.base + (long)(kScratchFusedCarry - kScratchXs) * sc.stride, sc.stride});
+    BackwardTrack g(b, t, Scratch{sc.base + (long)kScratchSlots * sc.stride, sc.stride});
     if (has_b) g.begin();
     if (has_f) f.begin();
     // tracks without usable statistics are smoothed entirely after the loop
@@ -414,20 +424,10 @@ STE_DEV void fused_track(const KernelArgs &a, const KernelArgs &b, const int t, 
         const bool do_b = i < nb_loop;
         if (do_b) g.prefetch_stats_step(sb);
         if (i < f.nt) f.step(i);
-        if (do_b) g.step<true>(sb);
+        if (do_b) g.step(sb);
     }
     if (has_f) f.end();
     if (has_b) {
-        double xs[4], Ps[10];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xs[r] = g.sc.at(kScratchXs + r);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) Ps[k] = g.sc.at(kScratchPs + k);
-        g.sc = sc;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) g.sc.at(kScratchXs + r) = xs[r];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) g.sc.at(kScratchPs + k) = Ps[k];
 #pragma unroll 1
         for (int step = g.nt - 1 - nb_loop; step >= 0; --step) g.step(step);
         g.end();

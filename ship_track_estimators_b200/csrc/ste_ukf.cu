@@ -151,6 +151,37 @@ __global__ void __launch_bounds__(kThreads) ukf_update_kernel(const __grid_const
     if (a.status) a.status[t] = status;
 }
 
+// criterion_index / update_lambda_factor (unscented.py:389-483): gamma = |y^T S^+ y| and the
+// denominator y^T S^+ R S^+ y of the lambda update, y = z - x (not z - Hx, no wrap), S = H P H^T + R.
+__global__ void __launch_bounds__(kThreads) gate_terms_kernel(const __grid_constant__ StepArgs a, double *gamma, double *denom) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.prob.n_tracks) return;
+    const int64_t ld = a.prob.ld;
+    double x[4], P[10], y[4], HP[16], S[10], Sinv[10], v[4];
+    load_xP(a, t, x, P);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) y[r] = a.z[r * ld + t] - x[r];
+    innovation_cov(P, a.prob.H, a.prob.R, 1.0, HP, S);
+    pinv_sym4(S, Sinv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = fma(Sinv[SYM(i, j)], y[j], acc);
+        v[i] = acc;
+    }
+    double den = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double row = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row = fma(a.prob.R[i * 4 + j], v[j], row);
+        den = fma(v[i], row, den);
+    }
+    gamma[t] = fabs(quad_form(Sinv, y));
+    denom[t] = den;
+}
+
 // ------------------------------------------------------------------------------------------ //
 // compute_sigma_points for any n <= 8 (unscented.py:76-107).  Not on the hot path: generic-n
 // cyclic Jacobi on thread-local arrays.
@@ -676,6 +707,19 @@ int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const doubl
         else ukf_update_kernel<false, false><<<grid, block, 0, s>>>(a);
     }
     return check_launch("ukf_update_kernel");
+}
+
+int ste_gate_terms_f64(const SteProblem *prob, const double *x, const double *P, const double *z, double *gamma, double *denom,
+                       void *stream) {
+    if (int rc = validate_problem(prob)) return rc;
+    if (!x || !P || !z || !gamma || !denom) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if (prob->n_tracks == 0) return STE_OK;
+    StepArgs a{};
+    a.prob = *prob;
+    a.x = const_cast<double *>(x); a.P = const_cast<double *>(P); a.z = z;
+    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    gate_terms_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, gamma, denom);
+    return check_launch("gate_terms_kernel");
 }
 
 int ste_sigma_points_f64(int32_t n, int32_t n_tracks, int64_t ld, double scale, const double *x, const double *P,

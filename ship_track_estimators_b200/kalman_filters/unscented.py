@@ -202,7 +202,7 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         self.sigma_points = sp1.cpu().numpy().reshape(4, 9)
         self.status |= int(st.item())
 
-    def _update_device(self, x, P, R, z, use_noise):
+    def _update_device(self, x, P, R, z, use_noise, gating=None):
         """Shared by ``update`` and ``check_robustness``: returns (x, P, iters, lambda, scale)."""
         import torch
 
@@ -212,7 +212,7 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         if self.measurement_model is not None:
             assert callable(self.measurement_model), "Measurement model must be callable."
             raise NotImplementedError("measurement_model hooks are not supported on the CUDA path")
-        engine = BatchedUKF(self.H, self.Q, R, P, gating=self.gating)
+        engine = BatchedUKF(self.H, self.Q, R, P, gating=self.gating if gating is None else gating)
         p = self._step_problem(engine)
         dev = torch.device("cuda")
         f64 = dict(dtype=torch.float64, device=dev)
@@ -235,8 +235,17 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         (reference ``:209-265``)."""
         self._require_n4("update")
         z = np.asarray(z, dtype=np.float64).reshape(-1, 1)
-        use_noise = self._noise_on() and not self.gating  # gating: zero measurement noise (see DESIGN.md)
-        self.x, self.P, it, lam, _ = self._update_device(self.x, self.P, self.R, z, use_noise)
+        if self.gating and self._noise_on():
+            # the reference's own sequence (:228-236 with the robustification line enabled): the judging
+            # loop draws fresh measurement noise per iteration, then the update draws once more with the
+            # inflated R - a data-dependent number of draws, so the loop runs on the host around the
+            # device evaluations of criterion_index / update_lambda_factor
+            R = self.check_robustness(z, self.P, self.R)
+            self.x, self.P, _, _, _ = self._update_device(self.x, self.P, R, z, True, gating=False)
+            self.gate_iters.append(self.last_gate["iterations"])
+            self.gate_lambda.append(self.last_gate["lambda_factor"])
+            return
+        self.x, self.P, it, lam, _ = self._update_device(self.x, self.P, self.R, z, self._noise_on())
         if self.gating:
             self.gate_iters.append(it)
             self.gate_lambda.append(lam)
@@ -348,10 +357,57 @@ class UnscentedKalmanFilter(KalmanFilterBase):
     # ------------------------------------------------------------------ #
     # robustification (reference :353-511; dead code there)              #
     # ------------------------------------------------------------------ #
+    def _gate_terms(self, z, P, R):
+        """(gamma, denominator) of ``criterion_index`` / ``update_lambda_factor`` from the device."""
+        import torch
+
+        from ..batch import BatchedUKF
+        from .. import _native as nat
+
+        self._require_n4("criterion_index")
+        engine = BatchedUKF(self.H, self.Q, R, P)
+        p = self._step_problem(engine)
+        dev = torch.device("cuda")
+        up = lambda a, n: torch.from_numpy(np.asarray(a, dtype=np.float64).reshape(n, 1).copy()).to(dev)   # noqa: E731
+        xd, Pd, zd = up(self.x, 4), up(P, 16), up(z, 4)
+        out = torch.zeros(2, dtype=torch.float64, device=dev)
+        nat.check(engine._lib.ste_gate_terms_f64(C.byref(p), nat.ptr(xd), nat.ptr(Pd), nat.ptr(zd), nat.ptr(out[0:1]), nat.ptr(out[1:2]),
+                                                 nat.current_stream()))
+        g, d = out.cpu().tolist()
+        return g, d
+
+    def criterion_index(self, z: np.ndarray, P: np.ndarray, R: np.ndarray) -> float:
+        """Mahalanobis judging index ``|(z - x)^T pinv(H P H^T + R) (z - x)|`` (reference ``:389-428``;
+        Chang, J Geod 88 (2014) 391-401, eq. 11/14)."""
+        return self._gate_terms(z, P, R)[0]
+
+    def update_lambda_factor(self, lambda_factor: float, criterion_index: float, chi_alpha: float, z: np.ndarray,
+                             P: np.ndarray, R: np.ndarray) -> float:
+        """``lambda + (gamma - chi) / ((z - x)^T S^+ R S^+ (z - x))`` (reference ``:430-483``, eq. 18)."""
+        return lambda_factor + (criterion_index - chi_alpha) / self._gate_terms(z, P, R)[1]
+
     def check_robustness(self, z: np.ndarray, P: np.ndarray, R: np.ndarray) -> np.ndarray:
         """Mahalanobis-distance outlier judging: returns the inflated measurement covariance
-        ``R * prod(lambda)`` (reference ``:353-387``), with zero measurement noise."""
+        ``R * prod(lambda)`` (reference ``:353-387``).  With the noise off the whole loop is one
+        kernel; with ``noise="numpy"`` it is the reference's loop, one fresh draw of measurement noise
+        per evaluation (``:359-373``), around the device evaluations."""
         self._require_n4("check_robustness")
+        if self._noise_on():
+            z = np.asarray(z, dtype=np.float64).reshape(-1, 1)
+            R = np.asarray(R, dtype=np.float64)
+            lam, chi, it, scale = 1.0, 50.0, 0, 1.0
+            draw = lambda: (np.random.normal(size=self.n) * np.sqrt(np.diag(R))).reshape(-1, 1)   # noqa: E731
+            zn = z + draw()
+            gamma = self.criterion_index(zn, P, R)
+            while gamma > chi:
+                zn = z + draw()
+                lam = self.update_lambda_factor(lam, gamma, chi, zn, P, R)
+                R = self.scale_measurement_uncertainty(R, lam)
+                scale *= lam
+                gamma = self.criterion_index(zn, P, R)
+                it += 1
+            self.last_gate = dict(iterations=it, lambda_factor=lam, scale=scale)
+            return R
         keep = self.gating
         self.gating = True
         try:

@@ -96,3 +96,46 @@ def test_gating_known_answers(cuda, native_lib):
         assert g.last_gate["iterations"] == int(iters)
         assert abs(g.last_gate["lambda_factor"] - lam) <= 1e-9 * lam
         assert abs(Rs[0, 0] / 0.25 - scale) <= 1e-9 * scale
+
+
+def _gate_kats():
+    import os
+
+    from _helpers import GOLDEN
+
+    d = np.load(os.path.join(GOLDEN, "kat_gating_noisy.npz"))
+    return [{k.split("_", 1)[1]: d[k] for k in d.files if k.startswith(f"c{i}_")} for i in range(int(d["n"]))]
+
+
+def test_robustification_entry_points_against_reference_kats(cuda, native_lib):
+    """criterion_index, update_lambda_factor and the reference's NOISY judging loop followed by the update
+    (unscented.py:209-265, 353-483 with the call at :228 enabled), the recorded np.random.normal draws replayed."""
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics
+
+    Q = np.diag([1e-2, 1e-2, 1e-4, 1e-4])
+    for i, c in enumerate(_gate_kats()):
+        ukf = UnscentedKalmanFilter(H=c["H"], Q=Q, R=c["R"], P=c["P"], x0=c["x"], non_linear_process=geodetic_dynamics, gating=True)
+        gamma = ukf.criterion_index(c["z"], c["P"], c["R"])
+        np.testing.assert_allclose(gamma, float(c["gamma"]), rtol=1e-9, err_msg=f"case {i} criterion_index")
+        lam = ukf.update_lambda_factor(1.0, float(c["gamma"]), 50.0, c["z"], c["P"], c["R"])
+        np.testing.assert_allclose(lam, float(c["lam"]), rtol=1e-9, err_msg=f"case {i} update_lambda_factor")
+        queue = [row for row in c["tape"]]
+        orig = np.random.normal
+
+        def replay(loc=0.0, scale=1.0, size=None):
+            rows = size[0] if isinstance(size, tuple) and len(size) == 2 else 1
+            out = np.stack([queue.pop(0) for _ in range(rows)])
+            return out if isinstance(size, tuple) and len(size) == 2 else out[0]
+
+        np.random.normal = replay
+        try:
+            ukf.update(c["z"])
+        finally:
+            np.random.normal = orig
+        assert not queue, f"case {i}: {len(queue)} recorded draws were not consumed"
+        assert ukf.last_gate["iterations"] == int(c["n_gate_draws"]) - 1
+        np.testing.assert_allclose(ukf.last_gate["scale"], c["R_out"][0, 0] / c["R"][0, 0], rtol=1e-9)
+        d = ukf.x.reshape(-1) - c["x_post"]
+        d[3] = (d[3] + 180.0) % 360.0 - 180.0
+        assert float(np.max(np.abs(d) / np.maximum(1.0, np.abs(c["x_post"])))) <= TOL, f"case {i} state"
+        assert float(np.max(np.abs(ukf.P - c["P_post"])) / np.max(np.abs(c["P_post"]))) <= TOL, f"case {i} covariance"

@@ -193,3 +193,16 @@ def test_wgs84_leg_known_answers():
     arc = lambda p: A0 * ((1 + n**2 / 4 + n**4 / 64) * p - 1.5 * (n - n**3 / 8) * np.sin(2 * p) + 15 / 16 * (n**2 - n**4 / 4) * np.sin(4 * p)
                           - 35 / 48 * n**3 * np.sin(6 * p) + 315 / 512 * n**4 * np.sin(8 * p))   # noqa: E731
     assert abs(s - (arc(np.radians(20.0)) - arc(np.radians(-10.0)))) < 1e-4 and abs(az) < 1e-12
+
+
+def test_oracle_criterion_index_against_reference_kats():
+    """The numpy oracle's judging index against the reference's criterion_index known answers."""
+    import os
+
+    from _helpers import GOLDEN
+    from oracle import ukf_numpy as O
+
+    d = np.load(os.path.join(GOLDEN, "kat_gating_noisy.npz"))
+    for i in range(int(d["n"])):
+        g = O.criterion_index(d[f"c{i}_x"].reshape(-1, 1), d[f"c{i}_z"].reshape(-1, 1), d[f"c{i}_P"], d[f"c{i}_H"], d[f"c{i}_R"])
+        np.testing.assert_allclose(g, float(d[f"c{i}_gamma"]), rtol=1e-12)

@@ -23,6 +23,7 @@ syn = make_tracks(T, nmax, seed=5, device="cpu", nobs_min=100, dts_choices=(1, 2
 u = HostUKF(H, Q, R, P, gating=gating, packed_cov=True, long_steps=True)
 b = TrackBatch.from_synthetic(syn, substeps=k, need_rows=u.model.rows_needed())
 t0 = time.time(); res = u.run(b); print("emul s", time.time() - t0, "track-steps", b.track_steps())
+print("status counts", res.check_status(raise_on=0))
 
 def one(t):
     m = int(syn.nobs[t])
