@@ -204,5 +204,5 @@ def test_oracle_criterion_index_against_reference_kats():
 
     d = np.load(os.path.join(GOLDEN, "kat_gating_noisy.npz"))
     for i in range(int(d["n"])):
-        g = O.criterion_index(d[f"c{i}_x"].reshape(-1, 1), d[f"c{i}_z"].reshape(-1, 1), d[f"c{i}_P"], d[f"c{i}_H"], d[f"c{i}_R"])
+        g = O.criterion_index(d[f"c{i}_x"], d[f"c{i}_z"], d[f"c{i}_P"], d[f"c{i}_H"], d[f"c{i}_R"])
         np.testing.assert_allclose(g, float(d[f"c{i}_gamma"]), rtol=1e-12)
