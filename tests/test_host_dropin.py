@@ -8,7 +8,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from _helpers import load_golden
+from _helpers import REPO, load_golden
 from ship_track_estimators_b200.cli.argument_parser import create_parser
 from ship_track_estimators_b200.cli.main_cli import _get_input_matrix, get_input_settings
 from ship_track_estimators_b200.ship_track import ShipTrack
@@ -167,3 +167,38 @@ def test_bulk_csv_ingest_on_the_historical_file():
         lat, lon, dts = ShipTrack().read_csv(csv, ship_id=fleet.ids[i], **kw)
         a, b, c = fleet.track(i)
         assert np.array_equal(a, lat) and np.array_equal(b, lon) and np.array_equal(c, dts)
+
+
+def test_reference_import_name_is_an_alias():
+    """`track_estimators` (the reference's import name, pyproject.toml packages) serves the same module
+    objects as ship_track_estimators_b200; the console script entry point exists."""
+    import importlib
+    import subprocess
+    import sys
+
+    code = (
+        "import track_estimators, ship_track_estimators_b200 as impl\n"
+        "from track_estimators.kalman_filters.unscented import UnscentedKalmanFilter\n"
+        "from track_estimators.kalman_filters.non_linear_process import geodetic_dynamics\n"
+        "from track_estimators.kalman_filters.kalman_filter import KalmanFilterBase\n"
+        "from track_estimators.ship_track import ShipTrack\n"
+        "from track_estimators.utils import generate_dts, smooth, haversine_formula, heading\n"
+        "from track_estimators.cli.main_cli import track_estimator\n"
+        "import ship_track_estimators_b200.kalman_filters.unscented as u\n"
+        "assert UnscentedKalmanFilter is u.UnscentedKalmanFilter and issubclass(UnscentedKalmanFilter, KalmanFilterBase)\n"
+        "assert track_estimators.utils is impl.utils if hasattr(impl, 'utils') else True\n"
+        "try:\n"
+        "    import track_estimators.gaussian_processes\n"
+        "except ImportError:\n"
+        "    print('ok')\n"
+    )
+    # a fresh interpreter: other tests may have put the real reference on sys.path under the same name
+    out = subprocess.run([sys.executable, "-c", code], cwd=REPO, capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+    import tomllib
+
+    with open(os.path.join(REPO, "pyproject.toml"), "rb") as fh:
+        meta = tomllib.load(fh)
+    assert meta["project"]["scripts"]["track_estimator"] == "ship_track_estimators_b200.cli.main_cli:track_estimator"
+    mod, fn = meta["project"]["scripts"]["track_estimator"].split(":")
+    assert callable(getattr(importlib.import_module(mod), fn))
