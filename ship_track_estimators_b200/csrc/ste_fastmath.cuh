@@ -41,6 +41,19 @@
 #define STE_LOAD_STREAM(p) (*(p))
 #endif
 
+// A streaming load the compiler may not sink below a later branch (volatile asm): used where a
+// bandwidth-bound loop must have ALL its loads in flight before the first dependent decision.
+#if defined(__CUDA_ARCH__)
+static __device__ __forceinline__ double ste_load_stream_pinned(const double *p) {
+    double v;
+    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+#define STE_LOAD_STREAM_PINNED(p) ste_load_stream_pinned(p)
+#else
+#define STE_LOAD_STREAM_PINNED(p) (*(p))
+#endif
+
 #define STE_PRAGMA_(x) _Pragma(#x)
 #define STE_UNROLL(n) STE_PRAGMA_(unroll n)
 

@@ -735,25 +735,34 @@ STE_DEV void urtss_gain(const double (&xf)[4], const double (&Pf)[10], const dou
 
 // One backward iteration from the statistics the forward pass stored for this step (kStatsPlanes
 // planes at `stats`): no sigma points, no square root - a pseudo-inverse and three small products.
-// What the tape leaves out comes from the filtered covariance and Q (see kStatsPlanes).  `dlt0` is
-// the entry's first plane, already loaded by the caller (NaN = entry invalid, handled there).
-STE_DEV void urtss_step_from_stats(const double (&xf)[4], const double (&Pf)[10], const double dlt0, const double *stats,
-                                   int64_t ld, const double *Q, const double (&e)[4], double (&xs)[4], double (&Ps)[10],
-                                   int &status, const Scratch &sc) {
-    double dlt[4], xb[4], Pb[10], D[16];
-    dlt[0] = dlt0;
+// What the tape leaves out comes from the filtered covariance and Q (see kStatsPlanes).
+// Returns false, with nothing changed, when the entry is marked invalid (delta_0 = NaN: the forward
+// pass's root clamped an eigenvalue at this step); the caller then recomputes the step.  Every load
+// is issued before that decision (pinned loads): the pass is bound by HBM latency and bandwidth, and
+// a load the first branch depends on must not hold back the other 25.
+STE_DEV bool urtss_step_from_stats(const double *mf, const double *cf, bool packed, const double *stats, int64_t ld,
+                                   const double *Q, const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status,
+                                   const Scratch &sc) {
+    double xf[4], Pf[10], dlt[4], xb[4], Pb[10], D[16];
 #pragma unroll
-    for (int r = 1; r < 4; ++r) dlt[r] = STE_LOAD_STREAM(stats + r * ld);
-    Pb[SYM(0, 0)] = STE_LOAD_STREAM(stats + (kStatsPb + 0) * ld);
-    Pb[SYM(0, 1)] = STE_LOAD_STREAM(stats + (kStatsPb + 1) * ld);
-    Pb[SYM(1, 1)] = STE_LOAD_STREAM(stats + (kStatsPb + 2) * ld);
+    for (int r = 0; r < 4; ++r) dlt[r] = STE_LOAD_STREAM_PINNED(stats + r * ld);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int k = 0; k < 3; ++k) Pb[k == 2 ? SYM(1, 1) : k] = STE_LOAD_STREAM_PINNED(stats + (kStatsPb + k) * ld);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) D[q * 4 + r] = STE_LOAD_STREAM(stats + (kStatsD + q * 2 + r) * ld);
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) D[q * 4 + r] = STE_LOAD_STREAM_PINNED(stats + (kStatsD + q * 2 + r) * ld);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xf[r] = STE_LOAD_STREAM_PINNED(mf + r * ld);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = STE_LOAD_STREAM_PINNED(cf + (packed ? SYM(i, j) : i * 4 + j) * ld);
+    if (!(dlt[0] == dlt[0])) return false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int r = 2; r < 4; ++r) D[q * 4 + r] = Pf[SYM(q, r)];
-    }
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -777,6 +786,7 @@ STE_DEV void urtss_step_from_stats(const double (&xf)[4], const double (&Pf)[10]
             K[i * 4 + j] = acc;
         }
     urtss_apply(xf, Pf, xb, Pb, K, xs, Ps, sc);
+    return true;
 }
 
 }  // namespace ste

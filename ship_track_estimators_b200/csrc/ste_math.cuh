@@ -273,7 +273,10 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 // rotation by rotation on its 10 unique entries - 114 FP64 operations per sweep instead of 96 for
 // the accumulation plus 104 for V S V^T, and 32 registers fewer across the sweeps.
 // Anything else - singular, indefinite, slowly converging - goes to the out-of-line finish.
-constexpr double kSqrtSeriesEps2 = 1e-8;     // eps^2 limit of the series finish
+#ifndef STE_SQRT_SERIES_EPS2
+#define STE_SQRT_SERIES_EPS2 1e-8
+#endif
+constexpr double kSqrtSeriesEps2 = STE_SQRT_SERIES_EPS2;     // eps^2 limit of the series finish
 constexpr int kSqrtMaxSweeps = 3;
 constexpr int kSqrtRotSlots = kSqrtMaxSweeps * kSweepSlots;
 
@@ -530,18 +533,20 @@ STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dt
     return t;
 }
 
-// trig of the three offset angles of one root column; takes the short series when all three are small
+// trig of the three offset angles of one root column: the short series, replaced by the full-range
+// evaluation only when an offset is not small (a wide course or latitude spread; written as an
+// overwrite so that the common path carries no merge copies)
 template <bool LIB>
 STE_DEV AngleTrig offset_trig(double dlat_deg, double dcog_deg, double du, double dtR) {
+    if (LIB) return angle_trig<LIB>(dlat_deg, dcog_deg, du, dtR);
     const double ang[3] = {dlat_deg * kDegToRad, dcog_deg * kDegToRad, du * dtR};
-    if (!LIB && fabs(ang[0]) <= kSmallAngle && fabs(ang[1]) <= kSmallAngle && fabs(ang[2]) <= kSmallAngle) {
-        AngleTrig t;
-        double sn[3], cs[3];
-        small_sincos_v<3>(ang, sn, cs);
-        t.sp = sn[0]; t.cp = cs[0]; t.sa = sn[1]; t.ca = cs[1]; t.sd = sn[2]; t.cd = cs[2];
-        return t;
-    }
-    return angle_trig<LIB>(dlat_deg, dcog_deg, du, dtR);
+    AngleTrig t;
+    double sn[3], cs[3];
+    small_sincos_v<3>(ang, sn, cs);
+    t.sp = sn[0]; t.cp = cs[0]; t.sa = sn[1]; t.ca = cs[1]; t.sd = sn[2]; t.cd = cs[2];
+    const bool small = fabs(ang[0]) <= kSmallAngle && fabs(ang[1]) <= kSmallAngle && fabs(ang[2]) <= kSmallAngle;
+    if (__builtin_expect(!small, 0)) t = angle_trig<false>(dlat_deg, dcog_deg, du, dtR);
+    return t;
 }
 
 // trig of (base + off) and (base - off) from the four shared products per angle

@@ -317,9 +317,7 @@ struct BackwardTrack {
     STE_DEV void step(int step) {
         const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
         const double *cf = a.out.cov_f + ((int64_t)step * cov_planes(packed)) * ld + t;
-        double xf[4], xs[4], Ps[10];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xf[r] = mf[r * ld];
+        double xs[4], Ps[10];
         double e[4] = {0.0, 0.0, 0.0, 0.0};
         if (a.in.noise_bwd) {
 #pragma unroll
@@ -327,18 +325,13 @@ struct BackwardTrack {
                 e[r] = a.in.noise_bwd[((int64_t)step * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
         bool done = false;
-        if (use_stats && step > 0) {
-            const double *st = a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t;
-            const double dlt0 = STE_LOAD_STREAM(st);
-            if (dlt0 == dlt0) {   // NaN: the forward pass's root clamped an eigenvalue at this step; recompute it below
-                double Pf[10];
-                load_cov(cf, ld, packed, Pf);
-                urtss_step_from_stats(xf, Pf, dlt0, st, ld, a.prob.Q, e, xs, Ps, status, sc);
-                done = true;
-            }
-        }
+        if (use_stats && step > 0)
+            done = urtss_step_from_stats(mf, cf, packed, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, a.prob.Q,
+                                         e, xs, Ps, status, sc);
         if (!done) {
-            double s1[4], Pb[10];
+            double xf[4], s1[4], Pb[10];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) xf[r] = mf[r * ld];
             const double dt = a.in.dt[(int64_t)step * ld + t];
             const int ri = min_(step / rep, a.prob.max_obs - 1);
             const double sr = a.in.sog_rate[(int64_t)ri * ld + t];

@@ -91,7 +91,7 @@ def test_gating_known_answers(cuda, native_lib):
     rows = np.load(__import__("os").path.join(__import__("_helpers").GOLDEN, "kat_gating.npz"))["rows"]
     for d, iters, lam, scale in rows:
         g = UnscentedKalmanFilter(H=np.diag([1.0, 1, 0, 0]), R=np.diag([0.25, 0.25, 0, 0]), P=np.diag([0.3, 0.3, 1, 1]),
-                                  x0=np.array([10.0, 20, 12, 90]))
+                                  x0=np.array([10.0, 20, 12, 90]), noise="zero")   # the known answers are noise-free
         Rs = g.check_robustness(np.array([10.0 + d, 20.0 - d, 12, 90]), g.P, g.R)
         assert g.last_gate["iterations"] == int(iters)
         assert abs(g.last_gate["lambda_factor"] - lam) <= 1e-9 * lam

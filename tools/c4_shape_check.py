@@ -19,7 +19,7 @@ nmax = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
 gating = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
 k = 2
 H = np.diag([1.0, 1, 0, 0]); R = np.diag([1e-3, 1e-3, 0, 0]); Q = np.diag([1e-2, 1e-2, 1e-4, 1e-4]); P = np.eye(4)
-syn = make_tracks(T, nmax, seed=5, device="cpu", nobs_min=100, dts_choices=(1, 2, 3, 6, 12, 24), outlier_frac=0.01, smooth_width=2)
+syn = make_tracks(T, nmax, seed=int(os.environ.get("SEED", "5")), device="cpu", nobs_min=100, dts_choices=(1, 2, 3, 6, 12, 24), outlier_frac=0.01, smooth_width=2)
 u = HostUKF(H, Q, R, P, gating=gating, packed_cov=True, long_steps=True)
 b = TrackBatch.from_synthetic(syn, substeps=k, need_rows=u.model.rows_needed())
 t0 = time.time(); res = u.run(b); print("emul s", time.time() - t0, "track-steps", b.track_steps())
