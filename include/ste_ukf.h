@@ -80,7 +80,7 @@ typedef struct SteProblem {
                            /* per-track array is NULL (unscented.py:287-292)                */
     uint32_t flags;        /* STE_FLAG_*                                                    */
     int32_t gate_max_iter; /* cap on robustification iterations (reference: unbounded)      */
-    int32_t reserved;
+    int32_t reserved;      /* must be 0                                                     */
     int64_t ld;            /* leading dimension of every SoA array (>= n_tracks)            */
     double gate_chi;       /* chi_alpha, reference value 50 (unscented.py:357)              */
     double H[16];
@@ -164,6 +164,27 @@ int ste_ukf_predict_f64(const SteProblem *prob, double *x, double *P, const doub
 int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const double *z,
                        const double *noise, uint8_t *gate_iters, double *gate_lambda,
                        double *gate_scale, int32_t *status, void *stream);
+
+/* Dimension-generic single steps: the reference's class takes n from H (unscented.py:52-62) and any process
+ * callable; these entry points serve that surface for n <= 8 and the process models the library ships.
+ *   STE_MODEL_GEODETIC        n = 4  geodetic_dynamics, rates from the sog_rate / cog_rate arguments
+ *   STE_MODEL_GEODETIC_RATES  n = 6  [lon, lat, sog, cog, sog_rate, cog_rate]: the geodetic step driven by the
+ *                                    state's own rates, which persist (the argument arrays are ignored, may be NULL)
+ * H, Q, R are HOST pointers to row-major n x n matrices (they travel in the kernel parameters).
+ * ste_ukf_predict_n_f64: UnscentedKalmanFilter.predict (unscented.py:144-207): x [n][ld], P [n*n][ld] in place;
+ *   dt [T]; noise [n][ld] unit normals or NULL; sigma_prior / sigma_post [n*(2n+1)][ld] or NULL; status [T] or NULL.
+ * ste_ukf_update_n_f64: UnscentedKalmanFilter.update (unscented.py:209-265) with dense H and R; state index 3 is
+ *   the heading (innovation wrapped to [-180, 180), state taken modulo 360) as the reference hard-codes (:250, 257).
+ * ste_process_f64: one evaluation of the process model for T states, x_in / x_out [n][ld]. */
+#define STE_MODEL_GEODETIC 0
+#define STE_MODEL_GEODETIC_RATES 1
+int ste_ukf_predict_n_f64(int32_t n, int32_t model, int32_t n_tracks, int64_t ld, const double *Q_host, double *x, double *P,
+                          const double *dt, const double *sog_rate, const double *cog_rate, const double *noise,
+                          double *sigma_prior, double *sigma_post, int32_t *status, void *stream);
+int ste_ukf_update_n_f64(int32_t n, int32_t n_tracks, int64_t ld, const double *H_host, const double *R_host, double *x,
+                         double *P, const double *z, const double *noise, int32_t *status, void *stream);
+int ste_process_f64(int32_t model, int32_t n, int32_t n_tracks, int64_t ld, const double *x_in, const double *dt,
+                    const double *sog_rate, const double *cog_rate, double *x_out, void *stream);
 
 /* UnscentedKalmanFilter.criterion_index and the denominator of update_lambda_factor
  * (unscented.py:389-483) for T filters: with y = z - x (not z - Hx, no angle wrap) and

@@ -24,6 +24,7 @@ STE_STATUS_RANK_DEFICIENT = 0x10
 STE_STATUS_SMOOTH_RECOMPUTE = 0x100
 STATS_PLANES = 15
 STE_GEODESY_SPHERE, STE_GEODESY_WGS84 = 0, 1
+STE_MODEL_GEODETIC, STE_MODEL_GEODETIC_RATES = 0, 1
 
 _dptr = C.c_void_p  # device pointers travel as plain integers
 
@@ -95,6 +96,9 @@ _PROTOTYPES = {
     "ste_ukf_fused_f64": (C.c_int, [C.POINTER(SteProblem), C.POINTER(SteInputs), C.POINTER(SteOutputs)] * 2 + [C.c_void_p]),
     "ste_ukf_predict_f64": (C.c_int, [C.POINTER(SteProblem)] + [_dptr] * 9 + [C.c_void_p]),
     "ste_ukf_update_f64": (C.c_int, [C.POINTER(SteProblem)] + [_dptr] * 8 + [C.c_void_p]),
+    "ste_ukf_predict_n_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_double)] + [_dptr] * 9 + [C.c_void_p]),
+    "ste_ukf_update_n_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)] + [_dptr] * 5 + [C.c_void_p]),
+    "ste_process_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [_dptr] * 5 + [C.c_void_p]),
     "ste_gate_terms_f64": (C.c_int, [C.POINTER(SteProblem)] + [_dptr] * 5 + [C.c_void_p]),
     "ste_sigma_points_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_double, _dptr, _dptr, _dptr, _dptr, C.c_void_p]),
     "ste_geodetic_f64": (C.c_int, [C.c_int32, C.c_int64, _dptr, _dptr, _dptr, _dptr, _dptr, C.c_void_p]),

@@ -737,12 +737,14 @@ STE_DEV void urtss_gain(const double (&xf)[4], const double (&Pf)[10], const dou
 // planes at `stats`): no sigma points, no square root - a pseudo-inverse and three small products.
 // What the tape leaves out comes from the filtered covariance and Q (see kStatsPlanes).
 // Returns false, with nothing changed, when the entry is marked invalid (delta_0 = NaN: the forward
-// pass's root clamped an eigenvalue at this step); the caller then recomputes the step.  Every load
-// is issued before that decision (pinned loads): the pass is bound by HBM latency and bandwidth, and
-// a load the first branch depends on must not hold back the other 25.
+// pass's root clamped an eigenvalue at this step); the caller then recomputes the step.
+// The pass is bound by HBM latency and bandwidth, so all 29 loads of a step must be in flight
+// before that first decision; left alone, ptxas sinks the other 28 below the branch on delta_0
+// (measured: +10 % run time).  The decision is therefore made to depend on every loaded word
+// through `guard`, a run-time zero the compiler cannot see through (SteProblem.reserved).
 STE_DEV bool urtss_step_from_stats(const double *mf, const double *cf, bool packed, const double *stats, int64_t ld,
                                    const double *Q, const double (&e)[4], double (&xs)[4], double (&Ps)[10], int &status,
-                                   const Scratch &sc) {
+                                   const Scratch &sc, const unsigned guard) {
     double xf[4], Pf[10], dlt[4], xb[4], Pb[10], D[16];
 #pragma unroll
     for (int r = 0; r < 4; ++r) dlt[r] = STE_LOAD_STREAM_PINNED(stats + r * ld);
@@ -758,7 +760,15 @@ STE_DEV bool urtss_step_from_stats(const double *mf, const double *cf, bool pack
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = i; j < 4; ++j) Pf[SYM(i, j)] = STE_LOAD_STREAM_PINNED(cf + (packed ? SYM(i, j) : i * 4 + j) * ld);
-    if (!(dlt[0] == dlt[0])) return false;
+    unsigned seen = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) seen |= (unsigned)(f64_bits(dlt[r]) >> 32) | (unsigned)(f64_bits(xf[r]) >> 32);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) seen |= (unsigned)(f64_bits(Pf[k]) >> 32);
+    seen |= (unsigned)(f64_bits(Pb[SYM(0, 0)]) >> 32) | (unsigned)(f64_bits(Pb[SYM(0, 1)]) >> 32) | (unsigned)(f64_bits(Pb[SYM(1, 1)]) >> 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) seen |= (unsigned)(f64_bits(D[q * 4]) >> 32) | (unsigned)(f64_bits(D[q * 4 + 1]) >> 32);
+    if (!(dlt[0] == dlt[0]) || (seen & guard) != 0u) return false;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll

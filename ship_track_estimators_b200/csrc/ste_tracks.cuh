@@ -327,7 +327,7 @@ struct BackwardTrack {
         bool done = false;
         if (use_stats && step > 0)
             done = urtss_step_from_stats(mf, cf, packed, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, a.prob.Q,
-                                         e, xs, Ps, status, sc);
+                                         e, xs, Ps, status, sc, (unsigned)a.prob.reserved);
         if (!done) {
             double xf[4], s1[4], Pb[10];
 #pragma unroll

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "ste_tracks.cuh"
+#include "ste_generic.cuh"
 
 namespace ste {
 
@@ -444,6 +445,32 @@ __global__ void __launch_bounds__(kThreads) derive_inputs_kernel(int T, int max_
     }
 }
 
+// ------------------------------------------------------------------------------------------ //
+// Dimension-generic single steps (ste_generic.cuh): the class API for n != 4 / other process models.
+// ------------------------------------------------------------------------------------------ //
+__global__ void __launch_bounds__(64) ukf_predict_n_kernel(const __grid_constant__ ProblemN p, double *x, double *P, const double *dt,
+                                                            const double *sog_rate, const double *cog_rate, const double *noise,
+                                                            double *sigma_prior, double *sigma_post, int32_t *status) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.n_tracks) predict_n(p, t, x, P, dt, sog_rate, cog_rate, noise, sigma_prior, sigma_post, status);
+}
+
+__global__ void __launch_bounds__(64) ukf_update_n_kernel(const __grid_constant__ ProblemN p, double *x, double *P, const double *z,
+                                                           const double *noise, int32_t *status) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.n_tracks) update_n(p, t, x, P, z, noise, status);
+}
+
+__global__ void __launch_bounds__(64) process_n_kernel(int model, int n, int T, int64_t ld, const double *xin, const double *dt,
+                                                        const double *sog_rate, const double *cog_rate, double *xout) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double x[kMaxN], y[kMaxN];
+    for (int r = 0; r < n; ++r) x[r] = xin[r * ld + t];
+    process_n(model, n, x, dt[t], sog_rate ? sog_rate[t] : 0.0, cog_rate ? cog_rate[t] : 0.0, y);
+    for (int r = 0; r < n; ++r) xout[r * ld + t] = y[r];
+}
+
 // accuracy probe for ste_fastmath.cuh (tests only): out0/out1 = f(a, b)
 __global__ void fastmath_probe_kernel(int kind, int n, const double *a, const double *b, double *out0, double *out1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -707,6 +734,53 @@ int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const doubl
         else ukf_update_kernel<false, false><<<grid, block, 0, s>>>(a);
     }
     return check_launch("ukf_update_kernel");
+}
+
+static int model_dim_ok(int32_t n, int32_t model) {
+    if (n < 1 || n > kMaxN) return fail(STE_ERR_UNSUPPORTED, "generic steps: 1 <= n <= 8");
+    if (model == STE_MODEL_GEODETIC && n != 4) return fail(STE_ERR_UNSUPPORTED, "geodetic_dynamics has n = 4");
+    if (model == STE_MODEL_GEODETIC_RATES && n != 6) return fail(STE_ERR_UNSUPPORTED, "geodetic_dynamics_rates has n = 6");
+    if (model != STE_MODEL_GEODETIC && model != STE_MODEL_GEODETIC_RATES) return fail(STE_ERR_UNSUPPORTED, "unknown process model");
+    return STE_OK;
+}
+
+int ste_ukf_predict_n_f64(int32_t n, int32_t model, int32_t n_tracks, int64_t ld, const double *Q_host, double *x, double *P,
+                          const double *dt, const double *sog_rate, const double *cog_rate, const double *noise, double *sigma_prior,
+                          double *sigma_post, int32_t *status, void *stream) {
+    if (int rc = model_dim_ok(n, model)) return rc;
+    if (n_tracks < 0 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / ld");
+    if (!Q_host || !x || !P || !dt) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if ((sigma_prior == nullptr) != (sigma_post == nullptr)) return fail(STE_ERR_INVALID_ARG, "sigma_prior and sigma_post must be given together");
+    if (n_tracks == 0) return STE_OK;
+    ProblemN p{};
+    p.n = n; p.model = model; p.n_tracks = n_tracks; p.ld = ld;
+    memcpy(p.Q, Q_host, sizeof(double) * n * n);
+    ukf_predict_n_kernel<<<(n_tracks + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, x, P, dt, sog_rate, cog_rate, noise, sigma_prior, sigma_post, status);
+    return check_launch("ukf_predict_n_kernel");
+}
+
+int ste_ukf_update_n_f64(int32_t n, int32_t n_tracks, int64_t ld, const double *H_host, const double *R_host, double *x, double *P,
+                         const double *z, const double *noise, int32_t *status, void *stream) {
+    if (n < 1 || n > kMaxN) return fail(STE_ERR_UNSUPPORTED, "generic steps: 1 <= n <= 8");
+    if (n_tracks < 0 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / ld");
+    if (!H_host || !R_host || !x || !P || !z) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if (n_tracks == 0) return STE_OK;
+    ProblemN p{};
+    p.n = n; p.n_tracks = n_tracks; p.ld = ld;
+    memcpy(p.H, H_host, sizeof(double) * n * n);
+    memcpy(p.R, R_host, sizeof(double) * n * n);
+    ukf_update_n_kernel<<<(n_tracks + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, x, P, z, noise, status);
+    return check_launch("ukf_update_n_kernel");
+}
+
+int ste_process_f64(int32_t model, int32_t n, int32_t n_tracks, int64_t ld, const double *x_in, const double *dt,
+                    const double *sog_rate, const double *cog_rate, double *x_out, void *stream) {
+    if (int rc = model_dim_ok(n, model)) return rc;
+    if (n_tracks < 0 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / ld");
+    if (!x_in || !dt || !x_out) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if (n_tracks == 0) return STE_OK;
+    process_n_kernel<<<(n_tracks + 63) / 64, 64, 0, (cudaStream_t)stream>>>(model, n, n_tracks, ld, x_in, dt, sog_rate, cog_rate, x_out);
+    return check_launch("process_n_kernel");
 }
 
 int ste_gate_terms_f64(const SteProblem *prob, const double *x, const double *P, const double *z, double *gamma, double *denom,
