@@ -32,8 +32,9 @@
 extern "C" {
 #endif
 
-#define STE_ABI_VERSION 3   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
+#define STE_ABI_VERSION 4   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
                             /* 3: smooth_stats holds STE_STATS_PLANES = 15 planes per step (was 30)                                          */
+                            /* 4: SteInputs.R_tracks, dimension-generic steps (ste_ukf_*_n_f64, ste_process_f64), ste_gate_terms_f64          */
 #define STE_STATS_PLANES 15
 #define STE_DIM 4
 #define STE_NSIGMA 9
@@ -108,6 +109,9 @@ typedef struct SteInputs {
     const double *noise_pred; /* [max_steps][4][ld]  unscented.py:198-202                        */
     const double *noise_upd;  /* [max_obs][4][ld]    unscented.py:232-236, row = update index    */
     const double *noise_bwd;  /* [max_steps][4][ld]  unscented.py:320-323, row = backward step   */
+    const double *R_tracks;   /* [16][ld] per-track measurement covariance (row-major 4x4 planes,  */
+                              /* symmetric), or NULL -> SteProblem.R for every track.  Needs the   */
+                              /* generic update: set STE_FLAG_FORCE_GENERIC (ABI 4)                */
 } SteInputs;
 
 typedef struct SteOutputs {
@@ -168,8 +172,9 @@ int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const doubl
 /* Dimension-generic single steps: the reference's class takes n from H (unscented.py:52-62) and any process
  * callable; these entry points serve that surface for n <= 8 and the process models the library ships.
  *   STE_MODEL_GEODETIC        n = 4  geodetic_dynamics, rates from the sog_rate / cog_rate arguments
- *   STE_MODEL_GEODETIC_RATES  n = 6  [lon, lat, sog, cog, sog_rate, cog_rate]: the geodetic step driven by the
- *                                    state's own rates, which persist (the argument arrays are ignored, may be NULL)
+ *   STE_MODEL_GEODETIC_TURN   n = 5  [lon, lat, sog, cog, cog_rate]: the geodetic step with the turn rate taken from
+ *                                    the state, where it persists (the cog_rate argument is ignored, may be NULL)
+ * (the reference's default weight W0 = 1 - n/3 must lie in (-1, 1), unscented.py:125-129: its class runs n <= 5)
  * H, Q, R are HOST pointers to row-major n x n matrices (they travel in the kernel parameters).
  * ste_ukf_predict_n_f64: UnscentedKalmanFilter.predict (unscented.py:144-207): x [n][ld], P [n*n][ld] in place;
  *   dt [T]; noise [n][ld] unit normals or NULL; sigma_prior / sigma_post [n*(2n+1)][ld] or NULL; status [T] or NULL.
@@ -177,7 +182,7 @@ int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const doubl
  *   the heading (innovation wrapped to [-180, 180), state taken modulo 360) as the reference hard-codes (:250, 257).
  * ste_process_f64: one evaluation of the process model for T states, x_in / x_out [n][ld]. */
 #define STE_MODEL_GEODETIC 0
-#define STE_MODEL_GEODETIC_RATES 1
+#define STE_MODEL_GEODETIC_TURN 1
 int ste_ukf_predict_n_f64(int32_t n, int32_t model, int32_t n_tracks, int64_t ld, const double *Q_host, double *x, double *P,
                           const double *dt, const double *sog_rate, const double *cog_rate, const double *noise,
                           double *sigma_prior, double *sigma_post, int32_t *status, void *stream);

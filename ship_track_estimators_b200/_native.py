@@ -13,7 +13,7 @@ from typing import Optional
 from . import build as _build
 
 # --- mirror of include/ste_ukf.h ------------------------------------------------------------ #
-STE_ABI_VERSION = 3
+STE_ABI_VERSION = 4
 STE_OK, STE_ERR_INVALID_ARG, STE_ERR_CUDA, STE_ERR_UNSUPPORTED = 0, -1, -2, -3
 STE_FLAG_GATING, STE_FLAG_FORCE_GENERIC, STE_FLAG_PACKED_COV, STE_FLAG_LONG_STEPS = 0x1, 0x2, 0x4, 0x8
 STE_STATUS_NONFINITE = 0x1
@@ -24,7 +24,7 @@ STE_STATUS_RANK_DEFICIENT = 0x10
 STE_STATUS_SMOOTH_RECOMPUTE = 0x100
 STATS_PLANES = 15
 STE_GEODESY_SPHERE, STE_GEODESY_WGS84 = 0, 1
-STE_MODEL_GEODETIC, STE_MODEL_GEODETIC_RATES = 0, 1
+STE_MODEL_GEODETIC, STE_MODEL_GEODETIC_TURN = 0, 1
 
 _dptr = C.c_void_p  # device pointers travel as plain integers
 
@@ -62,6 +62,7 @@ class SteInputs(C.Structure):
         ("noise_pred", _dptr),
         ("noise_upd", _dptr),
         ("noise_bwd", _dptr),
+        ("R_tracks", _dptr),
     ]
 
 

@@ -102,6 +102,7 @@ class TrackBatch:
     substeps: int = 1
     rate_repeat_all: int = 1
     P0: Optional[torch.Tensor] = None  # [16][T] per-track prior covariance
+    R: Optional[torch.Tensor] = None  # [16][T] per-track measurement covariance (ships with different sensors)
     noise_pred: Optional[torch.Tensor] = None  # [max_steps][4][T] unit normals
     noise_upd: Optional[torch.Tensor] = None  # [max_obs][4][T]
     noise_bwd: Optional[torch.Tensor] = None  # [max_steps][4][T]
@@ -143,7 +144,7 @@ class TrackBatch:
         expect += [("x0", self.x0, (4, T), f64), ("dt", self.dt, (N, T), f64), ("sog_rate", self.sog_rate, (M, T), f64),
                    ("cog_rate", self.cog_rate, (M, T), f64), ("upd_mask", self.upd_mask, (N, T), torch.uint8),
                    ("n_steps", self.n_steps, (T,), torch.int32), ("rate_repeat", self.rate_repeat, (T,), torch.int32),
-                   ("P0", self.P0, (16, T), f64), ("noise_pred", self.noise_pred, (N, 4, T), f64),
+                   ("P0", self.P0, (16, T), f64), ("R", self.R, (16, T), f64), ("noise_pred", self.noise_pred, (N, 4, T), f64),
                    ("noise_upd", self.noise_upd, (M, 4, T), f64), ("noise_bwd", self.noise_bwd, (N, 4, T), f64)]
         expect += [(f"z[{r}]", zr, (M, T), f64) for r, zr in enumerate(self.z)]
         for name, t, shape, dtype in expect:
@@ -184,7 +185,7 @@ class TrackBatch:
         total = int(valid.sum())
         return float(((km > limit_km) & valid).sum()) / total if total else 0.0
 
-    _TENSORS = ("x0", "dt", "sog_rate", "cog_rate", "upd_mask", "n_steps", "rate_repeat", "P0",
+    _TENSORS = ("x0", "dt", "sog_rate", "cog_rate", "upd_mask", "n_steps", "rate_repeat", "P0", "R",
                 "noise_pred", "noise_upd", "noise_bwd")
 
     def _map(self, fn) -> "TrackBatch":
@@ -268,6 +269,7 @@ class TrackBatch:
         noise: Optional[Sequence[Optional[Dict[str, np.ndarray]]]] = None,
         smoother: bool = True,
         sort_by_length: bool = True,
+        R: Optional[Sequence[np.ndarray]] = None,
     ):
         """Pack ``ShipTrack``-like objects (attributes ``dts, z, sog_rate, cog_rate``) with their step
         grids ``dt_arrays`` (what ``run(nsteps, dt, ship_track)`` receives).
@@ -276,7 +278,8 @@ class TrackBatch:
         lengths keep the caller's order): the threads of a warp then finish together and a tile runs
         as long as its work, not as its longest track times its width.  ``TrackBatch.order`` records
         the permutation and ``TrackResults.track(i)`` undoes it - ``i`` is always the caller's index,
-        and every track's numbers are bit-identical to the unsorted packing.
+        and every track's numbers are bit-identical to the unsorted packing.  ``R``: one symmetric
+        4 x 4 measurement covariance per track (instead of the filter's shared one).
 
         Raises ``IndexError`` where the reference would: more matched observation times than
         observations (``kalman_filter.py:101-108``) or a smoother rate index past the repeated rate
@@ -294,6 +297,7 @@ class TrackBatch:
             dt_arrays = [dt_arrays[j] for j in order]
             x0 = None if x0 is None else [x0[j] for j in order]
             noise = None if noise is None else [noise[j] for j in order]
+            R = None if R is None else [R[j] for j in order]
         nsteps = np.array([len(d) for d in dt_arrays], dtype=np.int32)
         nobs = np.array([np.asarray(tr.z).shape[1] for tr in tracks], dtype=np.int32)
         N, M = int(nsteps.max()), int(nobs.max())
@@ -331,6 +335,11 @@ class TrackBatch:
             return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
         kw = {}
+        if R is not None:
+            Rt = np.stack([_as44("R", Ri) for Ri in R], axis=-1).reshape(16, T)
+            if not np.array_equal(Rt.reshape(4, 4, T), Rt.reshape(4, 4, T).transpose(1, 0, 2)):
+                raise NotImplementedError("per-track R must be symmetric for the CUDA path")
+            kw["R"] = up(Rt)
         if noise is not None:
             npred = np.zeros((max(N, 1), 4, T))
             nupd = np.zeros((M, 4, T))
@@ -344,7 +353,7 @@ class TrackBatch:
                     nupd[: len(nz["upd"]), :, i] = nz["upd"]
                 if "bwd" in nz and nz["bwd"] is not None:
                     nbwd[: nsteps[i], :, i] = nz["bwd"]
-            kw = dict(noise_pred=up(npred), noise_upd=up(nupd), noise_bwd=up(nbwd))
+            kw.update(noise_pred=up(npred), noise_upd=up(nupd), noise_bwd=up(nbwd))
         return cls(
             x0=up(x0a), dt=up(dt), sog_rate=up(sr), cog_rate=up(cr), z=[up(z[r]) for r in range(4)],
             upd_mask=up(mask), n_steps=up(nsteps), rate_repeat=up(rep), substeps=1, rate_repeat_all=1,
@@ -481,7 +490,7 @@ class BatchedUKF:
     """
 
     def __init__(self, H, Q=None, R=None, P=None, *, gating=False, gate_chi=50.0, gate_max_iter=100, force_generic=False,
-                 packed_cov=False, long_steps=None):
+                 packed_cov=False, long_steps=None, measurement_model=None):
         if H is None:
             raise ValueError("Set proper system dynamics.")  # reference unscented.py:52-53
         eye = np.eye(4)
@@ -490,6 +499,12 @@ class BatchedUKF:
             gating=gating, gate_chi=gate_chi, gate_max_iter=gate_max_iter, force_generic=force_generic,
         )
         self._lib = nat.load()
+        # named element-wise transform of the observations before every update (reference unscented.py:221-225)
+        from .measurement_models import MEASUREMENT_MODELS
+        if measurement_model is not None and measurement_model not in MEASUREMENT_MODELS.values():
+            raise NotImplementedError("measurement_model must be one of ship_track_estimators_b200.measurement_models."
+                                      f"{sorted(MEASUREMENT_MODELS)} (arbitrary callables cannot run inside the kernels)")
+        self.measurement_model = measurement_model
         # store the 10 unique covariance entries per state instead of the full 4x4 (30 % less state
         # traffic, memory and PCIe volume; TrackResults.track() expands them back)
         self.packed_cov = bool(packed_cov)
@@ -508,7 +523,7 @@ class BatchedUKF:
         p = nat.SteProblem()
         p.n_tracks, p.max_steps, p.max_obs = b.n_tracks, b.max_steps, b.max_obs
         p.substeps, p.rate_repeat = int(b.substeps), int(b.rate_repeat_all)
-        p.flags = ((nat.STE_FLAG_GATING if m.gating else 0) | (nat.STE_FLAG_FORCE_GENERIC if m.force_generic else 0)
+        p.flags = ((nat.STE_FLAG_GATING if m.gating else 0) | (nat.STE_FLAG_FORCE_GENERIC if (m.force_generic or b.R is not None) else 0)
                    | (nat.STE_FLAG_PACKED_COV if self.packed_cov else 0) | (nat.STE_FLAG_LONG_STEPS if self._long_steps_for(b) else 0))
         p.gate_max_iter, p.gate_chi = int(m.gate_max_iter), float(m.gate_chi)
         p.ld = b.n_tracks
@@ -526,13 +541,20 @@ class BatchedUKF:
         lo, hi = self.LONG_STEP_MIX
         return lo < b.long_step_fraction() <= hi
 
-    @staticmethod
-    def _inputs(b: TrackBatch) -> nat.SteInputs:
+    def _inputs(self, b: TrackBatch) -> nat.SteInputs:
         i = nat.SteInputs()
         i.x0, i.P0, i.dt = nat.ptr(b.x0), nat.ptr(b.P0), nat.ptr(b.dt)
         i.upd_mask, i.n_steps = nat.ptr(b.upd_mask), nat.ptr(b.n_steps)
+        rows = b.z
+        if self.measurement_model is not None:
+            cached = getattr(b, "_z_model", None)
+            if cached is None or cached[0] is not self.measurement_model:
+                from .measurement_models import apply_rows
+                cached = b._z_model = (self.measurement_model, apply_rows(self.measurement_model, b.z))
+            rows = cached[1]
+        i.R_tracks = nat.ptr(b.R)
         for r in range(4):
-            i.z[r] = nat.ptr(b.z[r])
+            i.z[r] = nat.ptr(rows[r])
         i.sog_rate, i.cog_rate, i.rate_repeat = nat.ptr(b.sog_rate), nat.ptr(b.cog_rate), nat.ptr(b.rate_repeat)
         i.noise_pred, i.noise_upd, i.noise_bwd = nat.ptr(b.noise_pred), nat.ptr(b.noise_upd), nat.ptr(b.noise_bwd)
         return i
@@ -575,7 +597,8 @@ class BatchedUKF:
         return o
 
     def _check_rows(self, b: TrackBatch):
-        for r, need in enumerate(self.model.rows_needed()):
+        need_rows = [True] * 4 if b.R is not None else self.model.rows_needed()
+        for r, need in enumerate(need_rows):
             if need and b.z[r] is None:
                 raise ValueError(f"observation row {r} is referenced by H/R but absent from the batch")
 

@@ -16,10 +16,11 @@ constexpr int kMaxL = 2 * kMaxN + 1;
 
 // process models selectable on the device (SteProblemN.model)
 //   0  geodetic_dynamics        n = 4: [lon, lat, sog, cog], rates from the call's arguments
-//   1  geodetic_dynamics_rates  n = 6: [lon, lat, sog, cog, sog_rate, cog_rate], rates are states
+//   1  geodetic_dynamics_turn   n = 5: [lon, lat, sog, cog, cog_rate], the turn rate is a state that persists
+// (the reference's default weights W0 = 1 - n/3 must lie in (-1, 1), unscented.py:125-129, so its class runs n <= 5)
 STE_DEV void process_n(int model, int n, const double *x, double dt, double sog_rate, double cog_rate, double *y) {
     double x4[4] = {x[0], x[1], x[2], x[3]}, y4[4];
-    const double sr = model == 1 ? x[4] : sog_rate, cr = model == 1 ? x[5] : cog_rate;
+    const double sr = sog_rate, cr = model == 1 ? x[4] : cog_rate;
     geodetic_step(x4, dt, dt / kEarthRadiusKm, sr, cr, y4);
     for (int r = 0; r < 4; ++r) y[r] = y4[r];
     for (int r = 4; r < n; ++r) y[r] = x[r];

@@ -134,7 +134,18 @@ struct ForwardTrack {
     }
 
     STE_DEV void assimilate(int u) {
-        const Model model{a.prob.H, a.prob.Q, a.prob.R};
+        // a per-track measurement covariance (SteInputs.R_tracks: ships with different sensors) replaces the
+        // shared R; only the generic update reads a full 4x4 R
+        const double *Rp = a.prob.R;
+        double Rt[16];
+        if constexpr (!POS_ONLY) {
+            if (a.in.R_tracks) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) Rt[k] = a.in.R_tracks[k * ld + t];
+                Rp = Rt;
+            }
+        }
+        const Model model{a.prob.H, a.prob.Q, Rp};
         double z[4], un[4];
         stage_wait();
 #pragma unroll

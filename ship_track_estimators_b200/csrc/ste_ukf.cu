@@ -604,8 +604,10 @@ static int validate_forward(const SteProblem *prob, const SteInputs *in, const S
         return fail(STE_ERR_UNSUPPORTED, "gating draws a data-dependent number of normals; only zero measurement noise is supported with it");
     if (gating && prob->gate_max_iter < 1) return fail(STE_ERR_INVALID_ARG, "gate_max_iter < 1");
     const bool pos = position_only(*prob);
+    if (in->R_tracks && pos)
+        return fail(STE_ERR_INVALID_ARG, "a per-track R (SteInputs.R_tracks) needs the generic update: set STE_FLAG_FORCE_GENERIC");
     for (int r = 0; r < 4; ++r) {
-        bool used = gating;  // generic gating: y = z - x touches every row
+        bool used = gating || in->R_tracks != nullptr;  // generic gating: y = z - x touches every row
         for (int j = 0; j < 4; ++j) used |= prob->H[r * 4 + j] != 0.0 || prob->R[r * 4 + j] != 0.0;
         if (pos) used = r < 2;  // rows 2, 3 only ever multiply exact zeros of pinv(S)
         if (used && !in->z[r]) return fail(STE_ERR_INVALID_ARG, "observation row referenced by H/R is NULL");
@@ -739,8 +741,8 @@ int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const doubl
 static int model_dim_ok(int32_t n, int32_t model) {
     if (n < 1 || n > kMaxN) return fail(STE_ERR_UNSUPPORTED, "generic steps: 1 <= n <= 8");
     if (model == STE_MODEL_GEODETIC && n != 4) return fail(STE_ERR_UNSUPPORTED, "geodetic_dynamics has n = 4");
-    if (model == STE_MODEL_GEODETIC_RATES && n != 6) return fail(STE_ERR_UNSUPPORTED, "geodetic_dynamics_rates has n = 6");
-    if (model != STE_MODEL_GEODETIC && model != STE_MODEL_GEODETIC_RATES) return fail(STE_ERR_UNSUPPORTED, "unknown process model");
+    if (model == STE_MODEL_GEODETIC_TURN && n != 5) return fail(STE_ERR_UNSUPPORTED, "geodetic_dynamics_turn has n = 5");
+    if (model != STE_MODEL_GEODETIC && model != STE_MODEL_GEODETIC_TURN) return fail(STE_ERR_UNSUPPORTED, "unknown process model");
     return STE_OK;
 }
 

@@ -23,7 +23,7 @@ from typing import Callable, Optional
 import numpy as np
 
 from .kalman_filter import KalmanFilterBase
-from .non_linear_process import geodetic_dynamics
+from .non_linear_process import DEVICE_MODELS, geodetic_dynamics
 
 
 def _unit_normals(rows: int, n: int) -> np.ndarray:
@@ -92,24 +92,40 @@ class UnscentedKalmanFilter(KalmanFilterBase):
             )
 
     def _resolve_process(self, non_linear_process):
+        """-> (device model id, state dimension) of a process callable the CUDA path can run."""
         if non_linear_process is None:
             assert self.non_linear_process is not None, "Non-linear process is not set."
             non_linear_process = self.non_linear_process
         assert callable(non_linear_process), "Non-linear process model must be callable."
-        if non_linear_process is not geodetic_dynamics:
+        if non_linear_process not in DEVICE_MODELS:
             raise NotImplementedError(
-                "the CUDA path fuses the geodetic process model; pass "
-                "ship_track_estimators_b200.kalman_filters.non_linear_process.geodetic_dynamics"
+                "arbitrary Python callables cannot run inside a kernel; the CUDA path runs the process models of "
+                "ship_track_estimators_b200.kalman_filters.non_linear_process: geodetic_dynamics (n = 4) and "
+                "geodetic_dynamics_turn (n = 5)"
             )
-        return non_linear_process
+        model, n = DEVICE_MODELS[non_linear_process]
+        if n != self.n:
+            raise ValueError(f"{non_linear_process.__name__} propagates {n} states, this filter has n = {self.n}")
+        return model, n
+
+    def _apply_measurement_model(self, z):
+        """``z = self.measurement_model(z)`` (reference ``:221-225``) for the named models of
+        :mod:`ship_track_estimators_b200.measurement_models`."""
+        if self.measurement_model is None:
+            return z
+        assert callable(self.measurement_model), "Measurement model must be callable."
+        from ..measurement_models import MEASUREMENT_MODELS
+
+        if self.measurement_model not in MEASUREMENT_MODELS.values():
+            raise NotImplementedError("measurement_model must be one of ship_track_estimators_b200.measurement_models."
+                                      f"{sorted(MEASUREMENT_MODELS)} (arbitrary callables cannot be fused into the batched update)")
+        return np.asarray(self.measurement_model(z), dtype=np.float64).reshape(-1, 1)
 
     def _model(self, P0=None):
         from ..batch import BatchedUKF
 
-        if self.measurement_model is not None:
-            assert callable(self.measurement_model), "Measurement model must be callable."
-            raise NotImplementedError("measurement_model hooks are not supported on the CUDA path")
-        return BatchedUKF(self.H, self.Q, self.R, self.P if P0 is None else P0, gating=self.gating)
+        return BatchedUKF(self.H, self.Q, self.R, self.P if P0 is None else P0, gating=self.gating,
+                          measurement_model=self.measurement_model)
 
     def _step_problem(self, engine):
         from ..batch import TrackBatch  # noqa: F401  (keeps import order explicit)
@@ -174,8 +190,9 @@ class UnscentedKalmanFilter(KalmanFilterBase):
 
         from .. import _native as nat
 
-        self._resolve_process(non_linear_process)
-        self._require_n4("predict")
+        model, _ = self._resolve_process(non_linear_process)
+        if self.n != 4:
+            return self._predict_generic(model, dict(non_linear_process_kwargs))
         kw = dict(non_linear_process_kwargs)
         if kw.get("c", None) is not None and np.size(kw["c"]) != 0:
             raise NotImplementedError("only c=None is supported (the reference never passes a control vector)")
@@ -202,6 +219,54 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         self.sigma_points = sp1.cpu().numpy().reshape(4, 9)
         self.status |= int(st.item())
 
+    def _predict_generic(self, model, kw):
+        """``predict`` for n != 4 through the dimension-generic kernel (``ste_ukf_predict_n_f64``)."""
+        import torch
+
+        from .. import _native as nat
+
+        if kw.get("c", None) is not None and np.size(kw["c"]) != 0:
+            raise NotImplementedError("only c=None is supported (the reference never passes a control vector)")
+        n, L = self.n, self.n_sigma_points
+        self.x = self.x.reshape(-1, 1)
+        self.compute_weights()
+        lib, dev = nat.load(), torch.device("cuda")
+        f64 = dict(dtype=torch.float64, device=dev)
+        up = lambda a, rows: torch.from_numpy(np.asarray(a, dtype=np.float64).reshape(rows, 1).copy()).to(dev)   # noqa: E731
+        xd, Pd = up(self.x, n), up(self.P, n * n)
+        scal = torch.tensor([[float(kw["dt"])], [float(kw.get("sog_rate", 0.0))], [float(kw.get("cog_rate", 0.0))]], **f64)
+        noise = up(_unit_normals(1, n), n) if self._noise_on() else None
+        sp0, sp1 = torch.empty(n * L, 1, **f64), torch.empty(n * L, 1, **f64)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        Q = np.ascontiguousarray(self.Q, dtype=np.float64)
+        nat.check(lib.ste_ukf_predict_n_f64(n, model, 1, 1, Q.ctypes.data_as(C.POINTER(C.c_double)), nat.ptr(xd), nat.ptr(Pd), nat.ptr(scal[0]),
+                                            nat.ptr(scal[1]), nat.ptr(scal[2]), nat.ptr(noise), nat.ptr(sp0), nat.ptr(sp1), nat.ptr(st),
+                                            nat.current_stream()))
+        self.x, self.P = xd.cpu().numpy().reshape(n, 1), Pd.cpu().numpy().reshape(n, n)
+        self.sigma_points_orig, self.sigma_points = sp0.cpu().numpy().reshape(n, L), sp1.cpu().numpy().reshape(n, L)
+        self.status |= int(st.item())
+
+    def _update_generic(self, z):
+        """``update`` for n != 4 through ``ste_ukf_update_n_f64`` (dense H and R, heading at index 3)."""
+        import torch
+
+        from .. import _native as nat
+
+        if self.gating:
+            raise NotImplementedError("the robustification is implemented for the n = 4 state")
+        n = self.n
+        lib, dev = nat.load(), torch.device("cuda")
+        up = lambda a, rows: torch.from_numpy(np.asarray(a, dtype=np.float64).reshape(rows, 1).copy()).to(dev)   # noqa: E731
+        xd, Pd, zd = up(self.x, n), up(self.P, n * n), up(z, n)
+        noise = up(_unit_normals(1, n), n) if self._noise_on() else None
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        H, R = (np.ascontiguousarray(M, dtype=np.float64) for M in (self.H, self.R))
+        dp = C.POINTER(C.c_double)
+        nat.check(lib.ste_ukf_update_n_f64(n, 1, 1, H.ctypes.data_as(dp), R.ctypes.data_as(dp), nat.ptr(xd), nat.ptr(Pd), nat.ptr(zd),
+                                           nat.ptr(noise), nat.ptr(st), nat.current_stream()))
+        self.x, self.P = xd.cpu().numpy().reshape(n, 1), Pd.cpu().numpy().reshape(n, n)
+        self.status |= int(st.item())
+
     def _update_device(self, x, P, R, z, use_noise, gating=None):
         """Shared by ``update`` and ``check_robustness``: returns (x, P, iters, lambda, scale)."""
         import torch
@@ -209,9 +274,6 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         from ..batch import BatchedUKF
         from .. import _native as nat
 
-        if self.measurement_model is not None:
-            assert callable(self.measurement_model), "Measurement model must be callable."
-            raise NotImplementedError("measurement_model hooks are not supported on the CUDA path")
         engine = BatchedUKF(self.H, self.Q, R, P, gating=self.gating if gating is None else gating)
         p = self._step_problem(engine)
         dev = torch.device("cuda")
@@ -233,8 +295,9 @@ class UnscentedKalmanFilter(KalmanFilterBase):
     def update(self, z: np.ndarray) -> None:
         """Linear measurement update with pseudo-inverse gain and Joseph-form covariance
         (reference ``:209-265``)."""
-        self._require_n4("update")
-        z = np.asarray(z, dtype=np.float64).reshape(-1, 1)
+        z = self._apply_measurement_model(np.asarray(z, dtype=np.float64).reshape(-1, 1))
+        if self.n != 4:
+            return self._update_generic(z)
         if self.gating and self._noise_on():
             # the reference's own sequence (:228-236 with the robustification line enabled): the judging
             # loop draws fresh measurement noise per iteration, then the update draws once more with the
@@ -257,7 +320,8 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         from ..batch import TrackBatch, exact_update_mask
 
         self._resolve_process(None)
-        self._require_n4("run")
+        if self.n != 4:
+            return self._run_generic(int(nsteps), dt, ship_track)
         N = int(nsteps)
         mask = exact_update_mask(dt, ship_track.dts, self.time)
         tape = None
@@ -296,6 +360,29 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         if self.gating:
             self.gate_iters.extend(out["gate_iters"].tolist())
             self.gate_lambda.extend(out["gate_lambda"].tolist())
+
+    def _run_generic(self, N, dt, ship_track):
+        """The reference's time loop (``kalman_filter.py:76-111``) around the dimension-generic single-step
+        kernels: for states other than the batched n = 4 layout, one predict (and update) launch per step."""
+        from ..batch import exact_update_mask
+
+        mask = exact_update_mask(dt, ship_track.dts, self.time)
+        z = np.asarray(ship_track.z, dtype=np.float64)
+        if z.shape[0] > self.n:
+            raise ValueError("the measurement has more rows than the state")
+        pad = lambda col: np.concatenate([col, np.zeros(self.n - z.shape[0])])   # noqa: E731
+        ui = 0
+        self.means.append(self.x.reshape(self.n, 1).copy())
+        self.covariances.append(np.array(self.P, dtype=np.float64))
+        self.update(pad(z[:, 0]))
+        for s in range(N):
+            self.predict(dt=dt[s], c=None, sog_rate=ship_track.sog_rate[ui], cog_rate=ship_track.cog_rate[ui])
+            self.time = self.time + dt[s]
+            if mask[s]:
+                ui += 1   # IndexError past the last observation, as in the reference (:101-108)
+                self.update(pad(z[:, ui]))
+            self.means.append(self.x.reshape(self.n, 1).copy())
+            self.covariances.append(np.array(self.P, dtype=np.float64))
 
     def rts_step(self, fwd_means, fwd_vars, ship_track, *args, **kwargs):
         """Unscented RTS smoother over explicit filtered states (reference ``:267-351``).

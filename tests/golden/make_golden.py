@@ -50,9 +50,13 @@ with open(os.path.join(_stub, "geographiclib", "geodesic.py"), "w") as fh:
         "class Geodesic:\n"
         "    WGS84 = _W()\n"
     )
-sys.path.insert(0, _stub)
-sys.path.insert(0, os.path.join(REF, "src"))
 sys.path.insert(0, REPO)
+sys.path.insert(0, _stub)
+sys.path.insert(0, os.path.join(REF, "src"))   # first: the repository carries an alias package of the same name
+
+import track_estimators as _reference_package  # noqa: E402
+
+assert os.path.abspath(_reference_package.__file__).startswith(REF), "fixtures must come from the unmodified reference"
 
 from track_estimators.kalman_filters.non_linear_process import geodetic_dynamics  # noqa: E402
 from track_estimators.kalman_filters.unscented import UnscentedKalmanFilter  # noqa: E402

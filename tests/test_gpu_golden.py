@@ -139,3 +139,79 @@ def test_robustification_entry_points_against_reference_kats(cuda, native_lib):
         d[3] = (d[3] + 180.0) % 360.0 - 180.0
         assert float(np.max(np.abs(d) / np.maximum(1.0, np.abs(c["x_post"])))) <= TOL, f"case {i} state"
         assert float(np.max(np.abs(ukf.P - c["P_post"])) / np.max(np.abs(c["P_post"]))) <= TOL, f"case {i} covariance"
+
+
+def test_per_track_measurement_covariance(cuda, native_lib):
+    """every track of a tile with its OWN dense 4x4 R (SteInputs.R_tracks), H = I, UKF + URTSS, against
+    one reference run per track (tests/golden/per_track_r.npz); the filter's shared R must not matter."""
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+
+    tracks, _ = load_golden("per_track_r")
+    assert not np.array_equal(tracks[0]["R"], tracks[1]["R"]) and np.count_nonzero(tracks[0]["R"]) == 16
+    batch = TrackBatch.from_tracks([_as_track(t) for t in tracks], [t["dt_array"] for t in tracks], device=cuda,
+                                   x0=[t["x0"] for t in tracks], R=[t["R"] for t in tracks])
+    for shared in (np.eye(4) * 123.0, np.diag([1e-3, 1e-3, 0.0, 0.0])):   # the second would select the position-only update
+        res = BatchedUKF(tracks[0]["H"], tracks[0]["Q"], shared, tracks[0]["P0"]).run(batch)
+        for i, ref in enumerate(tracks):
+            assert_track_close(res.track(i), ref, tol=TOL, label=f"per_track_r[{i}]")
+
+
+def test_generic_dimension_class_api_against_reference_kats(cuda, native_lib):
+    """the class at n = 5 (state [lon, lat, sog, cog, cog_rate], process geodetic_dynamics_turn):
+    the process model, sigma points, predict and update against the reference's class run with the same five-state
+    process built from its own geodetic_dynamics (tests/golden/kat_n5.npz)."""
+    import os
+
+    from _helpers import GOLDEN
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics, geodetic_dynamics_turn
+
+    d = np.load(os.path.join(GOLDEN, "kat_n5.npz"))
+    H, Q, R = d["H"], d["Q"], d["R"]
+    rel = lambda got, ref: float(np.max(np.abs(np.asarray(got) - ref)) / max(1.0, float(np.max(np.abs(ref)))))   # noqa: E731
+    for i in range(int(d["n"])):
+        c = {k.split("_", 1)[1]: d[k] for k in d.files if k.startswith(f"c{i}_")}
+        dt, sr = float(c["dt"]), float(c["sog_rate"])
+        assert rel(geodetic_dynamics_turn(c["x"], None, dt, sog_rate=sr), c["f_x"]) <= 1e-13
+        ukf = UnscentedKalmanFilter(H=H, Q=Q, R=R, P=c["P"], x0=c["x"], non_linear_process=geodetic_dynamics_turn, noise="zero")
+        assert ukf.n == 5 and ukf.n_sigma_points == 11
+        ukf.compute_weights()
+        assert rel(ukf.compute_sigma_points(), c["X0"]) <= 1e-11
+        ukf.predict(dt=dt, c=None, sog_rate=sr)
+        assert rel(ukf.sigma_points_orig, c["X0"]) <= 1e-11 and rel(ukf.sigma_points, c["X_pred"]) <= 1e-11
+        assert rel(ukf.x.reshape(-1), c["x_pred"]) <= TOL and rel(ukf.P, c["P_pred"]) <= TOL, f"case {i} predict"
+        ukf.update(c["z"])
+        dx = ukf.x.reshape(-1) - c["x_post"]
+        dx[3] = (dx[3] + 180.0) % 360.0 - 180.0
+        assert float(np.max(np.abs(dx) / np.maximum(1.0, np.abs(c["x_post"])))) <= TOL and rel(ukf.P, c["P_post"]) <= TOL, f"case {i} update"
+    with pytest.raises(ValueError, match="propagates"):
+        UnscentedKalmanFilter(H=H, Q=Q, R=R, non_linear_process=geodetic_dynamics).predict(dt=1.0, c=None)
+    with pytest.raises(NotImplementedError, match="arbitrary Python callables"):
+        UnscentedKalmanFilter(H=H, Q=Q, R=R, non_linear_process=lambda x, **k: x).predict(dt=1.0, c=None)
+
+
+def test_generic_dimension_run_loop(cuda, native_lib):
+    """n = 5 through KalmanFilterBase.run (host loop around the generic single-step kernels): with a zero turn-rate
+    state that nothing excites (zero process noise and prior variance on it) the first four states must reproduce
+    the n = 4 filter of the batched path fed cog_rate = 0."""
+    from types import SimpleNamespace
+
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics, geodetic_dynamics_turn
+    from ship_track_estimators_b200.synthetic import make_tracks
+    from ship_track_estimators_b200.utils import generate_dts
+
+    syn = make_tracks(1, 13, seed=5, device="cpu", dts_choices=(1.0, 2.0))
+    z = np.stack([syn.lon[:, 0].numpy(), syn.lat[:, 0].numpy(), syn.sog[:, 0].numpy(), syn.cog[:, 0].numpy()])
+    st = SimpleNamespace(dts=syn.dts[:, 0].numpy(), z=z, sog_rate=syn.sog_rate[:, 0].numpy(), cog_rate=np.zeros(13), sog=z[2], cog=z[3])
+    dt = generate_dts(st.dts, 2)
+    H4, Q4, R4 = np.diag([1.0, 1, 0, 0]), np.diag([1e-2, 1e-2, 1e-4, 1e-4]), np.diag([1e-3, 1e-3, 0, 0])
+    u4 = UnscentedKalmanFilter(H=H4, Q=Q4, R=R4, P=np.eye(4), x0=z[:, 0], non_linear_process=geodetic_dynamics, noise="zero")
+    m4, c4 = u4.run(len(dt), dt, st)
+    pad = lambda M: np.pad(M, ((0, 1), (0, 1)))   # noqa: E731
+    u5 = UnscentedKalmanFilter(H=pad(H4), Q=pad(Q4), R=pad(R4), P=pad(np.eye(4)), x0=np.append(z[:, 0], 0.0),
+                               non_linear_process=geodetic_dynamics_turn, noise="zero")
+    m5, c5 = u5.run(len(dt), dt, st)
+    assert m5.shape == (len(dt) + 1, 5) and c5.shape == (len(dt) + 1, 5, 5)
+    # n = 5 has other sigma-point weights (W0 = -2/3, scale 5 / (1 - W0) = 3): the filters agree where the
+    # dynamics are linear in the spread and stay close elsewhere
+    assert np.allclose(m5[:, 4], 0.0) and np.max(np.abs(m5[:, :2] - m4[:, :2])) < 5e-3
+    assert np.all(np.isfinite(c5)) and np.allclose(c5[:, 4, :], 0.0)
