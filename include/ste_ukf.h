@@ -227,6 +227,19 @@ int ste_derive_inputs_f64(int32_t n_tracks, int32_t max_obs, int64_t ld, int32_t
                           const double *lon, const double *lat, const double *dts, const int32_t *n_obs,
                           double *sog, double *cog, double *sog_rate, double *cog_rate, void *stream);
 
+/* CSV rows -> columns for a whole file (ShipTrack.read_csv, ship_track.py:107-195, done for every ship at once):
+ * `bytes` is the file as it sits on disk, copied to the device; row r is bytes[row_start[r] .. row_start[r+1] - 1)
+ * (row_start has n_rows + 1 entries: the offset after each newline).  cols_host [8] (HOST array) gives the field index
+ * of yr, mo, dy, hr, lat, lon, id and of the row-label column (-1: the file has no index column; label = row number).
+ * Outputs [n_rows]: hours since 1970-01-01 00:00 of "yr-mo-dy hr:00" (the reference builds that string and parses it
+ * with pandas; gaps between rows are differences of these), lat / lon (NaN for NA / empty), id_key (FNV-1a 64 of the id
+ * text), id_int (its value when it is an integer literal), id_off / id_len (span of the id text inside the row),
+ * label, flags (bit 0 bad date, 1 bad position, 2 id not an integer, 3 label not an integer, 4 lat / lon needs the
+ * host's slow number path, 5 short row).  Fields may be double-quoted; no embedded quotes, commas or newlines. */
+int ste_csv_parse_rows(const uint8_t *bytes, const int64_t *row_start, int64_t n_rows, const int32_t *cols_host, int64_t *hours,
+                       double *lat, double *lon, uint64_t *id_key, int64_t *id_int, int32_t *id_off, int32_t *id_len,
+                       int64_t *label, int32_t *flags, void *stream);
+
 /* performance_metrics.rmse / abs_diff / cum_abs_diff (performance_metrics.py:4-58) of a state
  * estimate against the observations it assimilated, for T tracks in one launch.  For track t and
  * observation row r (rows with in->z[r] == NULL are skipped and left untouched), the pairs are

@@ -11,6 +11,7 @@
 
 #include "ste_tracks.cuh"
 #include "ste_generic.cuh"
+#include "ste_ingest.cuh"
 
 namespace ste {
 
@@ -783,6 +784,26 @@ int ste_process_f64(int32_t model, int32_t n, int32_t n_tracks, int64_t ld, cons
     if (n_tracks == 0) return STE_OK;
     process_n_kernel<<<(n_tracks + 63) / 64, 64, 0, (cudaStream_t)stream>>>(model, n, n_tracks, ld, x_in, dt, sog_rate, cog_rate, x_out);
     return check_launch("process_n_kernel");
+}
+
+int ste_csv_parse_rows(const uint8_t *bytes, const int64_t *row_start, int64_t n_rows, const int32_t *cols_host, int64_t *hours,
+                       double *lat, double *lon, uint64_t *id_key, int64_t *id_int, int32_t *id_off, int32_t *id_len, int64_t *label,
+                       int32_t *flags, void *stream) {
+    if (n_rows < 0) return fail(STE_ERR_INVALID_ARG, "negative row count");
+    if (!bytes || !row_start || !cols_host || !hours || !lat || !lon || !id_key || !id_int || !id_off || !id_len || !label || !flags)
+        return fail(STE_ERR_INVALID_ARG, "missing array");
+    for (int k = 0; k < kCsvColLabel; ++k)
+        if (cols_host[k] < 0) return fail(STE_ERR_INVALID_ARG, "yr, mo, dy, hr, lat, lon and id columns are required");
+    if (n_rows == 0) return STE_OK;
+    CsvArgs a{};
+    a.bytes = bytes; a.row_start = row_start; a.n_rows = n_rows;
+    for (int k = 0; k < kCsvTargets; ++k) a.cols[k] = cols_host[k];
+    a.hours = hours; a.lat = lat; a.lon = lon; a.id_key = id_key; a.id_int = id_int; a.id_off = id_off; a.id_len = id_len;
+    a.label = label; a.flags = flags;
+    const int64_t blocks = (n_rows + 255) / 256;
+    if (blocks > 0x7fffffffll) return fail(STE_ERR_UNSUPPORTED, "more than 2^31 blocks of rows: split the file");
+    csv_parse_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("csv_parse_rows_kernel");
 }
 
 int ste_gate_terms_f64(const SteProblem *prob, const double *x, const double *P, const double *z, double *gamma, double *denom,

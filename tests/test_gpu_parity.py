@@ -986,3 +986,78 @@ def test_pipelined_output_sets(cuda, native_lib):
                     want = torch.cat([m["rmse"], m["cum_abs"], m["max_abs"]], dim=0).cpu()
                 m = valid if want.dim() == 3 else 1.0
                 assert torch.equal(torch.nan_to_num(o[key]) * m, torch.nan_to_num(want) * m), (name, key, j)
+
+
+def _modern_csv(path, seed, n_ships=7, n_rows=400):
+    """A file shaped like data/modern_ships/modern_ship_data.csv: quoted first column WITH a header name (no index),
+    quoted text ids, NA fields, ships interleaved in time order."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    ids = [f"SHIP{k:03d}" if k % 2 else f"W{k}DG{7520 + k}" for k in range(n_ships)]
+    lat0, lon0 = rng.uniform(-60, 60, n_ships), rng.uniform(0, 359, n_ships)
+    t = pd.Timestamp("2021-01-01")
+    lines = ['"","yr","mo","dy","hr","dck","id","lat","lon","w","d"']
+    for r in range(n_rows):
+        k = int(rng.integers(0, n_ships))
+        t = t + pd.Timedelta(hours=int(rng.choice([0, 1, 1, 2, 3])))
+        lat0[k] += rng.normal(0, 0.05)
+        lon0[k] += rng.normal(0, 0.05)
+        lat = "NA" if r == 17 else f"{lat0[k]:.{int(rng.integers(1, 7))}f}"
+        w = "NA" if r % 3 else str(int(rng.integers(0, 30)))
+        lines.append(f'"{415 + 3 * r}",{t.year},{t.month},{t.day},{t.hour},992,"{ids[k]}",{lat},{lon0[k]:.2f},{w},NA')
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return ids
+
+
+def test_device_csv_ingest_matches_the_host_reader(cuda, native_lib, tmp_path):
+    """ingest.read_csv_fleet_device (bytes parsed by ste_csv_parse_rows, grouping and ordering by device sorts) against
+    ingest.read_csv_fleet (pandas): identical ids, fixes, gaps and counts - bit for bit - on a file with an integer index
+    column (numeric label order), on one with zero-padded labels, and on a modern-format file (quoted ids, NA fields,
+    no index column); explicit id lists, reverse, bad-row policy; text labels are refused."""
+    from test_host_dropin import _fleet_csv
+
+    from ship_track_estimators_b200.ingest import read_csv_fleet, read_csv_fleet_device
+
+    def same(dev_fleet, host_fleet):
+        h = dev_fleet.to_host()
+        assert h.ids == host_fleet.ids
+        assert np.array_equal(h.n_obs, host_fleet.n_obs)
+        for name in ("lon", "lat", "dts"):
+            assert np.array_equal(getattr(h, name), getattr(host_fleet, name), equal_nan=True), name
+
+    kw = dict(id_col="primary.id", lat_col="lat", lon_col="lon")
+    for case, opts in (("int_labels", dict(string_labels=False)), ("padded_labels", dict(string_labels=False, time_ordered=True))):
+        csv = str(tmp_path / f"{case}.csv")
+        ids = _fleet_csv(csv, seed=21, n_ships=14, **opts)
+        same(read_csv_fleet_device(csv, device=cuda, **kw), read_csv_fleet(csv, **kw))
+        some = sorted(str(int(i)) for i in ids)[::-2]
+        for reverse in (False, True):
+            same(read_csv_fleet_device(csv, ship_ids=some, reverse=reverse, device=cuda, **kw), read_csv_fleet(csv, ship_ids=some, reverse=reverse, **kw))
+        with pytest.raises(ValueError, match="No data found"):
+            read_csv_fleet_device(csv, ship_ids=["nobody"], device=cuda, **kw)
+    csv = str(tmp_path / "text_labels.csv")
+    _fleet_csv(csv, seed=22, string_labels=True)
+    with pytest.raises(NotImplementedError, match="read_csv_fleet"):
+        read_csv_fleet_device(csv, device=cuda, **kw)
+    csv = str(tmp_path / "modern.csv")
+    ids = _modern_csv(csv, seed=23)
+    mk = dict(id_col="id", lat_col="lat", lon_col="lon")
+    dev_fleet = read_csv_fleet_device(csv, device=cuda, **mk)
+    same(dev_fleet, read_csv_fleet(csv, **mk))
+    assert sorted(dev_fleet.ids) == sorted(ids) and dev_fleet.stats["rows"] == 400
+    assert bool(np.isnan(dev_fleet.to_host().lat).any())      # the NA latitude stays a missing value, as in pandas
+    # and straight into the filter: device-parsed fixes -> device-derived inputs -> UKF + URTSS
+    from ship_track_estimators_b200.batch import BatchedUKF
+
+    csv = str(tmp_path / "fleet.csv")
+    _fleet_csv(csv, seed=11, n_ships=12, string_labels=False, time_ordered=True)
+    host = read_csv_fleet(csv, **kw)
+    keep = [i for i in range(host.n_tracks) if host.n_obs[i] >= 3]
+    dev_fleet = read_csv_fleet_device(csv, ship_ids=[host.ids[i] for i in keep], device=cuda, **kw)
+    ukf = BatchedUKF(H_POS, Q_DEF, R_POS, P_DEF)
+    a, b = ukf.run(dev_fleet.to_batch(substeps=2)), ukf.run(host.select(keep).to_batch(device=cuda, substeps=2))
+    for i in range(len(keep)):
+        x, y = a.track(i), b.track(i)
+        assert all(np.array_equal(x[k], y[k]) for k in ("means", "covs", "means_s", "covs_s"))
