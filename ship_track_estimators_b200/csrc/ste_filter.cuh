@@ -25,7 +25,7 @@ struct Model {
 //             for the next step (3); backward: the carried smoothed state xs (4), Ps (10)
 //   [14, 30)  root M, column-major: M[r][c] at kScratchRoot + c * 4 + r
 //   [30, 46)  forward: Sigma_c / Delta_c of the pair loop; backward by recomputation: Delta_c
-//   [14, 50)  rotation parameters during sqrt_psd4 (kSqrtRotSlots = 36)
+//   [14, 62)  rotation parameters during sqrt_psd4 (kSqrtRotSlots = 48: four sweeps)
 constexpr int kScratchObs = 0;             // 4 slots
 constexpr int kScratchIn = 4;              // 3 slots
 constexpr int kScratchXs = 0;              // 4 slots  (backward)
@@ -34,7 +34,7 @@ constexpr int kScratchRoot = 14;           // 16 slots
 constexpr int kScratchDeltaFwd = 30;       // 16 slots
 constexpr int kScratchDelta = 30;          // 16 slots (backward by recomputation)
 constexpr int kScratchRot = kScratchRoot;  // kSqrtRotSlots slots, live only inside sqrt_psd4
-constexpr int kScratchSlots = kScratchRot + kSqrtRotSlots;   // 50
+constexpr int kScratchSlots = kScratchRot + kSqrtRotSlots;   // 62
 constexpr int kScratchSlotsFwd = kScratchSlots;
 constexpr int kScratchSlotsBwd = kScratchSlots;
 

@@ -266,8 +266,9 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 //     X2_ij = -(X1 X1)_ij / (s_i + s_j),             s = sqrt(diag D);
 // the neglected term is below 1e-12 of the smaller root eigenvalue (measured on filter
 // covariances: 4e-14).  One sweep is enough when every predict follows an update (eps at a median
-// of 2.5e-6 then, 99.95 % below 1e-4 on the benchmark tracks), two or three with sub-steps or
-// irregular updates.  No eigenvector matrix is accumulated: the sweeps leave their rotation
+// of 2.5e-6 then, 99.98 % below 1e-4 on the benchmark tracks), two to four with sub-steps or
+// irregular updates (config-4 shape, measured on the host build: 1 % / 46 % / 52 % / 0.6 % of the
+// roots take 1 / 2 / 3 / 4 sweeps, 0.01 % the out-of-line finish).  No eigenvector matrix is accumulated: the sweeps leave their rotation
 // parameters (c, s) in scratch (kSweepSlots per sweep, kSqrtRotSlots in all, starting at slot
 // `rot`) and the root S of the rotated matrix is carried back, M = J_1 (... (J_n S J_n^T) ...) J_1^T,
 // rotation by rotation on its 10 unique entries - 114 FP64 operations per sweep instead of 96 for
@@ -276,8 +277,11 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 #ifndef STE_SQRT_SERIES_EPS2
 #define STE_SQRT_SERIES_EPS2 1e-8
 #endif
+#if defined(STE_EMUL_STATS) && !defined(__CUDA_ARCH__)
+static long long ste_emul_sweep_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 constexpr double kSqrtSeriesEps2 = STE_SQRT_SERIES_EPS2;     // eps^2 limit of the series finish
-constexpr int kSqrtMaxSweeps = 3;
+constexpr int kSqrtMaxSweeps = 4;
 constexpr int kSqrtRotSlots = kSqrtMaxSweeps * kSweepSlots;
 
 STE_DEV bool jacobi_off_within(const double (&a)[10], double eps2) {
@@ -304,6 +308,13 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], con
         ++sweeps;
         if ((series_ok = jacobi_off_within(a, kSqrtSeriesEps2))) break;
     }
+#if defined(STE_EMUL_STATS) && !defined(__CUDA_ARCH__)
+    ++ste_emul_sweep_hist[series_ok ? sweeps : 0];   // developer sandbox only: sweeps per root, [0] = cold path
+    if (!series_ok) {
+        const double wmx = fmax(fmax(a[0], a[4]), fmax(a[7], a[9])), wmn = fmin(fmin(a[0], a[4]), fmin(a[7], a[9]));
+        ++ste_emul_sweep_hist[wmn < 0.0 ? 4 : (wmn > 1e-12 * wmx ? 6 : 5)];   // negative / tiny / off-diagonals still large
+    }
+#endif
     if (!series_ok) {
         double Mt[10];
         const bool clamped = sqrt_psd4_cold(A[0] * scale, A[1] * scale, A[2] * scale, A[3] * scale, A[4] * scale, A[5] * scale,

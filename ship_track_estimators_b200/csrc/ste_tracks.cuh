@@ -393,7 +393,7 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
 // Results are bit-identical to the two separate passes: the same step functions run in the
 // same order per track.
 //
-// Scratch layout of the fused kernel (slots per thread): [0, 50) the forward pass's slots, [50, 100)
+// Scratch layout of the fused kernel (slots per thread): [0, 62) the forward pass's slots, [62, 124)
 // the backward pass's (carried xs / Ps, and the root / Delta / rotation slots of a step that has to
 // be recomputed - step 0, a step whose tape entry is invalid, or every step of a flagged track).
 // ------------------------------------------------------------------------------------------ //

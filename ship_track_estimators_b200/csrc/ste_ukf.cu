@@ -24,7 +24,7 @@ constexpr int kThreads = STE_THREADS;
 //  - backward over the statistics tape: HBM-bound, and what hurts it is local-memory traffic, so
 //    it gets the registers it asks for (227, no spills) at 2 blocks = 8 warps: 13.7e9 track-steps/s
 //    against 10.2e9 at 4 blocks / 128 registers / 208 B of spills;
-//  - backward by recomputation (no tape): compute-bound like the forward pass, 4 blocks.
+//  - backward by recomputation (no tape): compute-bound like the forward pass, 3 blocks (shared memory).
 #ifndef STE_FWD_MIN_BLOCKS
 #define STE_FWD_MIN_BLOCKS 3
 #endif
@@ -32,12 +32,12 @@ constexpr int kThreads = STE_THREADS;
 #define STE_BWD_MIN_BLOCKS 2
 #endif
 #ifndef STE_BWD_RECOMPUTE_MIN_BLOCKS
-#define STE_BWD_RECOMPUTE_MIN_BLOCKS 4
+#define STE_BWD_RECOMPUTE_MIN_BLOCKS 3   // 62 scratch slots per thread: three 62 KB blocks per SM
 #endif
 
 template <bool POS_ONLY, bool GATING>
 __global__ void __launch_bounds__(kThreads, STE_FWD_MIN_BLOCKS) ukf_forward_kernel(const __grid_constant__ KernelArgs a) {
-    extern __shared__ double scratch[];   // kScratchSlotsFwd * kThreads doubles (50 KB: opt-in size)
+    extern __shared__ double scratch[];   // kScratchSlotsFwd * kThreads doubles (62 KB: opt-in size)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
@@ -52,7 +52,7 @@ urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
 }
 
 #ifndef STE_FUSED_MIN_BLOCKS
-#define STE_FUSED_MIN_BLOCKS 2   // 242 registers, no spills; at 3 blocks the 4000-instruction loop starves on instruction fetch
+#define STE_FUSED_MIN_BLOCKS 1   // 124 scratch slots per thread (127 KB per block): one block per SM
 #endif
 // forward pass of tile a + backward pass of tile b, one thread per (track of a, track of b)
 template <bool POS_ONLY, bool GATING>
@@ -102,7 +102,7 @@ __device__ __forceinline__ void store_xP(const StepArgs &a, int t, const double 
         for (int j = 0; j < 4; ++j) a.P[(i * 4 + j) * ld + t] = P[SYM(i, j)];
 }
 
-constexpr int kStepThreads = 64;   // single-step predict: 50 scratch slots per thread within the static 48 KB
+constexpr int kStepThreads = 64;   // single-step predict: 62 scratch slots per thread within the static 48 KB
 __global__ void __launch_bounds__(kStepThreads) ukf_predict_kernel(const __grid_constant__ StepArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.prob.n_tracks) return;

@@ -72,3 +72,7 @@ extern "C" void emul_geodetic_tiers(int n, const double *x, const double *dt, co
         for (int r = 0; r < 4; ++r) { y_generic[i * 4 + r] = a[r]; y_small[i * 4 + r] = b[r]; }
     }
 }
+
+#if defined(STE_EMUL_STATS)
+extern "C" void emul_sweep_hist(long long *out) { for (int i = 0; i < 8; ++i) { out[i] = ste::ste_emul_sweep_hist[i]; ste::ste_emul_sweep_hist[i] = 0; } }
+#endif
