@@ -218,3 +218,27 @@ def test_generic_dimension_run_loop(cuda, native_lib):
     assert np.allclose(m5[:, 4], 0.0) and float(np.max(np.abs(d) / np.maximum(1.0, np.abs(m4)))) <= 1e-8
     assert np.all(np.isfinite(c5)) and np.allclose(c5[:, 4, :], 0.0)
     assert float(np.max(np.abs(c5[:, :4, :4] - c4)) / np.max(np.abs(c4))) <= 1e-8
+
+
+def test_process_model_near_the_poles(cuda, native_lib):
+    """The reference takes the new latitude as arcsin(.), the CUDA path as atan2(up, hypot(east, north)): the same angle,
+    conditioned differently as |lat| -> 90.  Reference known answers at |lat| = 89.5 ... 89.9999 degrees
+    (tests/golden/kat_polar.npz): the process model to 1e-9 of max(1, |value|) and one unscented predict to 1e-9."""
+    import os
+
+    from _helpers import GOLDEN
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics
+
+    d = np.load(os.path.join(GOLDEN, "kat_polar.npz"))
+    worst = 0.0
+    for i in range(len(d["x"])):
+        y = geodetic_dynamics(d["x"][i], None, float(d["dt"][i]), sog_rate=float(d["sog_rate"][i]), cog_rate=float(d["cog_rate"][i]))
+        err = float(np.max(np.abs(y - d["y"][i]) / np.maximum(1.0, np.abs(d["y"][i]))))
+        worst = max(worst, err)
+        assert err <= TOL, (i, d["x"][i], y, d["y"][i])
+        ukf = UnscentedKalmanFilter(H=np.diag([1.0, 1, 0, 0]), Q=d["Q"], R=np.eye(4), P=d["P0"][i], x0=d["x"][i],
+                                    non_linear_process=geodetic_dynamics, noise="zero")
+        ukf.predict(dt=float(d["dt"][i]), c=None, sog_rate=float(d["sog_rate"][i]), cog_rate=float(d["cog_rate"][i]))
+        assert float(np.max(np.abs(ukf.x.reshape(-1) - d["x_pred"][i]) / np.maximum(1.0, np.abs(d["x_pred"][i])))) <= TOL, i
+        assert float(np.max(np.abs(ukf.P - d["P_pred"][i])) / np.max(np.abs(d["P_pred"][i]))) <= 1e-8, i
+    print(f"process model at |lat| up to 89.9999 deg: worst deviation from the reference {worst:.2e}")
