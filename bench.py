@@ -554,7 +554,9 @@ def run_e2e(args, D, ukf, cfg, make_tile, tile_track_steps):
     n_tiles = max(4, min(args.steps, 6))
     seq_in = [host_tiles[i % 2] for i in range(n_tiles)]
     sets = [cfg["e2e_outputs"]]
-    if not args.e2e_headline_only:   # ragged tiles are tens of GB of pinned memory per full output set: headline + summary only
+    # the other output sets are timed beside the headline on one GPU only: under torchrun every rank would pin
+    # several GB more of the one host's memory for numbers that do not enter the scaling run
+    if not args.e2e_headline_only and world == 1:   # ragged tiles are tens of GB of pinned memory per full output set: headline + summary only
         sets += [s for s in (("summary",) if cfg["ragged"] else ("all", "cli", "summary")) if smoother]
     out, by_set = None, {}
     for name in sets:
