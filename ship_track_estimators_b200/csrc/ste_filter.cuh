@@ -115,45 +115,75 @@ STE_DEV bool step_is_small(const double (&x)[4], const double (&P)[10], double d
 //     Sigma_c[r] = (y+[r] - c[r]) + (y-[r] - c[r]),   Delta_c[r] = y+[r] - y-[r]      (r = 0, 1)
 // (4 scratch slots per column); every moment is assembled after the loop from these 16 numbers and
 // the root itself, with no accumulator live across the trigonometry.
+#ifndef STE_PAIR_COLS
+#define STE_PAIR_COLS 1   // root columns (mirror pairs) propagated in lock-step per loop iteration: 1, 2 or 4
+#endif
 template <bool LIB, bool SMALL>
 STE_DEV void sigma_pair_loop(const double (&x)[4], const AngleTrig &base, const double (&c)[4], double dt, double dtR,
                              double sog_rate, double cog_rate, const Scratch &sc, double *sig_prior, double *sig_post,
                              int64_t ld) {
+    constexpr int NC = STE_PAIR_COLS, NP = 2 * NC;
 #ifndef STE_PAIR_UNROLL
 #define STE_PAIR_UNROLL 1
 #endif
     STE_UNROLL(STE_PAIR_UNROLL)
-    for (int col = 0; col < 4; ++col) {
+    for (int col = 0; col < 4; col += NC) {
 #if defined(STE_STEP_SYNC) && (STE_STEP_SYNC >= 2) && defined(__CUDA_ARCH__)
         __syncthreads();
 #endif
-        double m[4], xx[2][4], yy[2][4];
-        double (&xp)[4] = xx[0], (&xm)[4] = xx[1], (&yp)[4] = yy[0], (&ym)[4] = yy[1];
+        // points 2k, 2k+1 are the mirror pair x + m, x - m of column col + k
+        double m[NC][4], xx[NP][4], yy[NP][4];
+        AngleTrig tt[NP];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            m[r] = sc.at(kScratchRoot + col * 4 + r);
-            xp[r] = x[r] + m[r];
-            xm[r] = x[r] - m[r];
-        }
-        {
-            const AngleTrig off = offset_trig<LIB>(m[1], m[3], m[2], dtR);
-            AngleTrig tt[2];
-            angle_add_pair(base, off, tt[0], tt[1]);
-            geodetic_finish_n<LIB, 2, SMALL>(xx, tt, dt, sog_rate, cog_rate, yy);
-        }
-        if (sig_prior) {
+        for (int k = 0; k < NC; ++k)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                sig_prior[(r * 9 + 1 + col) * ld] = xp[r];
-                sig_post[(r * 9 + 1 + col) * ld] = yp[r];
-                sig_prior[(r * 9 + 5 + col) * ld] = xm[r];
-                sig_post[(r * 9 + 5 + col) * ld] = ym[r];
+                m[k][r] = sc.at(kScratchRoot + (col + k) * 4 + r);
+                xx[2 * k][r] = x[r] + m[k][r];
+                xx[2 * k + 1][r] = x[r] - m[k][r];
+            }
+        if constexpr (LIB || NC == 1) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) angle_add_pair(base, offset_trig<LIB>(m[k][1], m[k][3], m[k][2], dtR), tt[2 * k], tt[2 * k + 1]);
+        } else {
+            // the offsets of all NC columns through one lock-step series; the full-range evaluation replaces it
+            // (for all of them) only when some offset is not small
+            double ang[3 * NC], sn[3 * NC], cs[3 * NC];
+            bool small = true;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                ang[3 * k] = m[k][1] * kDegToRad;
+                ang[3 * k + 1] = m[k][3] * kDegToRad;
+                ang[3 * k + 2] = m[k][2] * dtR;
+            }
+#pragma unroll
+            for (int i = 0; i < 3 * NC; ++i) small &= fabs(ang[i]) <= kSmallAngle;
+            small_sincos_v<3 * NC>(ang, sn, cs);
+            if (__builtin_expect(!small, 0)) fast_sincos_v<3 * NC>(ang, sn, cs);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                AngleTrig off;
+                off.sp = sn[3 * k]; off.cp = cs[3 * k]; off.sa = sn[3 * k + 1]; off.ca = cs[3 * k + 1]; off.sd = sn[3 * k + 2]; off.cd = cs[3 * k + 2];
+                angle_add_pair(base, off, tt[2 * k], tt[2 * k + 1]);
             }
         }
+        geodetic_finish_n<LIB, NP, SMALL>(xx, tt, dt, sog_rate, cog_rate, yy);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            sc.at(kScratchDeltaFwd + col * 4 + r) = (yp[r] - c[r]) + (ym[r] - c[r]);
-            sc.at(kScratchDeltaFwd + col * 4 + 2 + r) = yp[r] - ym[r];
+        for (int k = 0; k < NC; ++k) {
+            if (sig_prior) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    sig_prior[(r * 9 + 1 + col + k) * ld] = xx[2 * k][r];
+                    sig_post[(r * 9 + 1 + col + k) * ld] = yy[2 * k][r];
+                    sig_prior[(r * 9 + 5 + col + k) * ld] = xx[2 * k + 1][r];
+                    sig_post[(r * 9 + 5 + col + k) * ld] = yy[2 * k + 1][r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                sc.at(kScratchDeltaFwd + (col + k) * 4 + r) = (yy[2 * k][r] - c[r]) + (yy[2 * k + 1][r] - c[r]);
+                sc.at(kScratchDeltaFwd + (col + k) * 4 + 2 + r) = yy[2 * k][r] - yy[2 * k + 1][r];
+            }
         }
     }
 }
