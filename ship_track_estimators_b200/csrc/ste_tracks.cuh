@@ -341,7 +341,7 @@ struct BackwardTrack {
 #endif
         // The tape pass is bound by memory latency at its 8 warps per SM (29 loads in flight per thread and step):
         // pulling the NEXT step's 29 lines towards L2 now, without registers, turns its DRAM round trip into an L2 hit.
-        if (STE_BWD_PREFETCH && use_stats && step > 1) prefetch_stats_step(step - 1);
+        if (STE_BWD_PREFETCH && use_stats && step > STE_BWD_PREFETCH) prefetch_stats_step(step - STE_BWD_PREFETCH);   // distance in steps
         if (use_stats && step > 0)
             done = urtss_step_from_stats(mf, cf, packed, a.out.smooth_stats + ((int64_t)step * kStatsPlanes) * ld + t, ld, a.prob.Q,
                                          e, xs, Ps, status, sc, (unsigned)a.prob.reserved);

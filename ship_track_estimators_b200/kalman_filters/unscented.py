@@ -33,6 +33,55 @@ def _unit_normals(rows: int, n: int) -> np.ndarray:
     return np.asarray(np.random.normal(size=(rows, n)), dtype=np.float64).reshape(rows, n)
 
 
+class _Stage:
+    """Staging of a single-step call: ONE pinned host buffer, ONE device buffer, so that a `predict` or
+    `update` costs one host->device copy, one launch and one device->host copy (the first round-2
+    version made ~8 small allocations and 5 synchronous copies per call).  ``slot(name)`` hands out
+    consecutive float64 ranges; the last one doubles as the int32 status word."""
+
+    def __init__(self, layout):
+        import torch
+
+        self.offsets, n = {}, 0
+        for name, size in layout:
+            self.offsets[name] = (n, n + size)
+            n += size
+        self.host = torch.zeros(n, dtype=torch.float64).pin_memory()
+        self.dev = torch.zeros(n, dtype=torch.float64, device="cuda")
+        self.np = self.host.numpy()
+
+    def put(self, name, values):
+        a, b = self.offsets[name]
+        self.np[a:b] = np.asarray(values, dtype=np.float64).reshape(-1)
+
+    def get(self, name):
+        a, b = self.offsets[name]
+        return self.np[a:b].copy()
+
+    def dev_slot(self, name):
+        a, b = self.offsets[name]
+        return self.dev[a:b]
+
+    def upload(self, upto):
+        self.dev[: self.offsets[upto][1]].copy_(self.host[: self.offsets[upto][1]], non_blocking=True)
+
+    def download(self):
+        import torch
+
+        self.host.copy_(self.dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def status(self):
+        a, _ = self.offsets["status"]
+        return int(self.host[a:a + 1].view(torch_int32())[0])
+
+
+def torch_int32():
+    import torch
+
+    return torch.int32
+
+
 class UnscentedKalmanFilter(KalmanFilterBase):
     default_noise = "numpy"  # "numpy": reference semantics; "zero": deterministic
 
@@ -72,6 +121,7 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         self.gating = bool(gating)
         self.noise = noise
         self.status = 0  # OR of STE_STATUS_* bits seen by this filter
+        self._stages: dict = {}  # pinned / device staging buffers of the single-step calls, allocated once
         self.gate_iters: list = []
         self.gate_lambda: list = []
 
@@ -202,22 +252,25 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         self.compute_weights()
         engine = self._model()
         p = self._step_problem(engine)
-        dev = torch.device("cuda")
-        f64 = dict(dtype=torch.float64, device=dev)
-        xd = torch.from_numpy(np.asarray(self.x, dtype=np.float64).reshape(4, 1).copy()).to(dev)
-        Pd = torch.from_numpy(np.asarray(self.P, dtype=np.float64).reshape(16, 1).copy()).to(dev)
-        scal = torch.tensor([[dt], [sog_rate], [cog_rate]], **f64)
-        noise = torch.from_numpy(_unit_normals(1, 4).reshape(4, 1).copy()).to(dev) if self._noise_on() else None
-        sp0, sp1 = torch.empty(36, 1, **f64), torch.empty(36, 1, **f64)
-        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = self._stages.get("predict")
+        if st is None:
+            st = self._stages["predict"] = _Stage([("x", 4), ("P", 16), ("dt", 1), ("sr", 1), ("cr", 1), ("noise", 4), ("status", 1),
+                                                   ("sp0", 36), ("sp1", 36)])
+        noisy = self._noise_on()
+        st.put("x", self.x); st.put("P", self.P); st.put("dt", dt); st.put("sr", sog_rate); st.put("cr", cog_rate)
+        st.put("noise", _unit_normals(1, 4) if noisy else np.zeros(4)); st.put("status", 0.0)
+        st.upload("status")
+        status_dev = st.dev_slot("status").view(torch.int32)
         nat.check(engine._lib.ste_ukf_predict_f64(
-            C.byref(p), nat.ptr(xd), nat.ptr(Pd), nat.ptr(scal[0]), nat.ptr(scal[1]), nat.ptr(scal[2]),
-            nat.ptr(noise), nat.ptr(sp0), nat.ptr(sp1), nat.ptr(st), nat.current_stream()))
-        self.x = xd.cpu().numpy().reshape(4, 1)
-        self.P = Pd.cpu().numpy().reshape(4, 4)
-        self.sigma_points_orig = sp0.cpu().numpy().reshape(4, 9)
-        self.sigma_points = sp1.cpu().numpy().reshape(4, 9)
-        self.status |= int(st.item())
+            C.byref(p), nat.ptr(st.dev_slot("x")), nat.ptr(st.dev_slot("P")), nat.ptr(st.dev_slot("dt")), nat.ptr(st.dev_slot("sr")),
+            nat.ptr(st.dev_slot("cr")), nat.ptr(st.dev_slot("noise")) if noisy else None, nat.ptr(st.dev_slot("sp0")),
+            nat.ptr(st.dev_slot("sp1")), nat.ptr(status_dev), nat.current_stream()))
+        st.download()
+        self.x = st.get("x").reshape(4, 1)
+        self.P = st.get("P").reshape(4, 4)
+        self.sigma_points_orig = st.get("sp0").reshape(4, 9)
+        self.sigma_points = st.get("sp1").reshape(4, 9)
+        self.status |= st.status()
 
     def _predict_generic(self, model, kw):
         """``predict`` for n != 4 through the dimension-generic kernel (``ste_ukf_predict_n_f64``)."""
@@ -276,21 +329,21 @@ class UnscentedKalmanFilter(KalmanFilterBase):
 
         engine = BatchedUKF(self.H, self.Q, R, P, gating=self.gating if gating is None else gating)
         p = self._step_problem(engine)
-        dev = torch.device("cuda")
-        f64 = dict(dtype=torch.float64, device=dev)
-        xd = torch.from_numpy(np.asarray(x, dtype=np.float64).reshape(4, 1).copy()).to(dev)
-        Pd = torch.from_numpy(np.asarray(P, dtype=np.float64).reshape(16, 1).copy()).to(dev)
-        zd = torch.from_numpy(np.asarray(z, dtype=np.float64).reshape(4, 1).copy()).to(dev)
-        noise = torch.from_numpy(_unit_normals(1, 4).reshape(4, 1).copy()).to(dev) if use_noise else None
-        it = torch.zeros(1, dtype=torch.uint8, device=dev)
-        lam = torch.ones(1, **f64)
-        scale = torch.ones(1, **f64)
-        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = self._stages.get("update")
+        if st is None:
+            st = self._stages["update"] = _Stage([("x", 4), ("P", 16), ("z", 4), ("noise", 4), ("lam", 1), ("scale", 1), ("status", 1), ("iters", 1)])
+        st.put("x", x); st.put("P", P); st.put("z", z); st.put("noise", _unit_normals(1, 4) if use_noise else np.zeros(4))
+        st.put("lam", 1.0); st.put("scale", 1.0); st.put("status", 0.0); st.put("iters", 0.0)
+        st.upload("iters")
         nat.check(engine._lib.ste_ukf_update_f64(
-            C.byref(p), nat.ptr(xd), nat.ptr(Pd), nat.ptr(zd), nat.ptr(noise), nat.ptr(it), nat.ptr(lam),
-            nat.ptr(scale), nat.ptr(st), nat.current_stream()))
-        self.status |= int(st.item())
-        return xd.cpu().numpy().reshape(4, 1), Pd.cpu().numpy().reshape(4, 4), int(it.item()), float(lam.item()), float(scale.item())
+            C.byref(p), nat.ptr(st.dev_slot("x")), nat.ptr(st.dev_slot("P")), nat.ptr(st.dev_slot("z")),
+            nat.ptr(st.dev_slot("noise")) if use_noise else None, nat.ptr(st.dev_slot("iters").view(torch.uint8)), nat.ptr(st.dev_slot("lam")),
+            nat.ptr(st.dev_slot("scale")), nat.ptr(st.dev_slot("status").view(torch.int32)), nat.current_stream()))
+        st.download()
+        self.status |= st.status()
+        a, _ = st.offsets["iters"]
+        iters = int(st.host[a:a + 1].view(torch.uint8)[0])
+        return st.get("x").reshape(4, 1), st.get("P").reshape(4, 4), iters, float(st.get("lam")[0]), float(st.get("scale")[0])
 
     def update(self, z: np.ndarray) -> None:
         """Linear measurement update with pseudo-inverse gain and Joseph-form covariance
