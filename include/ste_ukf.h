@@ -261,7 +261,7 @@ int ste_probe_fastmath(int32_t kind, int32_t n, const double *a, const double *b
 /* Measurement helper: one block of `warps` warps runs `iters` rounds of n independent dependent
  * chains per thread, chains = 100 * mode + n with n in {1, 2, 4, 8}: mode 0 DFMA on registers,
  * 1 DFMA with constant-bank operands, 2 DMUL/DADD alternating, 3 DFMA followed by a compare +
- * select.  cycles[0] (device int64) receives the clock64 span.  Gives the latency (warps = n = 1)
+ * select, 4 DFMA with three changing register sources (n in {4, 8}), 5 DMUL with two (n in {4, 8}).  cycles[0] (device int64) receives the clock64 span.  Gives the latency (warps = n = 1)
  * and the issue interval of the FP64 pipe for the instruction mixes the filter kernels issue. */
 int ste_probe_fp64_latency(int32_t warps, int32_t iters, int32_t chains, double *sink,
                            long long *cycles, void *stream);

@@ -494,6 +494,9 @@ __global__ void fastmath_probe_kernel(int kind, int n, const double *a, const do
 // FP64 pipe microbenchmark: CHAINS independent dependent chains per thread, clock64 timed.
 // MODE 0: DFMA, register operands.  1: DFMA with a __constant__ (uniform-register) multiplicand.
 // 2: DMUL + DADD alternating.  3: DFMA followed by a select on its result (DSETP + FSEL pair).
+// 4: DFMA whose three source operands are three DIFFERENT registers that change every instruction
+// (acc[k] = fma(acc[k], acc[k+1], acc[k+2])): what the filter's matrix code looks like to the register
+// file, against mode 0 where two of the three operands never change.  5: the same with two sources (DMUL).
 __constant__ double kProbeC[2] = {1.0000000001, 1e-12};
 template <int CHAINS, int MODE>
 __global__ void fp64_latency_probe_kernel(int iters, double *sink, long long *cycles) {
@@ -513,6 +516,8 @@ __global__ void fp64_latency_probe_kernel(int iters, double *sink, long long *cy
                 const double v = fma(acc[k], a, b);
                 acc[k] = (v > 1e300) ? b : v;
             }
+            if (MODE == 4) acc[k] = fma(acc[k], acc[(k + 1) % CHAINS], -acc[(k + 2) % CHAINS]);
+            if (MODE == 5) acc[k] = acc[k] * acc[(k + 1) % CHAINS];
         }
     }
     const long long t1 = clock64();
@@ -886,6 +891,7 @@ int ste_probe_fp64_latency(int32_t warps, int32_t iters, int32_t chains, double 
     STE_PROBE_CASE(1, 1) STE_PROBE_CASE(4, 1) STE_PROBE_CASE(8, 1)
     STE_PROBE_CASE(1, 2) STE_PROBE_CASE(4, 2) STE_PROBE_CASE(8, 2)
     STE_PROBE_CASE(1, 3) STE_PROBE_CASE(4, 3) STE_PROBE_CASE(8, 3)
+    STE_PROBE_CASE(4, 4) STE_PROBE_CASE(8, 4) STE_PROBE_CASE(4, 5) STE_PROBE_CASE(8, 5)
 #undef STE_PROBE_CASE
     return fail(STE_ERR_INVALID_ARG, "chains must be 100 * mode + {1, 2, 4, 8}");
     return check_launch("fp64_latency_probe_kernel");
