@@ -363,6 +363,9 @@ def roofline_block(cfg, track_steps_per_launch, f_ms, b_ms, fp64_peak, full_cov)
         if dram:
             dg = dram * track_steps_per_launch / (ms * 1e-3) / 1e9
             per_kernel[key].update(dram_bytes_per_track_step=dram, dram_gbs=dg, dram_frac=dg / peak)
+        if c.get("fp64_rf_cycles"):   # pipe + register-file bound: sum of max(2, distinct register sources) over the FP64 instructions
+            bound_ms = c["fp64_rf_cycles"] * track_steps_per_launch / 32.0 / (592 * 1.965e9) * 1e3
+            per_kernel[key].update(fp64_rf_bound_ms=bound_ms, frac_of_fp64_rf_bound=bound_ms / ms)
         if c.get("fp64_instr"):
             per_kernel[key].update(
                 fp64_instr_per_track_step=c["fp64_instr"], flops_per_track_step=c.get("flops"),
@@ -383,7 +386,9 @@ def roofline_block(cfg, track_steps_per_launch, f_ms, b_ms, fp64_peak, full_cov)
         "fp64_pipe": {"peak_tflops_measured": fp64_peak,
                       "note": "flops = 2*DFMA + DMUL + DADD and fp64_instr = DFMA + DMUL + DADD + DSETP warp-instructions per track-step, "
                               "counted with ncu (profiles/kernel_counts.json); peak = DFMA probe (ste_probe_fp64_fma); fp64_pipe_busy = "
-                              "fp64_instr x 2.05 cycles issue interval over 592 sub-partitions at 1965 MHz"},
+                              "fp64_instr x 2.05 cycles issue interval over 592 sub-partitions at 1965 MHz; fp64_rf_bound = the same instructions at "
+                              "max(2, distinct 64-bit register sources) cycles each (measured: a three-register DFMA issues every 3.0 cycles; "
+                              "tools/fp64_operand_model.py, profiles/r02_fp64_issue_intervals.txt)"},
     }
 
 

@@ -64,6 +64,10 @@ if __name__ == "__main__":
         full = classify(parse(sys.argv[sys.argv.index("--full-cov") + 1]), tracks * steps)
         for k in out:
             out[k]["dram_bytes_full_cov"] = full[k]["dram_bytes"]
+    if "--rf-model" in sys.argv:   # cycles per warp-step from tools/fp64_operand_model.py: forward=..,forward_no_tape=..,backward=..
+        for item in sys.argv[sys.argv.index("--rf-model") + 1].split(","):
+            k, v = item.split("=")
+            out[k]["fp64_rf_cycles"] = float(v)
     note = sys.argv[sys.argv.index("--note") + 1] if "--note" in sys.argv else ""
     out["source"] = (f"ncu --metrics ... --clock-control none over tools/quick_perf.py --tracks {tracks} --steps {steps} --packed "
                      f"(tools/ncu_counts.py); per track-step = per launch / ({tracks} x {steps}). {note}").strip()
