@@ -568,18 +568,21 @@ def run_e2e(args, D, ukf, cfg, make_tile, tile_track_steps):
         host_outs = [ukf.host_outputs(host_tiles[0], outputs=name, smoother=smoother) for _ in range(2)]
         seq_out = [host_outs[i % 2] for i in range(n_tiles)]
         ukf.run_host_pipelined(seq_in[:2], seq_out[:2], smoother=smoother, device=dev, outputs=name)  # warm-up
-        D.barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        moved = ukf.run_host_pipelined(seq_in, seq_out, smoother=smoother, device=dev, outputs=name)
-        t1.record()
-        D.barrier()
-        ms = D.reduce(t0.elapsed_time(t1), "max")
+        passes = []
+        for _ in range(3):   # three timed passes, the median is reported: the host side of PCIe is shared with other tenants
+            D.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            moved = ukf.run_host_pipelined(seq_in, seq_out, smoother=smoother, device=dev, outputs=name)
+            t1.record()
+            D.barrier()
+            passes.append(D.reduce(t0.elapsed_time(t1), "max"))
+        ms = statistics.median(passes)
         v = world * tile_track_steps * n_tiles / (ms * 1e-3)
         first = next(iter(host_outs[0].values()))
         assert bool(torch.isfinite(first.double()).all()) and float(first.double().abs().sum()) > 0.0
         entry = {"value": v, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"] // n_tiles, "d2h_bytes_per_step": moved["d2h_bytes"] // n_tiles,
-                 "outputs": list(ukf.OUTPUT_SETS[name])}
+                 "outputs": list(ukf.OUTPUT_SETS[name]), "passes_ms": passes}
         by_set[name] = entry
         if out is None:
             out = dict(entry, output_set=name, tile_tracks=host_tiles[0].n_tracks, steps=n_tiles,

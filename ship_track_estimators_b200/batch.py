@@ -198,6 +198,23 @@ class TrackBatch:
         """Copy of the tile on ``device`` (host->device copies are asynchronous from pinned memory)."""
         return self._map(lambda t: t.to(device, non_blocking=non_blocking))
 
+    def copy_from(self, other: "TrackBatch", non_blocking: bool = True) -> bool:
+        """Overwrite this tile's tensors with ``other``'s (same shapes and the same optional tensors
+        present; e.g. pinned host tile -> resident device tile, no allocation).  Returns False, with
+        nothing copied, when the layouts differ."""
+        pairs = [(getattr(self, n), getattr(other, n)) for n in self._TENSORS] + list(zip(self.z, other.z))
+        for dst, src in pairs:
+            if (dst is None) != (src is None) or (dst is not None and (dst.shape != src.shape or dst.dtype != src.dtype)):
+                return False
+        for dst, src in pairs:
+            if dst is not None:
+                dst.copy_(src, non_blocking=non_blocking)
+        self.substeps, self.rate_repeat_all = other.substeps, other.rate_repeat_all
+        self.n_steps_host, self.order, self._long_fraction = other.n_steps_host, other.order, other._long_fraction
+        if hasattr(self, "_z_model"):
+            del self._z_model
+        return True
+
     def pin_memory(self) -> "TrackBatch":
         """Host tile in page-locked memory (the staging form for :meth:`BatchedUKF.run_host`)."""
         return self._map(lambda t: t.cpu().pin_memory())
@@ -810,15 +827,15 @@ class BatchedUKF:
         cur = torch.cuda.current_stream(dev)
         if self._pipe is None or self._pipe["device"] != dev:
             self._pipe = {"device": dev, "streams": [torch.cuda.Stream(dev) for _ in range(3)], "res": [None, None],
-                          "scratch": [{}, {}], "shape": None}
+                          "in": [None, None], "scratch": [{}, {}], "shape": None}
         pipe = self._pipe
         key = (shape0, smoother, self.packed_cov)
-        if pipe["shape"] != key:                 # device result buffers are kept across calls of one shape
-            pipe["res"], pipe["scratch"], pipe["shape"] = [None, None], [{}, {}], key
+        if pipe["shape"] != key:                 # device input and result buffers are kept across calls of one shape
+            pipe["res"], pipe["in"], pipe["scratch"], pipe["shape"] = [None, None], [None, None], [{}, {}], key
         s_in, s_run, s_out = pipe["streams"]
         for s_ in (s_in, s_run, s_out):
             s_.wait_stream(cur)
-        dev_in: List[Optional[TrackBatch]] = [None, None]
+        dev_in: List[Optional[TrackBatch]] = pipe["in"]    # two resident input tiles, overwritten in place (no allocation in the loop)
         in_done = [torch.cuda.Event() for _ in range(n)]
         run_done = [torch.cuda.Event() for _ in range(n)]
         out_done = [torch.cuda.Event() for _ in range(n)]
@@ -828,7 +845,8 @@ class BatchedUKF:
             with torch.cuda.stream(s_in):
                 if i >= 2:
                     s_in.wait_event(run_done[i - 2])        # the kernels that read this input slot are done
-                dev_in[k] = host_batches[i].to(dev, non_blocking=True)
+                if dev_in[k] is None or not dev_in[k].copy_from(host_batches[i]):
+                    dev_in[k] = host_batches[i].to(dev, non_blocking=True)
                 in_done[i].record(s_in)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(in_done[i])
