@@ -148,10 +148,13 @@ int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutpu
 /* The loop of examples/example_ukf_rts_smoother_batch.py:19-71 over successive tiles of tracks,
  * software-pipelined: ONE launch runs KalmanFilterBase.run for the tracks of tile `fwd_*` and
  * UnscentedKalmanFilter.rts_step (all steps) for the tracks of tile `bwd_*`, which an earlier
- * call has already filtered (forward pass or fused pass, with smooth_stats).  Results are
- * bit-identical to ste_ukf_forward_f64(fwd) followed by ste_urtss_backward_f64(bwd); the
- * smoother's memory latency hides behind the filter's arithmetic.  The two tiles must use
- * different output arrays; either may be empty (n_tracks == 0). */
+ * call has already filtered (forward pass or fused pass).  The blocks of the launch take the
+ * filter's or the smoother's role, interleaved so that every SM holds both.  Results are
+ * bit-identical to ste_ukf_forward_f64(fwd) followed by ste_urtss_backward_f64(bwd).  Measured
+ * on B200 it is ~13 % slower than those two launches back to back (two instruction streams per
+ * SM overflow the instruction cache): an entry point for callers that want
+ * one launch per tile, not the fast path.  The two tiles must use different output arrays;
+ * either may be empty (n_tracks == 0). */
 int ste_ukf_fused_f64(const SteProblem *fwd_prob, const SteInputs *fwd_in, SteOutputs *fwd_out,
                       const SteProblem *bwd_prob, const SteInputs *bwd_in, SteOutputs *bwd_out, void *stream);
 

@@ -677,9 +677,10 @@ class BatchedUKF:
 
     def fused(self, fwd_batch: TrackBatch, fwd_res: TrackResults, bwd_batch: TrackBatch, bwd_res: TrackResults) -> None:
         """ONE launch: the forward filter of ``fwd_batch`` and the backward smoother of ``bwd_batch``
-        (filtered by an earlier ``forward``/``fused`` call into ``bwd_res``).  Bit-identical to
-        ``forward(fwd_batch, fwd_res); backward(bwd_batch, bwd_res)``; the smoother's memory
-        latency hides behind the filter's arithmetic.  The two result sets must be distinct."""
+        (filtered by an earlier ``forward``/``fused`` call into ``bwd_res``), as blocks of two roles
+        resident on every SM together.  Bit-identical to ``forward(fwd_batch, fwd_res);
+        backward(bwd_batch, bwd_res)``, and on B200 ~13 % slower than those two launches (two
+        instruction streams per SM overflow the instruction cache).  The two result sets must be distinct."""
         self._check_rows(fwd_batch)
         self._check_shapes(fwd_batch, fwd_res)
         self._check_shapes(bwd_batch, bwd_res, smoother=True)
@@ -695,14 +696,20 @@ class BatchedUKF:
             nat.check(self._lib.ste_ukf_fused_f64(C.byref(pf), C.byref(i_f), C.byref(of), C.byref(pb), C.byref(ib), C.byref(ob),
                                                   nat.current_stream()))
 
-    def run_many(self, batches: Sequence[TrackBatch], results: Sequence[TrackResults]) -> None:
-        """Filter and smooth a sequence of resident tiles, software-pipelined: tile i+1 is filtered
-        by the same launch that smooths tile i (``len(batches) + 1`` launches).  Consecutive tiles
-        must use different result sets (two alternating sets are enough when each tile's results
-        are consumed, in stream order, before its set comes round again)."""
+    def run_many(self, batches: Sequence[TrackBatch], results: Sequence[TrackResults], fused: bool = False) -> None:
+        """Filter and smooth a sequence of resident tiles.  Default: two launches per tile (the fast
+        route).  ``fused=True``: software-pipelined, tile i+1 is filtered by the same launch that
+        smooths tile i (``len(batches) + 1`` launches); consecutive tiles must then use different
+        result sets (two alternating sets are enough when each tile's results are consumed, in
+        stream order, before its set comes round again)."""
         n = len(batches)
         if n != len(results):
             raise ValueError("one result set per tile")
+        if not fused:
+            for b, r in zip(batches, results):
+                self.forward(b, r)
+                self.backward(b, r)
+            return
         for i in range(n + 1):
             if i == 0:
                 self.forward(batches[0], results[0])

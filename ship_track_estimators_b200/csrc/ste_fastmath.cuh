@@ -237,14 +237,24 @@ STE_DEV void fast_sincos_v(const double (&x)[N], double (&sn)[N], double (&cs)[N
 // The sigma-point offsets of a converged filter are a few degrees at most.
 constexpr double kSmallAngle = 0.125;
 
+// STE_POLY_LITERALS: the coefficients of the short series as literals instead of constant-table reads (experiment:
+// where the compiler keeps a table value in a vector register, the DFMA that uses it reads three register pairs and
+// issues every 3 cycles instead of 2; a literal is materialised in a uniform register, which is not a register-file read)
+#ifdef STE_POLY_LITERALS
+#define STE_SINC(i) ((i) == 0 ? -1.66666666666666324348e-01 : (i) == 1 ? 8.33333333332248946124e-03 : (i) == 2 ? -1.98412698298579493134e-04 : 2.75573137070700676789e-06)
+#define STE_COSC(i) ((i) == 0 ? 4.16666666666666019037e-02 : (i) == 1 ? -1.38888888888741095749e-03 : (i) == 2 ? 2.48015872894767294178e-05 : (i) == 3 ? -2.75573143513906633035e-07 : 2.08757232129817482790e-09)
+#else
+#define STE_SINC(i) kSinC[i]
+#define STE_COSC(i) kCosC[i]
+#endif
 template <int N>
 STE_DEV void small_sincos_v(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
     double z[N], ps[N], pc[N];
     STE_LANES z[l] = x[l] * x[l];
-    STE_LANES { ps[l] = fma(z[l], kSinC[3], kSinC[2]); pc[l] = fma(z[l], kCosC[4], kCosC[3]); }
-    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[1]); pc[l] = fma(z[l], pc[l], kCosC[2]); }
-    STE_LANES { ps[l] = fma(z[l], ps[l], kSinC[0]); pc[l] = fma(z[l], pc[l], kCosC[1]); }
-    STE_LANES pc[l] = fma(z[l], pc[l], kCosC[0]);
+    STE_LANES { ps[l] = fma(z[l], STE_SINC(3), STE_SINC(2)); pc[l] = fma(z[l], STE_COSC(4), STE_COSC(3)); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], STE_SINC(1)); pc[l] = fma(z[l], pc[l], STE_COSC(2)); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], STE_SINC(0)); pc[l] = fma(z[l], pc[l], STE_COSC(1)); }
+    STE_LANES pc[l] = fma(z[l], pc[l], STE_COSC(0));
     STE_LANES { sn[l] = fma(x[l] * z[l], ps[l], x[l]); cs[l] = fma(z[l] * z[l], pc[l], fma(-0.5, z[l], 1.0)); }
 }
 

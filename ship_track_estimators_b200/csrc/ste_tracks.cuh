@@ -84,12 +84,9 @@ STE_DEV bool any_nonfinite(const double (&x)[4], const double (&P)[10]) {
 // ------------------------------------------------------------------------------------------ //
 // Forward filter: KalmanFilterBase.run (kalman_filter.py:36-117).
 //
-// The time loop is written as begin() / step(s) / end() on a small state object so that the
-// fused kernel can interleave it, step by step, with the backward pass of another tile.
+// The time loop is written as begin() / step(s) / end() on a small state object.
 // ------------------------------------------------------------------------------------------ //
-// PARK: between steps the state (x, P) rests in the (then dead) root slots of the scratch instead
-// of in registers, so that whatever the caller runs between two steps does not compete with it.
-template <bool POS_ONLY, bool GATING, bool PARK = false>
+template <bool POS_ONLY, bool GATING>
 struct ForwardTrack {
     const KernelArgs &a;
     const int t;
@@ -191,28 +188,9 @@ struct ForwardTrack {
             upd_next = step_updates(0);
         }
         assimilate(0);   // kalman_filter.py:81 (waits for the staged copies, including step 0's inputs)
-        park();
-    }
-
-    STE_DEV void park() const {
-        if constexpr (PARK) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) sc.at(kScratchRoot + r) = x[r];
-#pragma unroll
-            for (int k = 0; k < 10; ++k) sc.at(kScratchRoot + 4 + k) = P[k];
-        }
-    }
-    STE_DEV void unpark() {
-        if constexpr (PARK) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) x[r] = sc.at(kScratchRoot + r);
-#pragma unroll
-            for (int k = 0; k < 10; ++k) P[k] = sc.at(kScratchRoot + 4 + k);
-        }
     }
 
     STE_DEV void step(int s) {
-        unpark();
         const bool upd = upd_next;
         const double dt = sc.at(kScratchIn + 0), sr = sc.at(kScratchIn + 1), cr = sc.at(kScratchIn + 2);
         consistent &= (min_(ri, a.prob.max_obs - 1) == ui);
@@ -241,11 +219,9 @@ struct ForwardTrack {
         if (advance) assimilate(++ui);
         else stage_wait();   // the next step's inputs must have landed before they are read
         store_state(a.out.mean_f, a.out.cov_f, ld, s + 1, t, packed, x, P);
-        park();
     }
 
     STE_DEV void end() {
-        unpark();
         if (any_nonfinite(x, P)) status |= STE_STATUS_NONFINITE;
         if (a.out.smooth_stats && !consistent) status |= STE_STATUS_SMOOTH_RECOMPUTE;
         a.out.status[t] = status;
@@ -309,8 +285,7 @@ struct BackwardTrack {
         use_stats = a.out.smooth_stats && !(a.out.status[t] & STE_STATUS_SMOOTH_RECOMPUTE);
     }
 
-    // Pull what step(step) will read from the statistics path towards L2 (no register, no
-    // scratch): issued a whole forward step ahead by the fused kernel.
+    // Pull what step(step) will read from the statistics path towards L2 (no register, no scratch).
     STE_DEV void prefetch_stats_step(int step) const {
         const double *mf = a.out.mean_f + ((int64_t)step * 4) * ld + t;
         const double *cf = a.out.cov_f + ((int64_t)step * cov_planes(packed)) * ld + t;
@@ -387,61 +362,6 @@ STE_DEV void backward_track(const KernelArgs &a, const int t, const Scratch &sc)
 #pragma unroll 1
     for (int step = g.nt - 1; step >= 0; --step) g.step(step);
     g.end();
-}
-
-// ------------------------------------------------------------------------------------------ //
-// Fused pass: the forward filter of tile A and the backward smoother of tile B (already
-// filtered, statistics on its tape) in ONE time loop per thread.  The smoother step is ~13 % of
-// the filter step's arithmetic but, run as its own kernel, it is bound by HBM latency/bandwidth
-// and takes ~30 % of the time.  Here its 44 input values are pulled towards L2 at the top of the
-// iteration, the forward step (several microseconds of FP64 work) runs, and the smoother step
-// then reads L2 hits and spends its few hundred instructions in the FP64 pipe's idle slots.
-// Results are bit-identical to the two separate passes: the same step functions run in the
-// same order per track.
-//
-// Scratch layout of the fused kernel (slots per thread): [0, 62) the forward pass's slots, [62, 124)
-// the backward pass's (carried xs / Ps, and the root / Delta / rotation slots of a step that has to
-// be recomputed - step 0, a step whose tape entry is invalid, or every step of a flagged track).
-// ------------------------------------------------------------------------------------------ //
-constexpr int kScratchSlotsFused = 2 * kScratchSlots;
-
-template <bool POS_ONLY, bool GATING>
-STE_DEV void fused_track(const KernelArgs &a, const KernelArgs &b, const int t, const Scratch &sc) {
-    const bool has_f = t < a.prob.n_tracks, has_b = t < b.prob.n_tracks;
-    ForwardTrack<POS_ONLY, GATING, true> f(a, t, sc);
-    BackwardTrack g(b, t, Scratch{sc.base + (long)kScratchSlots * sc.stride, sc.stride});
-    if (has_b) g.begin();
-    if (has_f) f.begin();
-    // tracks without usable statistics are smoothed entirely after the loop
-    const int nb_loop = (has_b && g.use_stats && g.nt > 0) ? g.nt - 1 : 0;
-    int n_iter = f.nt > nb_loop ? f.nt : nb_loop;
-#if defined(STE_FUSED_SYNC) && defined(__CUDA_ARCH__)
-    {
-        __shared__ int block_iters;
-        if (threadIdx.x == 0) block_iters = 0;
-        __syncthreads();
-        atomicMax(&block_iters, n_iter);
-        __syncthreads();
-        n_iter = block_iters;
-    }
-#endif
-#pragma unroll 1
-    for (int i = 0; i < n_iter; ++i) {
-#if defined(STE_FUSED_SYNC) && defined(__CUDA_ARCH__)
-        __syncthreads();   // keep the warps of a block on the same instructions (shared fetch)
-#endif
-        const int sb = g.nt - 1 - i;
-        const bool do_b = i < nb_loop;
-        if (do_b) g.prefetch_stats_step(sb);
-        if (i < f.nt) f.step(i);
-        if (do_b) g.step(sb);
-    }
-    if (has_f) f.end();
-    if (has_b) {
-#pragma unroll 1
-        for (int step = g.nt - 1 - nb_loop; step >= 0; --step) g.step(step);
-        g.end();
-    }
 }
 
 }  // namespace ste

@@ -51,21 +51,34 @@ urtss_backward_kernel(const __grid_constant__ KernelArgs a) {
     if (t < a.prob.n_tracks) backward_track(a, t, Scratch{scratch + threadIdx.x, kThreads});
 }
 
-#ifndef STE_FUSED_MIN_BLOCKS
-#define STE_FUSED_MIN_BLOCKS 1   // 124 scratch slots per thread (127 KB per block): one block per SM
+// Co-resident passes: ONE launch whose blocks take one of two roles - forward filter of tile a or backward smoother
+// of tile b (already filtered, statistics on its tape).  The filter is bound by the FP64 pipe and leaves DRAM idle, the
+// tape smoother is bound by DRAM and leaves the FP64 pipe idle; run back to back their times add.  Here the roles are
+// interleaved along blockIdx in proportion to the two block counts, so that every SM holds both kinds at once (the block
+// scheduler hands out blocks in index order, and the quicker smoother blocks turn over faster, which settles the
+// resident mix by itself) and the smoother's memory round trips pass behind the filter's arithmetic.  Every track runs
+// exactly the code of the separate kernels: results are bit-identical to forward(a) then backward(b).
+#ifndef STE_ROLES_MIN_BLOCKS
+#define STE_ROLES_MIN_BLOCKS 3   // both roles within 168 registers: any three blocks fit one SM
 #endif
-// forward pass of tile a + backward pass of tile b, one thread per (track of a, track of b)
+struct RoleSplit {
+    int blocks_a, blocks_b;   // forward blocks (tile a), backward blocks (tile b)
+};
 template <bool POS_ONLY, bool GATING>
-__global__ void __launch_bounds__(kThreads, STE_FUSED_MIN_BLOCKS)
-ukf_fused_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ KernelArgs b) {
-    extern __shared__ double scratch[];   // kScratchSlotsFused * kThreads doubles
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-#if defined(STE_FUSED_SYNC)
-    fused_track<POS_ONLY, GATING>(a, b, t, Scratch{scratch + threadIdx.x, kThreads});   // block-wide barriers inside
-#else
-    if (t < a.prob.n_tracks || t < b.prob.n_tracks)
-        fused_track<POS_ONLY, GATING>(a, b, t, Scratch{scratch + threadIdx.x, kThreads});
-#endif
+__global__ void __launch_bounds__(kThreads, STE_ROLES_MIN_BLOCKS)
+ukf_roles_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ KernelArgs b, const RoleSplit split) {
+    extern __shared__ double scratch[];   // kScratchSlots * kThreads doubles (either role)
+    // block i is a forward block when floor((i + 1) * A / N) > floor(i * A / N): A of N blocks, evenly spread
+    const long long A = split.blocks_a, N = (long long)split.blocks_a + split.blocks_b, i = blockIdx.x;
+    const int fa = (int)(i * A / N), fa1 = (int)((i + 1) * A / N);
+    const Scratch sc{scratch + threadIdx.x, kThreads};
+    if (fa1 > fa) {
+        const int t = fa * kThreads + threadIdx.x;
+        if (t < a.prob.n_tracks) forward_track<POS_ONLY, GATING>(a, t, sc);
+    } else {
+        const int t = ((int)i - fa) * kThreads + threadIdx.x;
+        if (t < b.prob.n_tracks) backward_track(b, t, sc);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -677,14 +690,14 @@ int ste_urtss_backward_f64(const SteProblem *prob, const SteInputs *in, SteOutpu
 
 extern "C++" {
 template <bool POS_ONLY, bool GATING>
-static int launch_fused(const KernelArgs &a, const KernelArgs &b, cudaStream_t s) {
-    const int n = a.prob.n_tracks > b.prob.n_tracks ? a.prob.n_tracks : b.prob.n_tracks;
-    const dim3 grid((n + kThreads - 1) / kThreads), block(kThreads);
-    const size_t smem = sizeof(double) * kScratchSlotsFused * kThreads;
-    if (cudaFuncSetAttribute(ukf_fused_kernel<POS_ONLY, GATING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(ukf_fused_kernel)");
-    ukf_fused_kernel<POS_ONLY, GATING><<<grid, block, smem, s>>>(a, b);
-    return check_launch("ukf_fused_kernel");
+static int launch_roles(const KernelArgs &a, const KernelArgs &b, cudaStream_t s) {
+    RoleSplit split{(a.prob.n_tracks + kThreads - 1) / kThreads, (b.prob.n_tracks + kThreads - 1) / kThreads};
+    const dim3 grid(split.blocks_a + split.blocks_b), block(kThreads);
+    const size_t smem = sizeof(double) * kScratchSlots * kThreads;
+    if (cudaFuncSetAttribute(ukf_roles_kernel<POS_ONLY, GATING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(ukf_roles_kernel)");
+    ukf_roles_kernel<POS_ONLY, GATING><<<grid, block, smem, s>>>(a, b, split);
+    return check_launch("ukf_roles_kernel");
 }
 }  // extern "C++"
 
@@ -699,8 +712,8 @@ int ste_ukf_fused_f64(const SteProblem *fwd_prob, const SteInputs *fwd_in, SteOu
     const bool gating = (fwd_prob->flags & STE_FLAG_GATING) != 0, pos = position_only(*fwd_prob);
     const KernelArgs a = kernel_args(fwd_prob, fwd_in, fwd_out), b = kernel_args(bwd_prob, bwd_in, bwd_out);
     cudaStream_t s = (cudaStream_t)stream;
-    if (pos) return gating ? launch_fused<true, true>(a, b, s) : launch_fused<true, false>(a, b, s);
-    return gating ? launch_fused<false, true>(a, b, s) : launch_fused<false, false>(a, b, s);
+    if (pos) return gating ? launch_roles<true, true>(a, b, s) : launch_roles<true, false>(a, b, s);
+    return gating ? launch_roles<false, true>(a, b, s) : launch_roles<false, false>(a, b, s);
 }
 
 int ste_ukf_predict_f64(const SteProblem *prob, double *x, double *P, const double *dt, const double *sog_rate,

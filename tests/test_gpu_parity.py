@@ -499,10 +499,10 @@ def test_pipelined_host_api(cuda, native_lib):
 
 @pytest.mark.parametrize("gating,packed", [(False, False), (False, True), (True, True)])
 def test_fused_pass_is_bit_identical_to_separate_passes(gating, packed, cuda, native_lib):
-    """ste_ukf_fused_f64 (forward of one tile + backward of another in one launch) and run_many
-    against forward() + backward(): ragged tiles of different sizes, a tile of irregular sub-step
-    grids (statistics unusable: smoothed by recomputation inside the fused kernel), and an empty
-    tile on either side."""
+    """ste_ukf_fused_f64 (forward blocks of one tile + backward blocks of another in one launch)
+    and run_many(fused=True) against forward() + backward(): ragged tiles of different sizes (the
+    two roles interleave in uneven proportions), a tile of irregular sub-step grids (statistics
+    unusable: smoothed by recomputation inside the launch), and an empty tile on either side."""
     import ctypes as C
 
     import torch
@@ -537,8 +537,12 @@ def test_fused_pass_is_bit_identical_to_separate_passes(gating, packed, cuda, na
     ref = [ukf.run(b) for b in tiles]
     assert int(((ref[1].status & nat.STE_STATUS_SMOOTH_RECOMPUTE) != 0).sum()) > 50
     got = [ukf.allocate(b) for b in tiles]
-    ukf.run_many(tiles, got)
+    ukf.run_many(tiles, got, fused=True)
     torch.cuda.synchronize()
+    plain = [ukf.allocate(b) for b in tiles]
+    ukf.run_many(tiles, plain)
+    for r, g in zip(ref, plain):
+        assert torch.equal(r.mean_s, g.mean_s) and torch.equal(r.cov_s, g.cov_s)
 
     def owned_equal(b, r, g, names=("mean_f", "cov_f", "mean_s", "cov_s")):
         T = b.n_tracks

@@ -36,29 +36,6 @@ extern "C" int emul_backward(const SteProblem *prob, const SteInputs *in, SteOut
     return 0;
 }
 
-extern "C" int emul_fused(const SteProblem *pa, const SteInputs *ia, SteOutputs *oa, const SteProblem *pb,
-                          const SteInputs *ib, SteOutputs *ob) {
-    KernelArgs a, b;
-    a.prob = *pa; a.in = *ia; a.out = *oa;
-    b.prob = *pb; b.in = *ib; b.out = *ob;
-    bool pos = !(pa->flags & STE_FLAG_FORCE_GENERIC);
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-            const double h = (i == j && i < 2) ? 1.0 : 0.0;
-            if (pa->H[i * 4 + j] != h) pos = false;
-            if ((i >= 2 || j >= 2) && pa->R[i * 4 + j] != 0.0) pos = false;
-        }
-    const bool gating = pa->flags & STE_FLAG_GATING;
-    double scratch[kScratchSlotsFused];
-    const Scratch sc{scratch, 1};
-    const int n = pa->n_tracks > pb->n_tracks ? pa->n_tracks : pb->n_tracks;
-    for (int t = 0; t < n; ++t) {
-        if (pos) { if (gating) fused_track<true, true>(a, b, t, sc); else fused_track<true, false>(a, b, t, sc); }
-        else     { if (gating) fused_track<false, true>(a, b, t, sc); else fused_track<false, false>(a, b, t, sc); }
-    }
-    return 0;
-}
-
 // geodetic step of n states through the generic branch-free tier and the small-displacement tier
 extern "C" void emul_geodetic_tiers(int n, const double *x, const double *dt, const double *sr, const double *cr,
                                     double *y_generic, double *y_small) {

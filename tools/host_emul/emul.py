@@ -48,54 +48,10 @@ class HostUKF(BatchedUKF):
         assert fn(C.byref(p), C.byref(i), C.byref(o)) == 0
     def forward(self, b, res): self._call(self._emul.emul_forward, b, res)
     def backward(self, b, res): self._call(self._emul.emul_backward, b, res)
-    def fused(self, fb, fr, bb, br):
-        keep = nat.ptr
-        nat.ptr = lambda t: None if t is None else t.data_ptr()
-        try:
-            a = (self._problem(fb), self._inputs(fb), self._outputs(fr), self._problem(bb), self._inputs(bb), self._outputs(br))
-        finally:
-            nat.ptr = keep
-        assert self._emul.emul_fused(*[C.byref(v) for v in a]) == 0
-
-def check_fused(names):
-    """fused(A, B) must reproduce forward(A) + backward(B) bit for bit (host build)."""
-    from types import SimpleNamespace
-    from _helpers import load_golden
-    for name in names:
-        tracks, _ = load_golden(name)
-        if "means_s" not in tracks[0]:
-            continue
-        tr0 = tracks[0]
-        gating = "gate_iters" in tr0
-        def batch(sel):
-            sts = [SimpleNamespace(dts=t["dts"], z=t["z"], sog_rate=t["sog_rate"], cog_rate=t["cog_rate"]) for t in sel]
-            noise = [dict(pred=t["noise_pred"], upd=t["noise_upd"], bwd=t.get("noise_bwd")) for t in sel] if "noise_pred" in tr0 else None
-            return TrackBatch.from_tracks(sts, [t["dt_array"] for t in sel], device="cpu", x0=[t["x0"] for t in sel], noise=noise, smoother=True)
-        A, B = batch(tracks[: max(1, len(tracks) // 2 + 1)]), batch(tracks[::-1][: max(1, len(tracks) // 2)])
-        for packed in (False, True):
-            u = HostUKF(tr0["H"], tr0["Q"], tr0["R"], tr0["P0"], gating=gating, packed_cov=packed)
-            ra, rb = u.allocate(A, smoother=True), u.allocate(B, smoother=True)
-            u.forward(A, ra); u.forward(B, rb); u.backward(B, rb)
-            fa, fb = u.allocate(A, smoother=True), u.allocate(B, smoother=True)
-            u.forward(B, fb); u.fused(A, fa, B, fb)
-            u.backward(A, ra)
-            ga = u.allocate(A, smoother=True)           # and A smoothed by a fused launch with an empty forward tile
-            u.forward(A, ga); u.fused(B, u.allocate(B, smoother=True), A, ga)
-            for x, y, n, what in ((ra, fa, A.n_tracks, "A fwd"), (rb, fb, B.n_tracks, "B bwd"), (ra, ga, A.n_tracks, "A bwd")):
-                for i in range(n):
-                    p, q = x.track(i), y.track(i)
-                    for k in p:
-                        if what == "A fwd" and k in ("means_s", "covs_s", "status"):
-                            continue
-                        assert np.array_equal(p[k], q[k], equal_nan=True), (name, packed, what, i, k)
-            print(f"{name:22s} packed={packed}: fused == separate (A {A.n_tracks} tracks, B {B.n_tracks} tracks)")
 
 if __name__ == "__main__":
     from types import SimpleNamespace
     from _helpers import load_golden, track_errors
-    if sys.argv[1:2] == ["--fused"]:
-        check_fused(sys.argv[2:] or ["c1_single_ship", "c2_historical_batch", "c4_ragged_ungated", "c4_ragged_gated", "tape_noise"])
-        sys.exit(0)
     names = sys.argv[1:] or ["c1_single_ship", "c2_historical_batch", "c2_modern_ship", "c3_const_dt", "c4_ragged_ungated", "c4_ragged_gated", "tape_noise", "dense_h"]
     for name in names:
         tracks, _ = load_golden(name)

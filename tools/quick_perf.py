@@ -13,6 +13,8 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--generic", action="store_true")
 ap.add_argument("--packed", action="store_true")
 ap.add_argument("--fused", action="store_true")
+ap.add_argument("--fused-fwd-tracks", type=int, default=0, help="tile size of the forward side of the fused launch (default: --tracks)")
+ap.add_argument("--fused-bwd-tracks", type=int, default=0, help="tile size of the backward side of the fused launch (default: --tracks)")
 ap.add_argument("--no-probe", action="store_true")
 ap.add_argument("--no-metrics", action="store_true")
 ap.add_argument("--label", default="")
@@ -58,10 +60,13 @@ if not a.no_metrics:
     print(json.dumps({"track_metrics_ms": m_ms, "GBs_algorithmic": ts * 32 / m_ms / 1e6}))
 
 if a.fused:
-    syn2 = make_tracks(a.tracks, a.steps + 1, seed=2, device="cuda:0")
-    batch2 = TrackBatch.from_synthetic(syn2, substeps=1)
+    nf, nb = a.fused_fwd_tracks or a.tracks, a.fused_bwd_tracks or a.tracks
+    batch2 = TrackBatch.from_synthetic(make_tracks(nf, a.steps + 1, seed=2, device="cuda:0"), substeps=1)
     res2 = ukf.allocate(batch2, smoother=True)
+    if nb != a.tracks:
+        batch = TrackBatch.from_synthetic(make_tracks(nb, a.steps + 1, seed=1, device="cuda:0"), substeps=1)
+        res = ukf.allocate(batch, smoother=True)
     ukf.forward(batch, res)
     fu_ms, fu_all = timed(lambda: ukf.fused(batch2, res2, batch, res), a.reps)
-    print(json.dumps({"fused_ms": fu_ms, "separate_ms": f_ms + b_ms, "fused_steps_per_s": ts / fu_ms * 1e3,
+    print(json.dumps({"fused_ms": fu_ms, "fwd_tracks": nf, "bwd_tracks": nb, "separate_ms": f_ms + b_ms, "fused_steps_per_s": ts / fu_ms * 1e3,
                       "gain": (f_ms + b_ms) / fu_ms, "all": fu_all}))
