@@ -129,14 +129,17 @@ STE_DEV double seed_rsqrt(double x) {
 // reciprocal, reciprocal square root, square root, division: MUFU seed (~20 bits) + Newton steps in
 // the FP64 pipe; no denormal / special-case slow paths: callers guarantee finite, normal, non-zero
 // arguments (or guard the result themselves).
-template <int N>
+// NEWTON = 2: full precision (2^-20 -> 2^-40 -> 2^-80).  NEWTON = 1: 2^-40, for callers whose own correction
+// step or whose error budget makes the second step redundant (fast_div_v; first-order terms of a series).
+template <int N, int NEWTON = 2>
 STE_DEV void fast_rcp_v(const double (&x)[N], double (&y)[N]) {
     double e[N];
     STE_LANES y[l] = seed_rcp(x[l]);
-    STE_LANES e[l] = fma(-x[l], y[l], 1.0);
-    STE_LANES y[l] = fma(y[l], e[l], y[l]);
-    STE_LANES e[l] = fma(-x[l], y[l], 1.0);
-    STE_LANES y[l] = fma(y[l], e[l], y[l]);
+#pragma unroll
+    for (int it = 0; it < NEWTON; ++it) {
+        STE_LANES e[l] = fma(-x[l], y[l], 1.0);
+        STE_LANES y[l] = fma(y[l], e[l], y[l]);
+    }
 }
 
 // y <- y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2 : cubic convergence, 2^-20 -> 2^-60
@@ -165,8 +168,10 @@ STE_DEV void fast_sqrt_v(const double (&x)[N], double (&s)[N]) {
 
 template <int N>
 STE_DEV void fast_div_v(const double (&num)[N], const double (&den)[N], double (&q)[N]) {
+    // r to 2^-40 is enough: q0 = num r is off by 2^-40 relative, the residual num - den q0 is exact (fma), and the
+    // correction rem r carries the 2^-40 of r on a term that is itself 2^-40 of q: 2^-80 before the final rounding
     double r[N], rem[N];
-    fast_rcp_v<N>(den, r);
+    fast_rcp_v<N, 1>(den, r);
     STE_LANES q[l] = num[l] * r[l];
     STE_LANES rem[l] = fma(-den[l], q[l], num[l]);
     STE_LANES q[l] = fma(rem[l], r[l], q[l]);
@@ -251,10 +256,10 @@ template <int N>
 STE_DEV void small_sincos_v(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
     double z[N], ps[N], pc[N];
     STE_LANES z[l] = x[l] * x[l];
-    STE_LANES { ps[l] = fma(z[l], STE_SINC(3), STE_SINC(2)); pc[l] = fma(z[l], STE_COSC(4), STE_COSC(3)); }
-    STE_LANES { ps[l] = fma(z[l], ps[l], STE_SINC(1)); pc[l] = fma(z[l], pc[l], STE_COSC(2)); }
-    STE_LANES { ps[l] = fma(z[l], ps[l], STE_SINC(0)); pc[l] = fma(z[l], pc[l], STE_COSC(1)); }
-    STE_LANES pc[l] = fma(z[l], pc[l], STE_COSC(0));
+    // cosine: the z^6 term (coefficient 2.1e-9) is below 4.2e-20 for |x| <= 0.125 and is left out
+    STE_LANES { ps[l] = fma(z[l], STE_SINC(3), STE_SINC(2)); pc[l] = fma(z[l], STE_COSC(3), STE_COSC(2)); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], STE_SINC(1)); pc[l] = fma(z[l], pc[l], STE_COSC(1)); }
+    STE_LANES { ps[l] = fma(z[l], ps[l], STE_SINC(0)); pc[l] = fma(z[l], pc[l], STE_COSC(0)); }
     STE_LANES { sn[l] = fma(x[l] * z[l], ps[l], x[l]); cs[l] = fma(z[l] * z[l], pc[l], fma(-0.5, z[l], 1.0)); }
 }
 

@@ -93,7 +93,12 @@ STE_DEV bool step_is_small(const double (&x)[4], const double (&P)[10], double d
     const double su2 = 3.0 * P[SYM(2, 2)], sl2 = 3.0 * P[SYM(1, 1)];
     const double a = kSmallAsinMax - fabs(x[2] * dtR);     // room left for the speed offset, in radians
     const double b = kSmallLatMaxDeg - fabs(x[1]);         // room left for the latitude offset, in degrees
-    return (a > 0.0) && (b > 0.0) && (su2 >= 0.0) && (sl2 >= 0.0) && (su2 * (dtR * dtR) <= a * a) && (sl2 <= b * b);   // false on NaN
+    // ... and the three offset angles of every root column stay within the short sincos series (kSmallAngle): the
+    // distance offset already does (a <= 2^-6), latitude and course offsets are bounded by sqrt(3 P_11), sqrt(3 P_33)
+    const double sc2 = 3.0 * P[SYM(3, 3)];
+    constexpr double kOff2 = (kSmallAngle * kRadToDeg) * (kSmallAngle * kRadToDeg);   // (7.16 degrees)^2
+    return (a > 0.0) && (b > 0.0) && (su2 >= 0.0) && (sl2 >= 0.0) && (su2 * (dtR * dtR) <= a * a) && (sl2 <= b * b) &&
+           (sl2 <= kOff2) && (sc2 <= kOff2);   // false on NaN
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -144,7 +149,7 @@ STE_DEV void sigma_pair_loop(const double (&x)[4], const AngleTrig &base, const 
             }
         if constexpr (LIB || NC == 1) {
 #pragma unroll
-            for (int k = 0; k < NC; ++k) angle_add_pair(base, offset_trig<LIB>(m[k][1], m[k][3], m[k][2], dtR), tt[2 * k], tt[2 * k + 1]);
+            for (int k = 0; k < NC; ++k) angle_add_pair(base, offset_trig<LIB, SMALL>(m[k][1], m[k][3], m[k][2], dtR), tt[2 * k], tt[2 * k + 1]);
         } else {
             // the offsets of all NC columns through one lock-step series; the full-range evaluation replaces it
             // (for all of them) only when some offset is not small
@@ -336,7 +341,7 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
     }
     if (fast) {
         predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld,
-                               allow_small && step_is_small(x, P, dtR), clamped);
+                               allow_small && !clamped && step_is_small(x, P, dtR), clamped);   // a clamped root is not bounded by P's diagonal
     } else {
         double xt[4], Pt[10], et[4];
 #pragma unroll
@@ -556,27 +561,27 @@ STE_DEV void ukf_update_position(double (&x)[4], double (&P)[10], const Model &m
 #pragma unroll
     for (int r = 0; r < 4; ++r) x[r] = fma(K0[r], y0, fma(K1[r], y1, x[r]));
     x[3] = py_mod360(x[3]);
-    // AP = P - K P[0:2, :]
+    // Joseph form (I - K H) P (I - K H)^T + K (rs R) K^T (:260-265) with AP = (I - K H) P = P - K P[0:2, :]:
+    //     AP A^T + KR K^T = AP + (KR - AP[:, 0:2]) K^T
+    // the same sum with the two rank-2 products merged (W = KR - AP[:, 0:2] is the gain's optimality residual: the
+    // errors of AP's position columns still meet their cancelling partner, as in the four-product form)
     double AP[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            AP[i * 4 + j] = fma(-K0[i], P[SYM(0, j)], fma(-K1[i], P[SYM(1, j)], P[SYM(i, j)]));
-    // K (rs R22) K^T
-    double KR0[4], KR1[4];
+            if (j < 2 || j >= i) AP[i * 4 + j] = fma(-K0[i], P[SYM(0, j)], fma(-K1[i], P[SYM(1, j)], P[SYM(i, j)]));
+    const double q00 = rs * r00, q01 = rs * r01, q11 = rs * r11;
+    double W0[4], W1[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        KR0[r] = rs * fma(K0[r], r00, K1[r] * r01);
-        KR1[r] = rs * fma(K0[r], r01, K1[r] * r11);
+        W0[r] = fma(K0[r], q00, K1[r] * q01) - AP[r * 4 + 0];
+        W1[r] = fma(K0[r], q01, K1[r] * q11) - AP[r * 4 + 1];
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = i; j < 4; ++j) {
-            double acc = fma(-AP[i * 4 + 0], K0[j], fma(-AP[i * 4 + 1], K1[j], AP[i * 4 + j]));
-            P[SYM(i, j)] = fma(KR0[i], K0[j], fma(KR1[i], K1[j], acc));
-        }
+        for (int j = i; j < 4; ++j) P[SYM(i, j)] = fma(W0[i], K0[j], fma(W1[i], K1[j], AP[i * 4 + j]));
 }
 
 // ------------------------------------------------------------------------------------------ //

@@ -38,7 +38,7 @@ struct Scratch {
 };
 
 // Python / numpy floored modulo by 360 (result in [0, 360], sign of the divisor).
-STE_DEV double py_mod360(double a) {
+STE_COLD double py_mod360_general(double a) {
     double r = fmod(a, 360.0);
     if (r != 0.0) {
         if (r < 0.0) r += 360.0;
@@ -46,6 +46,11 @@ STE_DEV double py_mod360(double a) {
         r = 0.0;  // copysign(0, 360)
     }
     return r;
+}
+// a course that is already in [0, 360) - nearly every call - comes back unchanged (a + 0.0: -0.0 -> +0.0 as Python gives)
+STE_DEV double py_mod360(double a) {
+    if (a >= 0.0 && a < 360.0) return a + 0.0;
+    return py_mod360_general(a);
 }
 STE_DEV double wrap180(double a) { return py_mod360(a + 180.0) - 180.0; }
 
@@ -68,14 +73,20 @@ STE_DEV void jacobi_params(const double (&app)[N], const double (&aqq)[N], const
     STE_LANES { d[l] = aqq[l] - app[l]; b[l] = apq[l] + apq[l]; }
     STE_LANES v[l] = fma(d[l], d[l], b[l] * b[l]);
     fast_rsqrt_v<N>(v, rh);
-    STE_LANES cc[l] = fma(0.5, fabs(d[l]) * rh[l], 0.5);
+    // identity on a zero or underflowed pivot (also d == b == 0) from TWO selects: 1/h := 0 makes sin 2theta = 0, and
+    // cos^2 theta := 1 makes cos theta = 1 (rsqrt(1) is exactly 1: its residual is 0), so c = 1, s = t = 0
+    bool skip[N];
+    STE_LANES {
+        skip[l] = (apq[l] == 0.0) || !(v[l] > 1e-290);
+        rh[l] = skip[l] ? 0.0 : rh[l];
+        cc[l] = skip[l] ? 1.0 : fma(0.5, fabs(d[l]) * rh[l], 0.5);
+    }
     fast_rsqrt_v<N>(cc, rc);
     STE_LANES {
-        const bool skip = (apq[l] == 0.0) || !(v[l] > 1e-290);   // zero or underflowed pivot: identity (also d == b == 0)
         const double s2t = (d[l] >= 0.0 ? b[l] : -b[l]) * rh[l];
-        c[l] = skip ? 1.0 : cc[l] * rc[l];
-        s[l] = skip ? 0.0 : (0.5 * s2t) * rc[l];
-        t[l] = s[l] * (skip ? 1.0 : rc[l]);
+        c[l] = cc[l] * rc[l];
+        s[l] = (0.5 * s2t) * rc[l];
+        t[l] = s[l] * rc[l];
     }
 }
 
@@ -286,9 +297,11 @@ constexpr int kSqrtRotSlots = kSqrtMaxSweeps * kSweepSlots;
 
 STE_DEV bool jacobi_off_within(const double (&a)[10], double eps2) {
     const double w[4] = {a[SYM(0, 0)], a[SYM(1, 1)], a[SYM(2, 2)], a[SYM(3, 3)]};
-    const double wmax = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
-    const double wmin = fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
-    bool ok = wmin > 1e-12 * wmax;   // false on NaN
+    // every diagonal entry against 1e-12 of the trace (wmax <= trace <= 4 wmax on a positive diagonal): no max / min chains
+    const double lim = 1e-12 * ((w[0] + w[1]) + (w[2] + w[3]));
+    bool ok = lim > 0.0;             // false on NaN and on a non-positive trace
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ok &= w[k] > lim;
 #pragma unroll
     for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -329,10 +342,7 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], con
     for (int k = 0; k < 4; ++k) w[k] = a[SYM(k, k)];
     fast_rsqrt_v<4>(w, rs);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double s0 = w[k] * rs[k];
-        sd[k] = fma(fma(-s0, s0, w[k]), 0.5 * rs[k], s0);   // one Newton correction: correctly rounded root (as fast_sqrt)
-    }
+    for (int k = 0; k < 4; ++k) sd[k] = w[k] * rs[k];   // within 2 ulp of the root (rs is good to 2^-60); no correction step
     // pair sums and their reciprocals, pairs in SYM order: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
     double ssum[6], rsum[6], X[10], G[10];
     {
@@ -342,7 +352,9 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], con
 #pragma unroll
             for (int q = p + 1; q < 4; ++q) ssum[k++] = sd[p] + sd[q];
     }
-    fast_rcp_v<6>(ssum, rsum);
+    // 2^-40 relative is enough: the reciprocals only multiply off-diagonal terms that are <= 1e-4 of the smaller root
+    // eigenvalue of their pair, so their error stays below 1e-16 of it
+    fast_rcp_v<6, 1>(ssum, rsum);
     {
         int k = 0;
 #pragma unroll
@@ -545,18 +557,23 @@ STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dt
 }
 
 // trig of the three offset angles of one root column: the short series, replaced by the full-range
-// evaluation only when an offset is not small (a wide course or latitude spread; written as an
-// overwrite so that the common path carries no merge copies)
-template <bool LIB>
+// evaluation only when an offset is not small (a wide course or latitude spread)
+// KNOWN_SMALL: the caller has bounded all three offsets by kSmallAngle for this step (step_is_small)
+template <bool LIB, bool KNOWN_SMALL = false>
 STE_DEV AngleTrig offset_trig(double dlat_deg, double dcog_deg, double du, double dtR) {
     if (LIB) return angle_trig<LIB>(dlat_deg, dcog_deg, du, dtR);
     const double ang[3] = {dlat_deg * kDegToRad, dcog_deg * kDegToRad, du * dtR};
     AngleTrig t;
     double sn[3], cs[3];
-    small_sincos_v<3>(ang, sn, cs);
+    if constexpr (KNOWN_SMALL) {
+        small_sincos_v<3>(ang, sn, cs);
+    } else {
+        // decide first, then evaluate ONE of the two: both arms write the same six values (no merge copies on the common arm)
+        const bool small = fabs(ang[0]) <= kSmallAngle && fabs(ang[1]) <= kSmallAngle && fabs(ang[2]) <= kSmallAngle;
+        if (__builtin_expect(small, 1)) small_sincos_v<3>(ang, sn, cs);
+        else fast_sincos_v<3>(ang, sn, cs);
+    }
     t.sp = sn[0]; t.cp = cs[0]; t.sa = sn[1]; t.ca = cs[1]; t.sd = sn[2]; t.cd = cs[2];
-    const bool small = fabs(ang[0]) <= kSmallAngle && fabs(ang[1]) <= kSmallAngle && fabs(ang[2]) <= kSmallAngle;
-    if (__builtin_expect(!small, 0)) t = angle_trig<false>(dlat_deg, dcog_deg, du, dtR);
     return t;
 }
 
