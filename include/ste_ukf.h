@@ -82,7 +82,7 @@ typedef struct SteProblem {
     uint32_t flags;        /* STE_FLAG_*                                                    */
     int32_t gate_max_iter; /* cap on robustification iterations (reference: unbounded)      */
     int32_t reserved;      /* must be 0                                                     */
-    int64_t ld;            /* leading dimension of every SoA array (>= n_tracks)            */
+    int64_t ld;            /* leading dimension of every SoA array (>= n_tracks, < 2^29)    */
     double gate_chi;       /* chi_alpha, reference value 50 (unscented.py:357)              */
     double H[16];
     double Q[16];

@@ -199,10 +199,11 @@ template <bool LIB>
 STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, double dt, double dtR,
                              double sog_rate, double cog_rate, const double (&e)[4], const Scratch &sc,
                              double *sig_prior, double *sig_post, double *stats, int64_t ld, const bool small = false,
-                             const bool clamped = false) {
-    const AngleTrig base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
+                             const bool clamped = false, const bool noisy = true) {
+    AngleTrig base;
     double c[4];
     if (!LIB && small) {
+        base = angle_trig<LIB, true>(x[1], x[3], x[2], dtR);
         geodetic_finish<LIB, true>(x, base, dt, sog_rate, cog_rate, c);
         if (sig_prior) {
 #pragma unroll
@@ -213,6 +214,7 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
         }
         sigma_pair_loop<LIB, true>(x, base, c, dt, dtR, sog_rate, cog_rate, sc, sig_prior, sig_post, ld);
     } else {
+        base = angle_trig<LIB>(x[1], x[3], x[2], dtR);
         geodetic_finish<LIB, false>(x, base, dt, sog_rate, cog_rate, c);
         if (sig_prior) {
 #pragma unroll
@@ -286,24 +288,32 @@ STE_DEV void predict_moments(double (&x)[4], double (&P)[10], const double *Q, d
                 cov[SYM(r, q)] = fma(2.0 * kWi, acc, Q[r * 4 + q]);
             }
     }
+    if (noisy) {   // launch-uniform: a noise tape is present
 #pragma unroll
-    for (int r = 0; r < 4; ++r) x[r] = c[r] + ((r < 2 ? mu[r] : 0.0) + e[r]);
+        for (int r = 0; r < 4; ++r) x[r] = c[r] + ((r < 2 ? mu[r] : 0.0) + e[r]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int q = r; q < 4; ++q) P[SYM(r, q)] = fma(e[r], e[q], cov[SYM(r, q)]);
+            for (int q = r; q < 4; ++q) P[SYM(r, q)] = fma(e[r], e[q], cov[SYM(r, q)]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[r] = r < 2 ? c[r] + mu[r] : c[r];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) P[k] = cov[k];
+    }
     if (stats) {
         // position block of P_b (about x); a clamped root invalidates the entry (see kStatsPlanes)
-        STE_STORE_STREAM(stats + (kStatsPb + 0) * ld, fma(delta[0], delta[0], cov[SYM(0, 0)]));
-        STE_STORE_STREAM(stats + (kStatsPb + 1) * ld, fma(delta[0], delta[1], cov[SYM(0, 1)]));
-        STE_STORE_STREAM(stats + (kStatsPb + 2) * ld, fma(delta[1], delta[1], cov[SYM(1, 1)]));
+        const uint32_t ldb = (uint32_t)ld * 8u;
+        STE_STORE_STREAM(plane_ptr(stats, ldb, kStatsPb + 0), fma(delta[0], delta[0], cov[SYM(0, 0)]));
+        STE_STORE_STREAM(plane_ptr(stats, ldb, kStatsPb + 1), fma(delta[0], delta[1], cov[SYM(0, 1)]));
+        STE_STORE_STREAM(plane_ptr(stats, ldb, kStatsPb + 2), fma(delta[1], delta[1], cov[SYM(1, 1)]));
         STE_STORE_STREAM(stats, clamped ? f64_from_bits(0x7ff8000000000000ull) : delta[0]);
 #pragma unroll
-        for (int r = 1; r < 4; ++r) STE_STORE_STREAM(stats + r * ld, delta[r]);
+        for (int r = 1; r < 4; ++r) STE_STORE_STREAM(plane_ptr(stats, ldb, r), delta[r]);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int r = 0; r < 2; ++r) STE_STORE_STREAM(stats + (kStatsD + q * 2 + r) * ld, G[q][r]);
+            for (int r = 0; r < 2; ++r) STE_STORE_STREAM(plane_ptr(stats, ldb, kStatsD + q * 2 + r), G[q][r]);
     }
 }
 
@@ -329,7 +339,7 @@ STE_COLD void predict_moments_cold(double *x_io, double *P_out, const double *Q,
 STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, double dt,
                          double sog_rate, double cog_rate, const double (&e)[4],
                          int &status, const Scratch &sc, double *sig_prior, double *sig_post, double *stats,
-                         int64_t ld, const bool allow_small = true) {
+                         int64_t ld, const bool allow_small = true, const bool noisy = true) {
     const double dtR = dt * (1.0 / kEarthRadiusKm);
     const bool fast = step_in_fast_range(x, P, dtR);
     bool clamped;
@@ -341,7 +351,7 @@ STE_DEV void ukf_predict(double (&x)[4], double (&P)[10], const double *Q, doubl
     }
     if (fast) {
         predict_moments<false>(x, P, Q, dt, dtR, sog_rate, cog_rate, e, sc, sig_prior, sig_post, stats, ld,
-                               allow_small && !clamped && step_is_small(x, P, dtR), clamped);   // a clamped root is not bounded by P's diagonal
+                               allow_small && !clamped && step_is_small(x, P, dtR), clamped, noisy);   // a clamped root is not bounded by P's diagonal
     } else {
         double xt[4], Pt[10], et[4];
 #pragma unroll

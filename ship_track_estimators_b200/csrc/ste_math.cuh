@@ -37,6 +37,15 @@ struct Scratch {
     STE_DEV double &at(int slot) const { return base[(long)slot * stride]; }
 };
 
+// Plane k (a compile-time index) of a [plane][track] array whose plane stride is ld_bytes: base + k * ld_bytes as ONE
+// integer instruction (32-bit stride x immediate + 64-bit base; the C ABI limits ld to 2^29 - 1 tracks for this).
+STE_DEV double *plane_ptr(double *base, uint32_t ld_bytes, uint32_t k) {
+    return reinterpret_cast<double *>(reinterpret_cast<char *>(base) + (uint64_t)ld_bytes * k);
+}
+STE_DEV const double *plane_ptr(const double *base, uint32_t ld_bytes, uint32_t k) {
+    return reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + (uint64_t)ld_bytes * k);
+}
+
 // Python / numpy floored modulo by 360 (result in [0, 360], sign of the divisor).
 STE_COLD double py_mod360_general(double a) {
     double r = fmod(a, 360.0);
@@ -540,13 +549,21 @@ struct AngleTrig {
     double sd, cd;   // angular distance u dt / R
 };
 
-template <bool LIB>
+// SMALL_DIST: the caller has bounded the angular distance |u dt / R| by kSmallAngle (step_is_small: 2^-6), so its sine and
+// cosine come from the short series (no range reduction, no quadrant selects)
+template <bool LIB, bool SMALL_DIST = false>
 STE_DEV AngleTrig angle_trig(double lat_deg, double cog_deg, double u, double dtR) {
     AngleTrig t;
     if (LIB) {
         sincos(lat_deg * kDegToRad, &t.sp, &t.cp);
         sincos(cog_deg * kDegToRad, &t.sa, &t.ca);
         sincos(u * dtR, &t.sd, &t.cd);
+    } else if constexpr (SMALL_DIST) {
+        const double ang[2] = {lat_deg * kDegToRad, cog_deg * kDegToRad}, dist[1] = {u * dtR};
+        double sn[2], cs[2], sd[1], cd[1];
+        fast_sincos_v<2>(ang, sn, cs);
+        small_sincos_v<1>(dist, sd, cd);
+        t.sp = sn[0]; t.cp = cs[0]; t.sa = sn[1]; t.ca = cs[1]; t.sd = sd[0]; t.cd = cd[0];
     } else {
         const double ang[3] = {lat_deg * kDegToRad, cog_deg * kDegToRad, u * dtR};
         double sn[3], cs[3];

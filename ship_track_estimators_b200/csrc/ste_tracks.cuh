@@ -41,19 +41,21 @@ STE_DEV int cov_plane(bool packed, int i, int j) { return packed ? SYM(i, j) : i
 
 STE_DEV void store_state(double *mean, double *cov, int64_t ld, int64_t s, int t, bool packed,
                          const double (&x)[4], const double (&P)[10]) {
-    // planes are consecutive in both layouts: one 64-bit add per store instead of a plane * ld product
+    // planes are consecutive in both layouts: plane k of a state is base + k * (ld * 8 bytes), one 32 x 32 + 64-bit
+    // multiply-add per store (plane_ptr)
+    const uint32_t ldb = (uint32_t)ld * 8u;
     double *m = mean + (s * 4) * ld + t;
 #pragma unroll
-    for (int r = 0; r < 4; ++r, m += ld) STE_STORE_STREAM(m, x[r]);
+    for (int r = 0; r < 4; ++r) STE_STORE_STREAM(plane_ptr(m, ldb, r), x[r]);
     double *c = cov + (s * cov_planes(packed)) * ld + t;
     if (packed) {
 #pragma unroll
-        for (int k = 0; k < 10; ++k, c += ld) STE_STORE_STREAM(c, P[k]);
+        for (int k = 0; k < 10; ++k) STE_STORE_STREAM(plane_ptr(c, ldb, k), P[k]);
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j, c += ld) STE_STORE_STREAM(c, P[SYM(i, j)]);
+            for (int j = 0; j < 4; ++j) STE_STORE_STREAM(plane_ptr(c, ldb, i * 4 + j), P[SYM(i, j)]);
     }
 }
 
@@ -108,19 +110,21 @@ struct ForwardTrack {
         : a(args), t(track), sc(scratch), ld(args.prob.ld), packed((args.prob.flags & STE_FLAG_PACKED_COV) != 0) {}
 
     // observation rows are staged into scratch a whole predict ahead of their use
+    // row u of a [row][track] input array for this track: base + t, then one 32 x 32 + 64-bit multiply-add (plane_ptr)
+    STE_DEV const double *row_ptr(const double *base, int u) const { return plane_ptr(base + t, (uint32_t)ld * 8u, (uint32_t)u); }
     STE_DEV void stage_obs(int u) const {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            if ((!POS_ONLY || r < 2) && a.in.z[r]) stage_async(&sc.at(kScratchObs + r), a.in.z[r] + (int64_t)u * ld + t);
+            if ((!POS_ONLY || r < 2) && a.in.z[r]) stage_async(&sc.at(kScratchObs + r), row_ptr(a.in.z[r], u));
         }
     }
     // Inputs of step s (dt, the two rates, the observation of its update) are staged into shared
     // scratch with cp.async one whole step ahead: no register is held across the sigma-point loop
     // and the DRAM latency hides behind ~4000 instructions of the previous step.
     STE_DEV void stage_step(int s, int rate_index) const {
-        stage_async(&sc.at(kScratchIn + 0), a.in.dt + (int64_t)s * ld + t);
-        stage_async(&sc.at(kScratchIn + 1), a.in.sog_rate + (int64_t)rate_index * ld + t);
-        stage_async(&sc.at(kScratchIn + 2), a.in.cog_rate + (int64_t)rate_index * ld + t);
+        stage_async(&sc.at(kScratchIn + 0), row_ptr(a.in.dt, s));
+        stage_async(&sc.at(kScratchIn + 1), row_ptr(a.in.sog_rate, rate_index));
+        stage_async(&sc.at(kScratchIn + 2), row_ptr(a.in.cog_rate, rate_index));
     }
     // does step s end on an observation?  (called once per step, in order: s = 0, 1, 2, ...)
     STE_DEV bool step_updates(int s) {
@@ -213,7 +217,8 @@ struct ForwardTrack {
             for (int r = 0; r < 4; ++r)
                 e[r] = a.in.noise_pred[((int64_t)s * 4 + r) * ld + t] * sqrt(a.prob.Q[r * 5]);
         }
-        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld, !(a.prob.flags & STE_FLAG_LONG_STEPS));
+        ukf_predict(x, P, a.prob.Q, dt, sr, cr, e, status, sc, nullptr, nullptr, stats, ld, !(a.prob.flags & STE_FLAG_LONG_STEPS),
+                    a.in.noise_pred != nullptr);
         // more matched update times than observation rows: the reference raises IndexError here
         // (kalman_filter.py:101-108); the track is flagged and the update skipped, nothing is re-read
         if (advance) assimilate(++ui);

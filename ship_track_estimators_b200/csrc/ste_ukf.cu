@@ -598,6 +598,7 @@ static int validate_problem(const SteProblem *p) {
     if (!p) return fail(STE_ERR_INVALID_ARG, "null SteProblem");
     if (p->n_tracks < 0 || p->max_steps < 0 || p->max_obs < 1) return fail(STE_ERR_INVALID_ARG, "negative sizes");
     if (p->ld < p->n_tracks) return fail(STE_ERR_INVALID_ARG, "ld < n_tracks");
+    if (p->ld >= (1ll << 29)) return fail(STE_ERR_INVALID_ARG, "ld >= 2^29 (the kernels address planes with 32-bit byte strides)");
     if (!is_symmetric(p->Q) || !is_symmetric(p->R) || !is_symmetric(p->P0))
         return fail(STE_ERR_UNSUPPORTED, "Q, R and P0 must be symmetric");
     return STE_OK;
