@@ -32,9 +32,10 @@
 extern "C" {
 #endif
 
-#define STE_ABI_VERSION 4   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
+#define STE_ABI_VERSION 5   /* 2: ste_ukf_fused_f64, ste_track_metrics_f64, geodesy argument of ste_derive_inputs_f64, STE_FLAG_LONG_STEPS */
                             /* 3: smooth_stats holds STE_STATS_PLANES = 15 planes per step (was 30)                                          */
                             /* 4: SteInputs.R_tracks, dimension-generic steps (ste_ukf_*_n_f64, ste_process_f64), ste_gate_terms_f64          */
+                            /* 5: ste_urtss_backward_n_f64 (dimension-generic smoother); ld < 2^29                                            */
 #define STE_STATS_PLANES 15
 #define STE_DIM 4
 #define STE_NSIGMA 9
@@ -183,6 +184,10 @@ int ste_ukf_update_f64(const SteProblem *prob, double *x, double *P, const doubl
  *   dt [T]; noise [n][ld] unit normals or NULL; sigma_prior / sigma_post [n*(2n+1)][ld] or NULL; status [T] or NULL.
  * ste_ukf_update_n_f64: UnscentedKalmanFilter.update (unscented.py:209-265) with dense H and R; state index 3 is
  *   the heading (innovation wrapped to [-180, 180), state taken modulo 360) as the reference hard-codes (:250, 257).
+ * ste_urtss_backward_n_f64: UnscentedKalmanFilter.rts_step (unscented.py:267-351), the whole backward loop of T tracks
+ *   of n_states stored states each: mean_f / mean_s [n_states][n][ld], cov_f / cov_s [n_states][n*n][ld] (distinct
+ *   arrays), dt [n_states-1][ld], sog_rate / cog_rate [n_rates][ld] indexed by step / rate_repeat (the reference's
+ *   np.repeat expansion, :287-292), noise [n_states-1][n][ld] unit normals in step order or NULL; status [T] or NULL.
  * ste_process_f64: one evaluation of the process model for T states, x_in / x_out [n][ld]. */
 #define STE_MODEL_GEODETIC 0
 #define STE_MODEL_GEODETIC_TURN 1
@@ -191,6 +196,10 @@ int ste_ukf_predict_n_f64(int32_t n, int32_t model, int32_t n_tracks, int64_t ld
                           double *sigma_prior, double *sigma_post, int32_t *status, void *stream);
 int ste_ukf_update_n_f64(int32_t n, int32_t n_tracks, int64_t ld, const double *H_host, const double *R_host, double *x,
                          double *P, const double *z, const double *noise, int32_t *status, void *stream);
+int ste_urtss_backward_n_f64(int32_t n, int32_t model, int32_t n_tracks, int64_t ld, int32_t n_states, int32_t rate_repeat,
+                             int32_t n_rates, const double *Q_host, const double *mean_f, const double *cov_f, const double *dt,
+                             const double *sog_rate, const double *cog_rate, const double *noise, double *mean_s,
+                             double *cov_s, int32_t *status, void *stream);
 int ste_process_f64(int32_t model, int32_t n, int32_t n_tracks, int64_t ld, const double *x_in, const double *dt,
                     const double *sog_rate, const double *cog_rate, double *x_out, void *stream);
 

@@ -221,4 +221,111 @@ STE_DEV void update_n(const ProblemN &p, int t, double *x_io, double *P_io, cons
     if (status) status[t] = bad ? STE_STATUS_NONFINITE : 0;
 }
 
+// UnscentedKalmanFilter.rts_step (unscented.py:267-351) for any n <= 8 and a device process model: the whole backward
+// loop of one track.  mean_f / mean_s [S][n][ld], cov_f / cov_s [S][n*n][ld] with S = n_states; dt [S-1][ld]; the rates
+// [n_rates][ld], indexed by step / rate_repeat as the reference's np.repeat expansion does (:287-292); noise [S-1][n][ld]
+// unit normals in step order or NULL.  The last state is copied (the loop starts at S - 2, :297).  Arithmetic written
+// literally after the reference: P_b about the FILTERED mean (:324-325), the cross covariance about the noisy x_b
+// (:328-330), pinv(P_b), state index 3 wrapped as the heading (:340, 346).
+STE_DEV void rts_n(const ProblemN &p, int t, int n_states, int rate_repeat, int n_rates, const double *mean_f, const double *cov_f,
+                   const double *dt, const double *sog_rate, const double *cog_rate, const double *noise, double *mean_s,
+                   double *cov_s, int32_t *status) {
+    const int n = p.n, L = 2 * n + 1;
+    const int64_t ld = p.ld;
+    const double w0 = 1.0 - n / 3.0, wi = (1.0 - w0) / (2.0 * n);
+    double xs[kMaxN], Ps[kMaxN * kMaxN];
+    int st = 0;
+    bool bad = false;
+    for (int r = 0; r < n; ++r) {
+        xs[r] = mean_f[((int64_t)(n_states - 1) * n + r) * ld + t];
+        mean_s[((int64_t)(n_states - 1) * n + r) * ld + t] = xs[r];
+        for (int q = 0; q < n; ++q) {
+            Ps[r * kMaxN + q] = cov_f[((int64_t)(n_states - 1) * n * n + r * n + q) * ld + t];
+            cov_s[((int64_t)(n_states - 1) * n * n + r * n + q) * ld + t] = Ps[r * kMaxN + q];
+        }
+    }
+    for (int step = n_states - 2; step >= 0; --step) {
+        double xf[kMaxN], Pf[kMaxN * kMaxN], S[kMaxN * kMaxN], M[kMaxN * kMaxN], X[kMaxN * kMaxL], Y[kMaxN * kMaxL], xb[kMaxN],
+            Pb[kMaxN * kMaxN], Pbi[kMaxN * kMaxN], D[kMaxN * kMaxN], K[kMaxN * kMaxN], y[kMaxN];
+        for (int r = 0; r < n; ++r) {
+            xf[r] = mean_f[((int64_t)step * n + r) * ld + t];
+            for (int q = 0; q < n; ++q) Pf[r * kMaxN + q] = cov_f[((int64_t)step * n * n + r * n + q) * ld + t];
+        }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) S[i * kMaxN + j] = (n / (1.0 - w0)) * Pf[i * kMaxN + j];
+        if (fun_sym_n(n, S, false, M)) st |= STE_STATUS_INDEFINITE;
+        int ri = step / rate_repeat;
+        ri = ri < n_rates ? ri : n_rates - 1;
+        const double d = dt[(int64_t)step * ld + t], sr = sog_rate ? sog_rate[(int64_t)ri * ld + t] : 0.0,
+                     cr = cog_rate ? cog_rate[(int64_t)ri * ld + t] : 0.0;
+        for (int j = 0; j < L; ++j) {
+            double xi[kMaxN], yi[kMaxN];
+            for (int r = 0; r < n; ++r) {
+                xi[r] = xf[r];
+                if (j >= 1 && j <= n) xi[r] = xf[r] + M[r * kMaxN + (j - 1)];
+                if (j > n) xi[r] = xf[r] - M[r * kMaxN + (j - 1 - n)];
+            }
+            process_n(p.model, n, xi, d, sr, cr, yi);
+            for (int r = 0; r < n; ++r) {
+                X[r * kMaxL + j] = xi[r];
+                Y[r * kMaxL + j] = yi[r];
+            }
+        }
+        for (int r = 0; r < n; ++r) {
+            double acc = w0 * Y[r * kMaxL];
+            for (int j = 1; j < L; ++j) acc = fma(wi, Y[r * kMaxL + j], acc);
+            xb[r] = acc + (noise ? noise[((int64_t)step * n + r) * ld + t] * sqrt(p.Q[r * n + r]) : 0.0);   // :313-322
+        }
+        for (int r = 0; r < n; ++r)
+            for (int q = 0; q < n; ++q) {
+                double pb = w0 * (Y[r * kMaxL] - xf[r]) * (Y[q * kMaxL] - xf[q]);     // :324-325
+                double dd = w0 * (X[r * kMaxL] - xf[r]) * (Y[q * kMaxL] - xb[q]);     // :328-330
+                for (int j = 1; j < L; ++j) {
+                    pb = fma(wi * (Y[r * kMaxL + j] - xf[r]), Y[q * kMaxL + j] - xf[q], pb);
+                    dd = fma(wi * (X[r * kMaxL + j] - xf[r]), Y[q * kMaxL + j] - xb[q], dd);
+                }
+                Pb[r * kMaxN + q] = pb + p.Q[r * n + q];
+                D[r * kMaxN + q] = dd;
+            }
+        fun_sym_n(n, Pb, true, Pbi);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k) acc = fma(D[i * kMaxN + k], Pbi[k * kMaxN + j], acc);
+                K[i * kMaxN + j] = acc;     // :333
+            }
+        for (int r = 0; r < n; ++r) y[r] = xs[r] - xb[r];
+        if (n > 3) y[3] = wrap180(y[3]);    // :340
+        for (int i = 0; i < n; ++i) {
+            double acc = xf[i];
+            for (int k = 0; k < n; ++k) acc = fma(K[i * kMaxN + k], y[k], acc);
+            xs[i] = acc;                    // :343
+        }
+        if (n > 3) xs[3] = py_mod360(xs[3]);   // :346
+        // Ps <- Pf + K (Ps - P_b) K^T (:349); S holds K (Ps - P_b)
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k) acc = fma(K[i * kMaxN + k], Ps[k * kMaxN + j] - Pb[k * kMaxN + j], acc);
+                S[i * kMaxN + j] = acc;
+            }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double acc = Pf[i * kMaxN + j];
+                for (int k = 0; k < n; ++k) acc = fma(S[i * kMaxN + k], K[j * kMaxN + k], acc);
+                M[i * kMaxN + j] = acc;
+            }
+        for (int r = 0; r < n; ++r) {
+            mean_s[((int64_t)step * n + r) * ld + t] = xs[r];
+            bad |= !(xs[r] * 0.0 == 0.0);
+            for (int q = 0; q < n; ++q) {
+                Ps[r * kMaxN + q] = M[r * kMaxN + q];
+                cov_s[((int64_t)step * n * n + r * n + q) * ld + t] = Ps[r * kMaxN + q];
+                bad |= !(Ps[r * kMaxN + q] * 0.0 == 0.0);
+            }
+        }
+    }
+    if (status) status[t] = st | (bad ? STE_STATUS_NONFINITE : 0);
+}
+
 }  // namespace ste

@@ -475,6 +475,13 @@ __global__ void __launch_bounds__(64) ukf_update_n_kernel(const __grid_constant_
     if (t < p.n_tracks) update_n(p, t, x, P, z, noise, status);
 }
 
+__global__ void __launch_bounds__(64) urtss_backward_n_kernel(const __grid_constant__ ProblemN p, int n_states, int rate_repeat, int n_rates,
+                                                             const double *mean_f, const double *cov_f, const double *dt,
+                                                             const double *sog_rate, const double *cog_rate, const double *noise,
+                                                             double *mean_s, double *cov_s, int32_t *status) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.n_tracks) rts_n(p, t, n_states, rate_repeat, n_rates, mean_f, cov_f, dt, sog_rate, cog_rate, noise, mean_s, cov_s, status);
+}
 __global__ void __launch_bounds__(64) process_n_kernel(int model, int n, int T, int64_t ld, const double *xin, const double *dt,
                                                         const double *sog_rate, const double *cog_rate, double *xout) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -793,6 +800,24 @@ int ste_ukf_update_n_f64(int32_t n, int32_t n_tracks, int64_t ld, const double *
     memcpy(p.R, R_host, sizeof(double) * n * n);
     ukf_update_n_kernel<<<(n_tracks + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, x, P, z, noise, status);
     return check_launch("ukf_update_n_kernel");
+}
+
+int ste_urtss_backward_n_f64(int32_t n, int32_t model, int32_t n_tracks, int64_t ld, int32_t n_states, int32_t rate_repeat,
+                             int32_t n_rates, const double *Q_host, const double *mean_f, const double *cov_f, const double *dt,
+                             const double *sog_rate, const double *cog_rate, const double *noise, double *mean_s, double *cov_s,
+                             int32_t *status, void *stream) {
+    if (int rc = model_dim_ok(n, model)) return rc;
+    if (n_tracks < 0 || ld < n_tracks) return fail(STE_ERR_INVALID_ARG, "bad n_tracks / ld");
+    if (n_states < 1 || rate_repeat < 1 || n_rates < 1) return fail(STE_ERR_INVALID_ARG, "n_states, rate_repeat and n_rates must be >= 1");
+    if (!Q_host || !mean_f || !cov_f || !mean_s || !cov_s || (n_states > 1 && !dt)) return fail(STE_ERR_INVALID_ARG, "missing array");
+    if (mean_s == mean_f || cov_s == cov_f) return fail(STE_ERR_INVALID_ARG, "the generic smoother does not run in place");
+    if (n_tracks == 0) return STE_OK;
+    ProblemN p{};
+    p.n = n; p.model = model; p.n_tracks = n_tracks; p.ld = ld;
+    memcpy(p.Q, Q_host, sizeof(double) * n * n);
+    urtss_backward_n_kernel<<<(n_tracks + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, n_states, rate_repeat, n_rates, mean_f, cov_f, dt,
+                                                                                  sog_rate, cog_rate, noise, mean_s, cov_s, status);
+    return check_launch("urtss_backward_n_kernel");
 }
 
 int ste_process_f64(int32_t model, int32_t n, int32_t n_tracks, int64_t ld, const double *x_in, const double *dt,

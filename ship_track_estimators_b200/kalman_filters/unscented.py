@@ -440,7 +440,8 @@ class UnscentedKalmanFilter(KalmanFilterBase):
     def rts_step(self, fwd_means, fwd_vars, ship_track, *args, **kwargs):
         """Unscented RTS smoother over explicit filtered states (reference ``:267-351``).
 
-        ``fwd_means (N+1, 4, 1)``, ``fwd_vars (N+1, 4, 4)``; returns arrays of the same shapes.
+        ``fwd_means (N+1, n, 1)``, ``fwd_vars (N+1, n, n)``; returns arrays of the same shapes (n = 4: the
+        batched backward kernel on a tile of one track; other n: the dimension-generic kernel).
         Unlike the reference this does not overwrite ``ship_track.sog_rate / cog_rate`` with their
         ``np.repeat`` expansion (``:287-292``); the expansion is applied as an index map on the device.
         """
@@ -448,10 +449,11 @@ class UnscentedKalmanFilter(KalmanFilterBase):
 
         from ..batch import BatchedUKF, TrackBatch, TrackResults
 
-        self._resolve_process(None)
-        self._require_n4("rts_step")
+        model, _ = self._resolve_process(None)
         fwd_means = np.asarray(fwd_means, dtype=np.float64)
         fwd_vars = np.asarray(fwd_vars, dtype=np.float64)
+        if self.n != 4:
+            return self._rts_generic(model, fwd_means, fwd_vars, ship_track)
         nstates = fwd_means.shape[0]
         N = nstates - 1
         if self.dt is None or len(self.dt) < N:
@@ -493,6 +495,40 @@ class UnscentedKalmanFilter(KalmanFilterBase):
         x = res.mean_s[:nstates].cpu().numpy().reshape(nstates, 4, 1)
         P = res.cov_s[:nstates].cpu().numpy().reshape(nstates, 4, 4)
         return x, P
+
+    def _rts_generic(self, model, fwd_means, fwd_vars, ship_track):
+        """``rts_step`` for n != 4: the whole backward loop in one launch of the dimension-generic kernel
+        (``ste_urtss_backward_n_f64``), arithmetic written literally after the reference."""
+        import torch
+
+        from .. import _native as nat
+
+        n, S = self.n, fwd_means.shape[0]
+        N = S - 1
+        if self.dt is None or len(self.dt) < N:
+            raise IndexError("rts_step needs the dt array of the forward run (self.dt)")
+        sog_rate = np.asarray(ship_track.sog_rate, dtype=np.float64).reshape(-1)
+        cog_rate = np.asarray(ship_track.cog_rate, dtype=np.float64).reshape(-1)
+        rep = int(S / len(ship_track.dts))
+        m = min(len(sog_rate), len(cog_rate))
+        if N > 0 and (rep < 1 or (N - 1) // rep >= m):
+            raise IndexError("index out of bounds for the repeated sog_rate / cog_rate arrays")
+        lib, dev = nat.load(), torch.device("cuda")
+        up = lambda a, shape: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(shape)).to(dev)   # noqa: E731
+        mf, cf = up(fwd_means, (S, n, 1)), up(fwd_vars, (S, n * n, 1))
+        ms, cs = torch.empty_like(mf), torch.empty_like(cf)
+        dt = up(np.asarray(self.dt, dtype=np.float64)[:N] if N else np.zeros(1), (max(N, 1), 1))
+        sr, cr = up(sog_rate[:m], (m, 1)), up(cog_rate[:m], (m, 1))
+        noise = None
+        if self._noise_on() and N > 0:
+            noise = up(_unit_normals(N, n)[::-1], (N, n, 1))   # the reference draws for step N-1 first
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        Q = np.ascontiguousarray(self.Q, dtype=np.float64)
+        nat.check(lib.ste_urtss_backward_n_f64(n, model, 1, 1, S, max(rep, 1), m, Q.ctypes.data_as(C.POINTER(C.c_double)), nat.ptr(mf), nat.ptr(cf),
+                                               nat.ptr(dt), nat.ptr(sr), nat.ptr(cr), nat.ptr(noise), nat.ptr(ms), nat.ptr(cs), nat.ptr(st),
+                                               nat.current_stream()))
+        self.status |= int(st.item())
+        return ms.cpu().numpy().reshape(S, n, 1), cs.cpu().numpy().reshape(S, n, n)
 
     # ------------------------------------------------------------------ #
     # robustification (reference :353-511; dead code there)              #

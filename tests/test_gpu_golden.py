@@ -189,6 +189,39 @@ def test_generic_dimension_class_api_against_reference_kats(cuda, native_lib):
         UnscentedKalmanFilter(H=H, Q=Q, R=R, non_linear_process=lambda x, **k: x).predict(dt=1.0, c=None)
 
 
+def test_generic_dimension_run_and_smoother_against_the_reference(cuda, native_lib):
+    """``run`` and ``run_rts_smoother`` of the class at n = 5 (geodetic_dynamics_turn) against the
+    unmodified reference run with the same five-state process (tests/golden/kat_n5_tracks.npz: k = 1, 2, 2)."""
+    import os
+    from types import SimpleNamespace
+
+    from _helpers import GOLDEN
+    from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics_turn
+
+    d = np.load(os.path.join(GOLDEN, "kat_n5_tracks.npz"))
+    H, Q, R, P0 = d["H"], d["Q"], d["R"], d["P0"]
+
+    def errs(got_m, got_c, ref_m, ref_c):
+        dm = np.asarray(got_m).reshape(ref_m.shape) - ref_m
+        dm[:, 3] = (dm[:, 3] + 180.0) % 360.0 - 180.0
+        em = float(np.max(np.abs(dm) / np.maximum(1.0, np.abs(ref_m))))
+        ec = max(float(np.max(np.abs(g - r)) / np.max(np.abs(r))) for g, r in zip(np.asarray(got_c), ref_c))
+        return em, ec
+
+    for i in range(int(d["n"])):
+        t = {k.split("_", 1)[1]: d[k] for k in d.files if k.startswith(f"t{i}_")}
+        st = SimpleNamespace(dts=t["dts"], z=t["z"], sog=t["z"][2], cog=t["z"][3], sog_rate=t["sog_rate"].copy(), cog_rate=t["cog_rate"].copy())
+        ukf = UnscentedKalmanFilter(H=H, Q=Q, R=R, P=P0, x0=t["x0"], non_linear_process=geodetic_dynamics_turn, noise="zero")
+        m, c = ukf.run(len(t["dt_array"]), t["dt_array"], st)
+        em, ec = errs(m, c, t["means"], t["covs"])
+        assert m.shape == t["means"].shape and em <= TOL and ec <= TOL, (i, em, ec)
+        ms, cs = ukf.run_rts_smoother(st)
+        es, ecs = errs(ms, cs, t["means_s"], t["covs_s"])
+        print(f"  n = 5 track {i}: filtered {em:.1e} {ec:.1e}  smoothed {es:.1e} {ecs:.1e}")
+        assert ms.shape == t["means_s"].shape and es <= TOL and ecs <= TOL, (i, es, ecs)
+        assert ukf.status == 0
+
+
 def test_generic_dimension_run_loop(cuda, native_lib):
     """n = 5 through KalmanFilterBase.run (host loop around the generic single-step kernels): with a zero turn-rate
     state that nothing excites (zero process noise and prior variance on it) the first four states must reproduce
