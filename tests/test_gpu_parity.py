@@ -148,8 +148,9 @@ def test_single_step_predict_update_against_oracle(cuda, native_lib):
 
 def test_predict_at_the_edges_of_the_small_displacement_tier(cuda, native_lib):
     """One predict on either side of the limits that select the geodetic step's small-displacement
-    series (2^-6 rad per step, 75 degrees of latitude, offsets bounded by sqrt(3 P_rr)): both tiers
-    must reproduce the oracle's predict, so the choice is invisible at 1e-12."""
+    series (2^-6 rad per step, 75 degrees of latitude, offsets bounded by sqrt(3 P_rr), latitude and
+    course spreads within the short offset series): both tiers must reproduce the oracle's predict, so
+    the choice is invisible at 1e-12."""
     from oracle import ukf_numpy as O
     from ship_track_estimators_b200.kalman_filters import UnscentedKalmanFilter, geodetic_dynamics
 
@@ -166,11 +167,21 @@ def test_predict_at_the_edges_of_the_small_displacement_tier(cuda, native_lib):
         cases.append((5.0, 75.0 - off_lat + dl, 30.0, 45.0, 1.0))
         cases.append((5.0, -(75.0 - off_lat + dl), 30.0, 200.0, 2.5))
     cases += [(0.0, 0.0, 0.0, 0.0, 1.0), (179.99, 10.0, 45.0, 90.0, 1.0), (10.0, 74.9, 99.0, 0.0, 1.0)]
-    for lon, lat, u, cog, dt in cases:
+    cases = [(c, P) for c in cases]
+    # course and latitude spreads on either side of the limit of the short offset series: sqrt(3 P_rr) = 0.125 rad = 7.162 deg
+    # (inside: the small tier's column loop evaluates the offsets without a test; outside: the full-range tier takes the step)
+    lim2 = np.degrees(0.125) ** 2 / 3.0
+    for f in (0.98, 0.999999, 1.000001, 1.05, 4.0):
+        Pc = P.copy()
+        Pc[3, 3] = f * lim2
+        Pl = P.copy()
+        Pl[1, 1] = f * lim2
+        cases += [((12.0, 33.0, 25.0, 77.0, 1.0), Pc), ((-100.0, -41.0, 18.0, 310.0, 2.0), Pl)]
+    for (lon, lat, u, cog, dt), Pk in cases:
         x = np.array([lon, lat, u, cog])
-        ukf = UnscentedKalmanFilter(H=H_POS, Q=Q_DEF, R=R_POS, P=P.copy(), x0=x, non_linear_process=geodetic_dynamics, noise="zero")
+        ukf = UnscentedKalmanFilter(H=H_POS, Q=Q_DEF, R=R_POS, P=Pk.copy(), x0=x, non_linear_process=geodetic_dynamics, noise="zero")
         ukf.predict(dt=dt, c=None, sog_rate=0.01, cog_rate=0.3)
-        xr, Pr, _, X1 = O.predict(x, P, Q_DEF, dt, 0.01, 0.3, O.ZeroNoise())
+        xr, Pr, _, X1 = O.predict(x, Pk, Q_DEF, dt, 0.01, 0.3, O.ZeroNoise())
         assert mean_err(ukf.x[:, 0][None], xr[None]) <= 1e-12, (lon, lat, u)
         assert cov_err(ukf.P[None], Pr[None]) <= 1e-10, (lon, lat, u)
         d = ukf.sigma_points - X1
@@ -339,6 +350,8 @@ def test_fastmath_accuracy(cuda, native_lib):
     assert ulps(run(2, pos)[0], np.sqrt(pos)) <= 1.0
     assert run(2, np.array([0.0]))[0][0] == 0.0
     assert ulps(run(3, pos)[0], 1.0 / np.sqrt(pos)) <= 2.0
+    # exact at 1 (and at powers of 4): the Jacobi rotation's identity case is c = 1 * rsqrt(1)
+    assert np.array_equal(run(3, np.array([1.0, 4.0, 0.25, 16.0]))[0], np.array([1.0, 0.5, 2.0, 0.25]))
     sgn = pos * rng.choice([-1.0, 1.0], len(pos))
     assert ulps(run(4, sgn)[0], 1.0 / sgn) <= 1.5
     num = rng.normal(size=len(pos))
