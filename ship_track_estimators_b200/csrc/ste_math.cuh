@@ -66,8 +66,8 @@ STE_DEV double wrap180(double a) { return py_mod360(a + 180.0) - 180.0; }
 // ------------------------------------------------------------------------------------------ //
 // Cyclic Jacobi eigen-decomposition of a symmetric 4x4:  A = V diag(w) V^T.
 // On return a[SYM(i,i)] hold the eigenvalues, V (row-major 4x4) the eigenvectors as columns.
-// Rotations on an exactly-zero off-diagonal are the identity, so structurally block-diagonal
-// inputs (S = H P H^T + R with zero rows/columns) keep their exact zeros and unit eigenvectors.
+// A rotation on an exactly-zero off-diagonal has s = t = 0 exactly (and c within an ulp of 1), so structurally
+// block-diagonal inputs (S = H P H^T + R with zero rows/columns) keep their exact zeros.
 // ------------------------------------------------------------------------------------------ //
 // Rotation parameters for L disjoint index pairs at once (lock-step: the L dependency chains
 // interleave in the FP64 pipe).  Angle theta in (-pi/4, pi/4] with tan 2 theta = 2 a_pq / (a_qq - a_pp):
@@ -82,17 +82,20 @@ STE_DEV void jacobi_params(const double (&app)[N], const double (&aqq)[N], const
     STE_LANES { d[l] = aqq[l] - app[l]; b[l] = apq[l] + apq[l]; }
     STE_LANES v[l] = fma(d[l], d[l], b[l] * b[l]);
     fast_rsqrt_v<N>(v, rh);
-    // identity on a zero or underflowed pivot (also d == b == 0) from TWO selects: 1/h := 0 makes sin 2theta = 0, and
+    // identity on a vanishing pivot block (d == b == 0, or underflow) from TWO selects: 1/h := 0 makes sin 2theta = 0, and
     // cos^2 theta := 1 makes cos theta = 1 (rsqrt(1) is exactly 1: its residual is 0), so c = 1, s = t = 0
     bool skip[N];
     STE_LANES {
-        skip[l] = (apq[l] == 0.0) || !(v[l] > 1e-290);
+        // a zero pivot with d != 0 needs no test: b = 0 gives s = t = 0 exactly and c within an ulp of 1, which leaves
+        // exact zeros exact; only v = d^2 + b^2 == 0 (or underflowed) has no finite 1/h
+        skip[l] = !(v[l] > 1e-290);
         rh[l] = skip[l] ? 0.0 : rh[l];
         cc[l] = skip[l] ? 1.0 : fma(0.5, fabs(d[l]) * rh[l], 0.5);
     }
     fast_rsqrt_v<N>(cc, rc);
     STE_LANES {
-        const double s2t = (d[l] >= 0.0 ? b[l] : -b[l]) * rh[l];
+        // sign(d) b through the integer pipe (d = -0.0 counts as negative: either 45-degree rotation annihilates the pivot)
+        const double s2t = f64_from_bits(f64_bits(b[l]) ^ (f64_bits(d[l]) & 0x8000000000000000ull)) * rh[l];
         c[l] = cc[l] * rc[l];
         s[l] = (0.5 * s2t) * rc[l];
         t[l] = s[l] * rc[l];
