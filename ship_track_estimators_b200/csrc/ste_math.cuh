@@ -304,7 +304,10 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 static long long ste_emul_sweep_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 constexpr double kSqrtSeriesEps2 = STE_SQRT_SERIES_EPS2;     // eps^2 limit of the series finish
-constexpr int kSqrtMaxSweeps = 4;
+#ifndef STE_SQRT_MAX_SWEEPS
+#define STE_SQRT_MAX_SWEEPS 4
+#endif
+constexpr int kSqrtMaxSweeps = STE_SQRT_MAX_SWEEPS;
 constexpr int kSqrtRotSlots = kSqrtMaxSweeps * kSweepSlots;
 
 STE_DEV bool jacobi_off_within(const double (&a)[10], double eps2) {
