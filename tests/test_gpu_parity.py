@@ -1078,3 +1078,33 @@ def test_device_csv_ingest_matches_the_host_reader(cuda, native_lib, tmp_path):
     for i in range(len(keep)):
         x, y = a.track(i), b.track(i)
         assert all(np.array_equal(x[k], y[k]) for k in ("means", "covs", "means_s", "covs_s"))
+
+
+def test_examples_run(cuda, native_lib, tmp_path):
+    """examples/single_ship.py and examples/fleet_from_csv.py on a CSV shaped like the reference's historical file."""
+    import json
+    import subprocess
+    import sys
+
+    from test_host_dropin import _fleet_csv
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv = str(tmp_path / "fleet.csv")
+    ids = _fleet_csv(csv, seed=21, n_ships=8, time_ordered=True)
+    settings = dict(dim=4, H=[[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]], R=[[1e-3, 0, 0, 0], [0, 1e-3, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]],
+                    Q=[[1e-2, 0, 0, 0], [0, 1e-2, 0, 0], [0, 0, 1e-4, 0], [0, 0, 0, 1e-4]], P=np.eye(4).tolist(), dt=-1, nsteps=2, smooth=-1)
+    with open(tmp_path / "input.json", "w") as fh:
+        json.dump(settings, fh)
+    env = dict(os.environ, PYTHONPATH=repo + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run([sys.executable, os.path.join(repo, "examples", "fleet_from_csv.py"), csv, str(tmp_path / "input.json"), "--out-dir",
+                          str(tmp_path / "res"), "--geodesy", "sphere"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ships" in out.stdout and len(os.listdir(tmp_path / "res")) >= 5
+    counts = {}
+    for line in open(csv).read().splitlines()[1:]:
+        counts[line.split(",")[1]] = counts.get(line.split(",")[1], 0) + 1
+    longest = max((i for i in ids), key=lambda i: counts.get(i, 0))
+    out = subprocess.run([sys.executable, os.path.join(repo, "examples", "single_ship.py"), csv, longest], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "last filtered state" in out.stdout
