@@ -292,24 +292,29 @@ struct MetricsArgs {
     int32_t *n_pairs;
 };
 
+// One thread per (track, observation row): the rows of a track are independent sums, and twice (position-only) to four
+// times the threads of a one-thread-per-track launch keep twice to four times the loads in flight.  blockIdx.y
+// counts the rows that exist (z[r] != NULL), in order.
 __global__ void __launch_bounds__(kThreads) track_metrics_kernel(const __grid_constant__ MetricsArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.prob.n_tracks) return;
+    int r = 0;
+    for (int seen = -1; r < 4; ++r) {
+        if (a.in.z[r] && ++seen == (int)blockIdx.y) break;
+    }
     const int64_t ld = a.prob.ld;
     const int nt = a.in.n_steps ? min(a.in.n_steps[t], a.prob.max_steps) : a.prob.max_steps;
     const int k_sub = a.prob.substeps > 0 ? a.prob.substeps : 1;
-    double sq[4] = {0.0, 0.0, 0.0, 0.0}, sa[4] = {0.0, 0.0, 0.0, 0.0}, mx[4] = {0.0, 0.0, 0.0, 0.0};
+    const double *zr = a.in.z[r] + t;
+    const double *mr = a.mean + (int64_t)r * ld + t;
+    double sq = 0.0, sa = 0.0, mx = 0.0;
     int pairs = 0, ui = 0;
     auto pair = [&](int state, int obs) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (!a.in.z[r]) continue;
-            const double d = fabs(STE_LOAD_STREAM(a.mean + ((int64_t)state * 4 + r) * ld + t) - a.in.z[r][(int64_t)obs * ld + t]);
-            sq[r] = fma(d, d, sq[r]);
-            sa[r] += d;
-            mx[r] = fmax(mx[r], d);   // NaN residuals propagate through sq / sa
-            if (a.abs_diff) STE_STORE_STREAM(a.abs_diff + ((int64_t)obs * 4 + r) * ld + t, d);
-        }
+        const double d = fabs(STE_LOAD_STREAM(mr + ((int64_t)state * 4) * ld) - zr[(int64_t)obs * ld]);
+        sq = fma(d, d, sq);
+        sa += d;
+        mx = fmax(mx, d);   // NaN residuals propagate through sq / sa
+        if (a.abs_diff) STE_STORE_STREAM(a.abs_diff + ((int64_t)obs * 4 + r) * ld + t, d);
         ++pairs;
     };
     pair(0, 0);
@@ -319,14 +324,10 @@ __global__ void __launch_bounds__(kThreads) track_metrics_kernel(const __grid_co
         const bool upd = a.in.upd_mask ? (a.in.upd_mask[(int64_t)s * ld + t] != 0) : ((s + 1) % k_sub == 0);
         if (upd && ui + 1 < a.prob.max_obs) pair(s + 1, ++ui);
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if (!a.in.z[r]) continue;
-        if (a.rmse) a.rmse[r * ld + t] = sqrt(sq[r] / (double)pairs);
-        if (a.cum_abs) a.cum_abs[r * ld + t] = sa[r];
-        if (a.max_abs) a.max_abs[r * ld + t] = mx[r];
-    }
-    if (a.n_pairs) a.n_pairs[t] = pairs;
+    if (a.rmse) a.rmse[r * ld + t] = sqrt(sq / (double)pairs);
+    if (a.cum_abs) a.cum_abs[r * ld + t] = sa;
+    if (a.max_abs) a.max_abs[r * ld + t] = mx;
+    if (a.n_pairs && blockIdx.y == 0) a.n_pairs[t] = pairs;
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -907,7 +908,10 @@ int ste_track_metrics_f64(const SteProblem *prob, const SteInputs *in, const dou
     a.prob = *prob;
     a.in = *in;
     a.mean = mean; a.rmse = rmse; a.cum_abs = cum_abs; a.max_abs = max_abs; a.abs_diff = abs_diff; a.n_pairs = n_pairs;
-    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads), block(kThreads);
+    int rows = 0;
+    for (int r = 0; r < 4; ++r) rows += in->z[r] != nullptr;
+    if (rows == 0) return fail(STE_ERR_INVALID_ARG, "no observation row to compare with");
+    const dim3 grid((prob->n_tracks + kThreads - 1) / kThreads, rows), block(kThreads);
     track_metrics_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
     return check_launch("track_metrics_kernel");
 }
