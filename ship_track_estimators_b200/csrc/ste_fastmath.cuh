@@ -358,11 +358,11 @@ STE_DEV void small_hypot_scale_v(const double (&a)[N], const double (&e)[N], dou
 }
 
 // a * (sqrt(1 + e) - 1)
+// (without the e^6 term: it is 0.041 e^5 <= 5.4e-14 of the excess, 1.1e-16 absolute at the tier's limit)
 template <int N>
 STE_DEV void small_hypot_excess_v(const double (&a)[N], const double (&e)[N], double (&out)[N]) {
     double p[N];
-    STE_LANES p[l] = fma(e[l], kSqrt1pS[5], kSqrt1pS[4]);
-    STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[3]);
+    STE_LANES p[l] = fma(e[l], kSqrt1pS[4], kSqrt1pS[3]);
     STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[2]);
     STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[1]);
     STE_LANES p[l] = fma(e[l], p[l], kSqrt1pS[0]);
