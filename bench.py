@@ -66,10 +66,11 @@ def alg_bytes(k, smoother):
     return fwd, (bwd if smoother else 0.0)
 
 
-def kernel_counts():
-    """Instruction / flop / DRAM-byte counts per track-step of the kernels, written by
-    tools/ncu_counts.py from an ncu capture (profiles/kernel_counts.json); None when absent."""
-    path = os.path.join(REPO, "profiles", "kernel_counts.json")
+def kernel_counts(shape="uniform"):
+    """Instruction / flop / DRAM-byte counts per track-step of the kernels, written from ncu captures by
+    tools/ncu_counts.py (profiles/kernel_counts.json: the uniform k = 1 shape of configs 3 / 5) and
+    tools/c4_counts.py (profiles/kernel_counts_c4.json: the ragged, gated k = 2 shape of config 4); None when absent."""
+    path = os.path.join(REPO, "profiles", "kernel_counts.json" if shape == "uniform" else "kernel_counts_c4.json")
     if os.path.exists(path):
         with open(path) as fh:
             return json.load(fh)
@@ -416,9 +417,9 @@ def roofline_block(cfg, track_steps_per_launch, f_ms, b_ms, fp64_peak, full_cov)
     instructions (profiles/kernel_counts.json)."""
     peak, peak_src = measured_peaks()
     bytes_f, bytes_b = alg_bytes(cfg["k"], cfg["smoother"])
-    # the counts were captured on the uniform k = 1 shape (configs 3 / 5); the ragged config runs other instruction
-    # paths (full-range geodetic tier, 2-4 Jacobi sweeps per root, gating), so it reports times and algorithmic bytes only
-    counts = {} if cfg["ragged"] else (kernel_counts() or {})
+    # counts per shape: the ragged, gated config runs other instruction paths (full-range geodetic tier, 2-4 Jacobi sweeps per
+    # root, gating) and has its own capture; the real-data fleet (72 tracks, latency-bound) has none
+    counts = {} if cfg.get("fleet") else (kernel_counts("c4" if cfg["ragged"] else "uniform") or {})
     fwd_key = "forward" if cfg["smoother"] else "forward_no_tape"
     per_kernel = {}
     for key, ckey, alg, ms in (("forward", fwd_key, bytes_f, f_ms), ("backward", "backward", bytes_b, b_ms)):
@@ -447,7 +448,7 @@ def roofline_block(cfg, track_steps_per_launch, f_ms, b_ms, fp64_peak, full_cov)
     return {
         "bound": "hbm", "kernel": {"forward": "ukf_forward_kernel", "backward": "urtss_backward_kernel"}[dom],
         "achieved": d["algorithmic_gbs"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
-        "traffic": traffic * track_steps_per_launch if traffic else None, "traffic_source": counts.get("source") or "not captured for this shape (profiles/kernel_counts.json is the uniform k = 1 shape)",
+        "traffic": traffic * track_steps_per_launch if traffic else None, "traffic_source": counts.get("source") or "not captured for this shape",
         "peak_source": peak_src, "algorithmic_bytes_per_track_step": d["algorithmic_bytes_per_track_step"],
         "kernel_ms": d["ms"], "kernels": per_kernel,
         "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes_per_track_step": bytes_f + bytes_b},
