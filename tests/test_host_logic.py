@@ -169,3 +169,23 @@ def test_long_step_fraction_flags_mixed_tiles():
     mixed = TrackBatch.from_synthetic(make_tracks(64, 120, seed=2, device="cpu", nobs_min=30, dts_choices=(1, 2, 3, 6, 12, 24)), 2)
     assert dense.long_step_fraction() < 0.02
     assert 0.2 < mixed.long_step_fraction() < 0.8
+
+
+def test_bench_reference_arm_line_for_the_real_data_config():
+    """`bench.py --impl reference --config c2`: the reference (or, where it is not installed, the numpy port) over the
+    fleet of the committed real-data fixtures on the host cores; one JSON line with the contract's keys and the GPU arm's
+    config block."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--config", "c2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=repo)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "track-steps/s" and line["value"] > 0
+    assert line["config"]["config"] == "c2" and line["config"]["job_tracks"] == 72 and line["config"]["fixtures"] == ["c2_historical_batch", "c2_modern_ship"]
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
