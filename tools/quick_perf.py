@@ -15,6 +15,7 @@ ap.add_argument("--packed", action="store_true")
 ap.add_argument("--fused", action="store_true")
 ap.add_argument("--fused-fwd-tracks", type=int, default=0, help="tile size of the forward side of the fused launch (default: --tracks)")
 ap.add_argument("--fused-bwd-tracks", type=int, default=0, help="tile size of the backward side of the fused launch (default: --tracks)")
+ap.add_argument("--two-streams", action="store_true", help="forward of one tile and backward of another launched on two streams")
 ap.add_argument("--no-probe", action="store_true")
 ap.add_argument("--no-metrics", action="store_true")
 ap.add_argument("--label", default="")
@@ -70,3 +71,21 @@ if a.fused:
     fu_ms, fu_all = timed(lambda: ukf.fused(batch2, res2, batch, res), a.reps)
     print(json.dumps({"fused_ms": fu_ms, "fwd_tracks": nf, "bwd_tracks": nb, "separate_ms": f_ms + b_ms, "fused_steps_per_s": ts / fu_ms * 1e3,
                       "gain": (f_ms + b_ms) / fu_ms, "all": fu_all}))
+
+if a.two_streams:
+    batch2 = TrackBatch.from_synthetic(make_tracks(a.tracks, a.steps + 1, seed=2, device="cuda:0"), substeps=1)
+    res2 = ukf.allocate(batch2, smoother=True)
+    ukf.forward(batch, res)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+    def both(order):
+        e0 = torch.cuda.Event(); e0.record()
+        s1.wait_event(e0); s2.wait_event(e0)
+        def f():
+            with torch.cuda.stream(s1): ukf.forward(batch2, res2)
+        def b():
+            with torch.cuda.stream(s2): ukf.backward(batch, res)
+        (f(), b()) if order == "fb" else (b(), f())
+        torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+    for order in ("fb", "bf"):
+        ms, allv = timed(lambda: both(order), a.reps)
+        print(json.dumps({"two_streams": order, "ms": ms, "separate_ms": f_ms + b_ms, "gain": (f_ms + b_ms) / ms, "all": allv}))
