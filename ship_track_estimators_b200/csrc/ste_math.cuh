@@ -302,6 +302,8 @@ STE_COLD bool sqrt_psd4_cold(double a0, double a1, double a2, double a3, double 
 #endif
 #if defined(STE_EMUL_STATS) && !defined(__CUDA_ARCH__)
 static long long ste_emul_sweep_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static unsigned char *ste_emul_sweep_log = nullptr;   // developer sandbox only: sweeps of every root in call order (0 = cold path)
+static long long ste_emul_sweep_log_n = 0, ste_emul_sweep_log_cap = 0;
 #endif
 constexpr double kSqrtSeriesEps2 = STE_SQRT_SERIES_EPS2;     // eps^2 limit of the series finish
 #ifndef STE_SQRT_MAX_SWEEPS
@@ -338,6 +340,7 @@ STE_DEV bool sqrt_psd4(const double (&A)[10], double scale, double (&M)[10], con
     }
 #if defined(STE_EMUL_STATS) && !defined(__CUDA_ARCH__)
     ++ste_emul_sweep_hist[series_ok ? sweeps : 0];   // developer sandbox only: sweeps per root, [0] = cold path
+    if (ste_emul_sweep_log && ste_emul_sweep_log_n < ste_emul_sweep_log_cap) ste_emul_sweep_log[ste_emul_sweep_log_n++] = (unsigned char)(series_ok ? sweeps : 0);
     if (!series_ok) {
         const double wmx = fmax(fmax(a[0], a[4]), fmax(a[7], a[9])), wmn = fmin(fmin(a[0], a[4]), fmin(a[7], a[9]));
         ++ste_emul_sweep_hist[wmn < 0.0 ? 4 : (wmn > 1e-12 * wmx ? 6 : 5)];   // negative / tiny / off-diagonals still large

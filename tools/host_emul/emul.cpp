@@ -51,5 +51,7 @@ extern "C" void emul_geodetic_tiers(int n, const double *x, const double *dt, co
 }
 
 #if defined(STE_EMUL_STATS)
+extern "C" void emul_sweep_log(unsigned char *buf, long long cap) { ste::ste_emul_sweep_log = buf; ste::ste_emul_sweep_log_cap = cap; ste::ste_emul_sweep_log_n = 0; }
+extern "C" long long emul_sweep_log_count() { return ste::ste_emul_sweep_log_n; }
 extern "C" void emul_sweep_hist(long long *out) { for (int i = 0; i < 8; ++i) { out[i] = ste::ste_emul_sweep_hist[i]; ste::ste_emul_sweep_hist[i] = 0; } }
 #endif
