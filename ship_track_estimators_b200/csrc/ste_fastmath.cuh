@@ -276,7 +276,9 @@ STE_DEV void fast_sincos(double x, double *sn, double *cs) {
 // q = mn/mx (mn <= tan(pi/8) mx) or q = (mn - mx)/(mn + mx) (then atan = pi/4 + atan q), |q| <= 0.4143.
 // Branch-free for finite arguments; (0, 0) -> 0 (the sign conventions of atan2(+-0, -0) are not
 // reproduced, the filter never needs them); non-finite input gives NaN.
-template <int N>
+// Lanes l >= UNIT_FROM promise x >= 0 and x^2 + y^2 = 1 (a latitude from (up, hypot(east, north))): no reflection for
+// x < 0 and no (0, 0) guard there - same values, fewer selects.
+template <int N, int UNIT_FROM = N>
 STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&out)[N]) {
     double mx[N], mn[N], num[N], den[N], q[N], z[N], w[N], s1[N], s2[N], p[N], off[N], sg[N];
     bool swap[N], big[N];
@@ -290,7 +292,7 @@ STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&o
         big[l] = mn[l] > kTanPiEighth * mx[l];
         num[l] = big[l] ? mn[l] - mx[l] : mn[l];
         const double d = big[l] ? mn[l] + mx[l] : mx[l];
-        den[l] = (f64_bits(mx[l]) << 1) != 0 ? d : 1.0;          // (0, 0): 0 / 1
+        den[l] = (l >= UNIT_FROM || (f64_bits(mx[l]) << 1) != 0) ? d : 1.0;          // (0, 0): 0 / 1
     }
     fast_div_v<N>(num, den, q);
     STE_LANES z[l] = q[l] * q[l];
@@ -306,7 +308,7 @@ STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&o
         off[l] = big[l] ? kPiQuarter : 0.0;
         sg[l] = 1.0;
         if (swap[l]) { off[l] = kPiHalf - off[l]; sg[l] = -1.0; }
-        if ((int64_t)f64_bits(x[l]) < 0) { off[l] = kPi - off[l]; sg[l] = -sg[l]; }
+        if (l < UNIT_FROM && (int64_t)f64_bits(x[l]) < 0) { off[l] = kPi - off[l]; sg[l] = -sg[l]; }
     }
     STE_LANES {
         const double r = fma(sg[l], p[l], off[l]);

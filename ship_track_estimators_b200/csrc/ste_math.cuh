@@ -674,7 +674,7 @@ STE_DEV void geodetic_finish_n(const double (&x)[NP][4], const AngleTrig (&t)[NP
             fast_sqrt_v<NP>(h2, h);
 #pragma unroll
             for (int i = 0; i < NP; ++i) ax[NP + i] = h[i];
-            fast_atan2_v<2 * NP>(ay, ax, ang);
+            fast_atan2_v<2 * NP, NP>(ay, ax, ang);   // lanes NP.. are latitudes: (up, hypot) is a unit vector with hypot >= 0
         }
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
