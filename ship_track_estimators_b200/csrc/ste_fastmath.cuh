@@ -288,10 +288,14 @@ STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&o
         mx[l] = swap[l] ? ay : ax;
         mn[l] = swap[l] ? ax : ay;
     }
+    double bigf[N];
     STE_LANES {
+        // second reduction, (mn - mx) / (mn + mx) above tan(pi/8), as multiply-adds by a 0 / 1 flag: the same values as
+        // selecting between mn - mx and mn (a zero product adds exactly nothing), one select per lane instead of six
         big[l] = mn[l] > kTanPiEighth * mx[l];
-        num[l] = big[l] ? mn[l] - mx[l] : mn[l];
-        const double d = big[l] ? mn[l] + mx[l] : mx[l];
+        bigf[l] = big[l] ? 1.0 : 0.0;
+        num[l] = fma(-bigf[l], mx[l], mn[l]);
+        const double d = fma(bigf[l], mn[l], mx[l]);
         den[l] = (l >= UNIT_FROM || (f64_bits(mx[l]) << 1) != 0) ? d : 1.0;          // (0, 0): 0 / 1
     }
     fast_div_v<N>(num, den, q);
@@ -305,7 +309,7 @@ STE_DEV void fast_atan2_v(const double (&y)[N], const double (&x)[N], double (&o
     STE_LANES p[l] = fma(-q[l], fma(z[l], s1[l], w[l] * s2[l]), q[l]);   // atan(q) = q - q (z s1 + w s2)
     // angle of (mx, mn) in [0, pi/4], then undo the reflections: r = off + sg * p
     STE_LANES {
-        off[l] = big[l] ? kPiQuarter : 0.0;
+        off[l] = bigf[l] * kPiQuarter;
         sg[l] = 1.0;
         if (swap[l]) { off[l] = kPiHalf - off[l]; sg[l] = -1.0; }
         if (l < UNIT_FROM && (int64_t)f64_bits(x[l]) < 0) { off[l] = kPi - off[l]; sg[l] = -sg[l]; }

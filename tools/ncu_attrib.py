@@ -73,6 +73,8 @@ for r in rows:
             pass
 base = min(counts) if counts else 0
 inner, path_tot, fp64_inner = collections.Counter(), collections.Counter(), collections.Counter()
+WATCH = set(os.environ.get("STE_ATTRIB_OPS", "").split())   # e.g. STE_ATTRIB_OPS="FSEL IMAD": where these opcodes are executed
+watch_inner = collections.Counter()
 tot = 0
 samples, stall_by = collections.Counter(), collections.defaultdict(collections.Counter)
 for addr, (n, src, smp, stl) in counts.items():
@@ -92,6 +94,8 @@ for addr, (n, src, smp, stl) in counts.items():
     op = re.match(r"(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", src.strip())
     if op and op.group(1) in ("DFMA", "DMUL", "DADD", "DSETP"):
         fp64_inner[" < ".join(dedup[:4])] += n
+    if op and op.group(1) in WATCH:
+        watch_inner[(op.group(1), " < ".join(dedup[:3]))] += n
     tot += n
 print(f"kernel ~{kernel_sub}: {tot/per:.0f} warp-instructions per warp-step")
 print("-- by innermost function")
@@ -106,3 +110,8 @@ print("-- stall samples by inline path (share of all samples; top stall reasons)
 for k, v in samples.most_common(16):
     top = ", ".join(f"{a[6:]} {100*b/max(v,1):.0f}%" for a, b in stall_by[k].most_common(4))
     print(f"   {k:72s} {100*v/tot_s:5.1f}%   {top}")
+
+if WATCH:
+    print("-- watched opcodes by inline path (per warp-step)")
+    for (o, k), v in watch_inner.most_common(30):
+        print(f"   {o:8s} {k:80s} {v/per:8.1f}")
