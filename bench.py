@@ -256,6 +256,11 @@ def cpu_sample_text(kind, cfg_name, cores, tracks_per_core, steps, busy):
             f"{steps} track-steps, slowest worker {busy:.1f} s")
 
 
+# tracks per core and bench step of the reference arm: 4 x 1 024 steps are ~2 s per step on a B200 box's host cores (one
+# track per step under-reads the reference by a third: the slowest of 16 workers over 0.4 s decides the step)
+REF_ARM_TRACKS_PER_CORE = 4
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -265,7 +270,7 @@ def run_reference_arm(args):
     pool = CpuPool(cores, kind, args.config)
     done = []
     for i in range(args.warmup + args.steps):
-        _, steps, busy = pool.run_fleet() if cfg.get("fleet") else pool.run(1, seed=100 + 1000 * i)
+        _, steps, busy = pool.run_fleet() if cfg.get("fleet") else pool.run(REF_ARM_TRACKS_PER_CORE, seed=100 + 1000 * i)
         if i >= args.warmup:
             done.append((steps, busy))
     pool.close()
@@ -280,7 +285,7 @@ def run_reference_arm(args):
         # tile; the CPU sample of each step is described under cpu_baseline.sample)
         "config": workload_config(args, per_gpu_tracks=None if cfg["ragged"] else args.tracks),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "per_core": value / cores,
-                         "sample": "each bench step = " + cpu_sample_text(kind, args.config, cores, 1, done[-1][0], done[-1][1])},
+                         "sample": "each bench step = " + cpu_sample_text(kind, args.config, cores, 1 if cfg.get("fleet") else REF_ARM_TRACKS_PER_CORE, done[-1][0], done[-1][1])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
