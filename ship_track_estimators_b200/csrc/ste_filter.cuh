@@ -537,25 +537,29 @@ STE_DEV void ukf_update_position(double (&x)[4], double (&P)[10], const Model &m
     const double r00 = m.R[0], r01 = m.R[1], r11 = m.R[5];
     rs = 1.0;
     double Si[3];
-    pinv_sym2(fma(rs, r00, P[SYM(0, 0)]), fma(rs, r01, P[SYM(0, 1)]), fma(rs, r11, P[SYM(1, 1)]), Si);
     gate_it = 0;
     gate_lam = 1.0;
     if (GATING) {
+        // one copy of the inverse and of the criterion in the instruction stream (the loop is entered at its test):
+        // the gated kernel's executed path sits at the size of the instruction cache
         const double y0 = z[0] - x[0], y1 = z[1] - x[1];
-        double gamma = fabs(fma(y0, fma(Si[0], y0, Si[1] * y1), y1 * fma(Si[1], y0, Si[2] * y1)));
-        while (gamma > chi) {
+#pragma unroll 1
+        for (;;) {
+            pinv_sym2(fma(rs, r00, P[SYM(0, 0)]), fma(rs, r01, P[SYM(0, 1)]), fma(rs, r11, P[SYM(1, 1)]), Si);
+            const double v0 = fma(Si[0], y0, Si[1] * y1), v1 = fma(Si[1], y0, Si[2] * y1);
+            const double gamma = fabs(fma(y0, v0, y1 * v1));
+            if (!(gamma > chi)) break;
             if (gate_it >= max_iter) {
                 status |= STE_STATUS_GATE_CAP;
                 break;
             }
-            const double v0 = fma(Si[0], y0, Si[1] * y1), v1 = fma(Si[1], y0, Si[2] * y1);
             const double den = rs * fma(v0, fma(r00, v0, r01 * v1), v1 * fma(r01, v0, r11 * v1));
             gate_lam = gate_lam + (gamma - chi) / den;
             rs *= gate_lam;
-            pinv_sym2(fma(rs, r00, P[SYM(0, 0)]), fma(rs, r01, P[SYM(0, 1)]), fma(rs, r11, P[SYM(1, 1)]), Si);
-            gamma = fabs(fma(y0, fma(Si[0], y0, Si[1] * y1), y1 * fma(Si[1], y0, Si[2] * y1)));
             ++gate_it;
         }
+    } else {
+        pinv_sym2(fma(rs, r00, P[SYM(0, 0)]), fma(rs, r01, P[SYM(0, 1)]), fma(rs, r11, P[SYM(1, 1)]), Si);
     }
     if (unit_noise) {
         z[0] = fma(unit_noise[0], sqrt(rs * r00), z[0]);
