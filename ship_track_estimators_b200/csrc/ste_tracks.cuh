@@ -238,13 +238,17 @@ template <bool POS_ONLY, bool GATING>
 STE_DEV void forward_track(const KernelArgs &a, const int t, const Scratch &sc) {
     ForwardTrack<POS_ONLY, GATING> f(a, t, sc);
     f.begin();
-#pragma unroll 1
-    for (int s = 0; s < f.nt; ++s) {
 #if defined(STE_STEP_SYNC) && defined(__CUDA_ARCH__)
-        __syncthreads();   // experiment: keep the warps of a block in phase (uniform track lengths only)
-#endif
-        f.step(s);
+    // experiment: the warps of a block start every step together (instruction-cache locality); ragged lengths are safe,
+    // the loop runs while any thread of the block has a step left
+#pragma unroll 1
+    for (int s = 0; __syncthreads_or(s < f.nt); ++s) {
+        if (s < f.nt) f.step(s);
     }
+#else
+#pragma unroll 1
+    for (int s = 0; s < f.nt; ++s) f.step(s);
+#endif
     f.end();
 }
 
