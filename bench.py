@@ -555,6 +555,9 @@ def run_uniform(args, D):
     value = world * tile_steps * args.steps / (total_ms * 1e-3)
     launches = (2 if smoother else 1) * args.steps
 
+    # ---- the same K steps with the two passes of successive tiles on disjoint SMs ---- #
+    partitioned = run_partitioned(args, D, ukf, tiles, res, f_ms + b_ms, tile_steps) if (smoother and not args.no_partitioned) else None
+
     # ---- the whole job through the tile loop ---- #
     job = None
     if not args.no_job:
@@ -612,11 +615,90 @@ def run_uniform(args, D):
         line["e2e"], line["gpu_launches"], line["clocks"] = e2e, launches, clocks.summary()
         if job:
             line["job"] = job
+        if partitioned:
+            line["partitioned_schedule"] = partitioned
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], compiled = cpu_baseline_block(args, args.config)
             if compiled:
                 line["compiled_port"] = compiled
         print(json.dumps(line), flush=True)
+
+
+def run_partitioned(args, D, ukf, tiles, res, back_to_back_ms, tile_steps):
+    """K steady-state steps of the software-pipelined schedule: forward(tile i+1) on one set of SMs beside backward(tile i)
+    on the rest (green contexts, ship_track_estimators_b200/partition.py).  Every timed step is one full forward and one full
+    backward launch, as in the headline loop; the first tile is filtered before the clock starts and the last one smoothed
+    after it stops.  An extra key: the headline `value` stays the two launches back to back on all SMs."""
+    import torch
+
+    from ship_track_estimators_b200.partition import SmPartition
+
+    res2 = part = None
+    try:
+        free, _ = torch.cuda.mem_get_info(D.dev)
+        need = sum(t.numel() * t.element_size() for t in vars(res).values() if isinstance(t, torch.Tensor))
+        if free < 1.1 * need:
+            return {"unavailable": f"a second result set needs {need / 1e9:.0f} GB, {free / 1e9:.0f} GB free"}
+        part = SmPartition(D.dev, smoother_sms=args.smoother_sms)
+        res2 = ukf.allocate(tiles[0], smoother=True, in_place=args.in_place)
+        sets = [res, res2]
+        cur, fs, bs = torch.cuda.current_stream(D.dev), part.filter_stream, part.smoother_stream
+
+        def stage(i, fwd=True, bwd=True, after=None):
+            # forward(tile i) into sets[i % 2] beside backward(tile i - 1) from sets[(i - 1) % 2]; `after`: the event
+            # pair (forward done, backward done) of the previous stage, which both of this stage's launches wait for
+            if after:
+                fs.wait_event(after[0]); fs.wait_event(after[1]); bs.wait_event(after[0]); bs.wait_event(after[1])
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+            with torch.cuda.stream(fs):
+                if fwd:
+                    ukf.forward(tiles[i % 2], sets[i % 2])
+                done[0].record(fs)
+            with torch.cuda.stream(bs):
+                if bwd:
+                    ukf.backward(tiles[(i - 1) % 2], sets[(i - 1) % 2])
+                done[1].record(bs)
+            return done
+
+        def run(k):
+            fs.wait_stream(cur); bs.wait_stream(cur)
+            ev = stage(0, bwd=False)                       # prime: tile 0 filtered
+            for i in range(1, 3):
+                ev = stage(i, after=ev)                    # warm the pipeline
+            cur.wait_event(ev[0]); cur.wait_event(ev[1])
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(cur)
+            fs.wait_event(t0); bs.wait_event(t0)
+            for i in range(3, 3 + k):
+                ev = stage(i, after=ev)
+            cur.wait_event(ev[0]); cur.wait_event(ev[1])
+            t1.record(cur)
+            ev = stage(3 + k, fwd=False, after=ev)         # drain: the last tile smoothed
+            cur.wait_event(ev[1])
+            torch.cuda.synchronize(D.dev)
+            return t0.elapsed_time(t1)
+
+        run(1)
+        D.barrier()
+        ms = D.reduce(run(args.steps), "max")
+        D.barrier()
+        return {"value": D.world * tile_steps * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
+                "back_to_back_ms_per_step": back_to_back_ms, "gain": back_to_back_ms / (ms / args.steps),
+                "filter_sms": part.filter_sms, "smoother_sms": part.smoother_sms, "steps": args.steps,
+                "schedule": "forward(tile i+1) on the filter SMs beside backward(tile i) on the smoother SMs (CUDA green contexts); "
+                            "the same two kernels, bit-identical results (tests/test_gpu_parity.py::test_partitioned_schedule_is_bit_identical); "
+                            "BatchedUKF.run_many(partition=SmPartition(...))",
+                "gpu_launches": 2 * args.steps}
+    except Exception as exc:   # an extra measurement must not take the bench line with it
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+    finally:
+        del res2
+        if part is not None:
+            try:
+                torch.cuda.synchronize(D.dev)
+                part.close()
+            except Exception:
+                pass
 
 
 def base_line(args, cfg, value, world, ms_per_step, tile_tracks):
@@ -911,6 +993,8 @@ def main():
     ap.add_argument("--state-budget", type=float, default=4.0e8, help="stored states per ragged tile (config c4)")
     ap.add_argument("--full-job", action="store_true", help="c4: run every tile of this rank's share, not a stratified K-tile subset")
     ap.add_argument("--no-job", action="store_true", help="c3/c5: skip the whole-job pass")
+    ap.add_argument("--no-partitioned", action="store_true", help="c5: skip the SM-partitioned (green context) schedule")
+    ap.add_argument("--smoother-sms", type=int, default=48, help="SMs of the smoother's partition in the partitioned schedule")
     ap.add_argument("--in-place", action="store_true", help="smooth in place (halves the state memory)")
     ap.add_argument("--full-cov", action="store_true", help="store full 4x4 covariances (default: the 10 unique entries)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

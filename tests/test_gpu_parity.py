@@ -589,6 +589,46 @@ def test_fused_pass_is_bit_identical_to_separate_passes(gating, packed, cuda, na
         ukf.fused(tiles[0], again, tiles[0], again)
 
 
+@pytest.mark.parametrize("gating", [False, True])
+def test_partitioned_schedule_is_bit_identical(gating, cuda, native_lib):
+    """run_many(partition=SmPartition(...)): tile i+1 filtered on one set of SMs while tile i is smoothed on the
+    rest (green contexts).  The same two kernels run, so every state must equal the two-launches-per-tile run bit for
+    bit - also when only two result sets alternate over five tiles (a set is refilled only after its smoother pass)."""
+    import torch
+
+    from ship_track_estimators_b200.batch import BatchedUKF, TrackBatch
+    from ship_track_estimators_b200.partition import SmPartition
+    from ship_track_estimators_b200.synthetic import make_tracks
+
+    R = np.diag([0.05, 0.05, 0.0, 0.0]) if gating else R_POS
+    ukf = BatchedUKF(H_POS, Q_DEF, R, P_DEF, gating=gating, packed_cov=True)
+    kw = dict(outlier_frac=0.05, dts_choices=(1, 2, 3)) if gating else {}   # uniform lengths: every stored state is owned by its track
+    tiles = [TrackBatch.from_synthetic(make_tracks(2048, 120, seed=80 + i, device="cpu", **kw), substeps=2 if gating else 1,
+                                       need_rows=ukf.model.rows_needed()).to(cuda) for i in range(5)]
+    ref = [ukf.run(b) for b in tiles]
+    torch.cuda.synchronize()
+    with SmPartition(cuda, smoother_sms=48) as part:
+        assert part.filter_sms + part.smoother_sms == part.total_sms and part.smoother_sms >= 48
+        got = [ukf.allocate(b) for b in tiles]
+        ukf.run_many(tiles, got, partition=part)
+        torch.cuda.synchronize()
+        for r, g in zip(ref, got):
+            for name in ("mean_f", "cov_f", "mean_s", "cov_s", "status", "n_updates"):
+                assert torch.equal(getattr(r, name), getattr(g, name)), name
+        # two alternating result sets, each tile's smoothed states copied out (in stream order) before its set is reused
+        sets = [ukf.allocate(tiles[0]), ukf.allocate(tiles[0])]
+        kept = []
+        for lo in range(0, 5, 2):
+            chunk = tiles[lo:lo + 2]
+            ukf.run_many(chunk, sets[:len(chunk)], partition=part)
+            kept += [sets[j].mean_s.clone() for j in range(len(chunk))]
+        torch.cuda.synchronize()
+        for r, k in zip(ref, kept):
+            assert torch.equal(r.mean_s, k)
+        with pytest.raises(ValueError, match="different result sets"):
+            ukf.run_many(tiles[:2], [sets[0], sets[0]], partition=part)
+
+
 def test_long_tracks_against_oracle(cuda, native_lib):
     """Track lengths of the modern-ship data (thousands of fixes, BASELINE config 2): a 3000-step
     track against the oracle, and 64 tracks of 10 000 steps for finiteness / determinism."""
