@@ -638,7 +638,7 @@ def run_partitioned(args, D, ukf, tiles, res, back_to_back_ms, tile_steps):
         free, _ = torch.cuda.mem_get_info(D.dev)
         need = sum(t.numel() * t.element_size() for t in vars(res).values() if isinstance(t, torch.Tensor))
         if free < 1.1 * need:
-            return {"unavailable": f"a second result set needs {need / 1e9:.0f} GB, {free / 1e9:.0f} GB free"}
+            raise MemoryError(f"a second result set needs {need / 1e9:.0f} GB, {free / 1e9:.0f} GB free")
         part = SmPartition(D.dev, smoother_sms=args.smoother_sms)
         res2 = ukf.allocate(tiles[0], smoother=True, in_place=args.in_place)
         sets = [res, res2]
@@ -679,18 +679,9 @@ def run_partitioned(args, D, ukf, tiles, res, back_to_back_ms, tile_steps):
             return t0.elapsed_time(t1)
 
         run(1)
-        D.barrier()
-        ms = D.reduce(run(args.steps), "max")
-        D.barrier()
-        return {"value": D.world * tile_steps * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
-                "back_to_back_ms_per_step": back_to_back_ms, "gain": back_to_back_ms / (ms / args.steps),
-                "filter_sms": part.filter_sms, "smoother_sms": part.smoother_sms, "steps": args.steps,
-                "schedule": "forward(tile i+1) on the filter SMs beside backward(tile i) on the smoother SMs (CUDA green contexts); "
-                            "the same two kernels, bit-identical results (tests/test_gpu_parity.py::test_partitioned_schedule_is_bit_identical); "
-                            "BatchedUKF.run_many(partition=SmPartition(...))",
-                "gpu_launches": 2 * args.steps}
+        local_ms, info = run(args.steps), {"filter_sms": part.filter_sms, "smoother_sms": part.smoother_sms}
     except Exception as exc:   # an extra measurement must not take the bench line with it
-        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+        local_ms, info = None, {"unavailable": f"{type(exc).__name__}: {exc}"}
     finally:
         del res2
         if part is not None:
@@ -699,6 +690,21 @@ def run_partitioned(args, D, ukf, tiles, res, back_to_back_ms, tile_steps):
                 part.close()
             except Exception:
                 pass
+    # the collectives are unconditional: a rank that could not measure must not leave the others waiting
+    n_ok = D.reduce(0.0 if local_ms is None else 1.0, "sum")
+    ms = D.reduce(local_ms or 0.0, "max")
+    if n_ok < D.world:
+        return info if "unavailable" in info else {"unavailable": "another rank could not measure it"}
+    return {**_partitioned_line(D, tile_steps, args.steps, ms, back_to_back_ms), **info}
+
+
+def _partitioned_line(D, tile_steps, steps, ms, back_to_back_ms):
+    return {"value": D.world * tile_steps * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "back_to_back_ms_per_step": back_to_back_ms, "gain": back_to_back_ms / (ms / steps), "steps": steps,
+            "schedule": "forward(tile i+1) on the filter SMs beside backward(tile i) on the smoother SMs (CUDA green contexts); "
+                        "the same two kernels, bit-identical results (tests/test_gpu_parity.py::test_partitioned_schedule_is_bit_identical); "
+                        "BatchedUKF.run_many(partition=SmPartition(...))",
+            "gpu_launches": 2 * steps}
 
 
 def base_line(args, cfg, value, world, ms_per_step, tile_tracks):
